@@ -1,0 +1,155 @@
+/*
+ * radnerf_b200.h -- C ABI of libradnerf_b200.so: RAD-NeRF's per-ray rendering hot path on B200 (sm_100a).
+ *
+ * Drop-in boundary.  Every entry point below replaces one function of the reference's four pybind11
+ * torch extensions (the `_backend.<fn>` calls made by raymarching/raymarching.py, gridencoder/grid.py,
+ * freqencoder/freq.py, shencoder/sphere_harmonics.py).  The reference passes at::Tensor; here every
+ * tensor is a raw DEVICE pointer plus extents, and the CUDA stream is explicit (the reference launches
+ * on the legacy default stream).  No torch types cross this boundary.
+ *
+ * Conventions
+ *   - return value: 0 = ok, <0 = argument error (RN_E_*), >0 = cudaError_t of the launch.
+ *     rn_last_error_string() returns a thread-local, human-readable description of the last failure.
+ *   - ownership: the CALLER allocates every output (as the reference's Python wrappers do); kernels
+ *     never allocate.  In-place semantics are the reference's (composite_rays, packbits, counter).
+ *   - all pointers are device pointers on the current device; `stream` is a cudaStream_t (0 = legacy).
+ *   - dtype: RN_F32 (0) or RN_F16 (1) selects the table/feature arithmetic of the grid encoder
+ *     (reference: AT_DISPATCH_FLOATING_TYPES_AND_HALF on embeddings, gridencoder.cu:466).
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef RADNERF_B200_H
+#define RADNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RN_F32 0
+#define RN_F16 1
+
+#define RN_OK 0
+#define RN_E_BADARG (-1)     /* null pointer / zero extent where not allowed */
+#define RN_E_UNSUPPORTED (-2) /* D, C, degree ... outside the supported template set */
+
+/* output layout of the grid encoder */
+#define RN_LAYOUT_LBC 0 /* [L, B, C]   -- what the reference kernel writes (gridencoder.cu:108)           */
+#define RN_LAYOUT_BLC 1 /* [B, L*C]    -- what GridEncoder.forward returns after its permute (grid.py:57) */
+
+const char* rn_last_error_string(void);
+/* library/ABI version, bumped on any signature change */
+int rn_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t rn_launch_count(void);
+
+/* ------------------------------------------------------------------ gridencoder ------------------- */
+
+/* replaces grid_encode_forward (gridencoder/src/gridencoder.h:12, gridencoder.cu:447-470; kernel_grid :87-244).
+ * inputs [B,D] f32 in [0,1]; embeddings [rows,C] dtype; offsets [L+1] i32; outputs dtype, layout as given;
+ * dy_dx (nullable) [B, L*D*C] dtype.  D in {2,3,4,5}, C in {1,2,4,8}.  gridtype 0 = hash, 1 = tiled;
+ * interp 0 = linear, 1 = smoothstep. */
+int rn_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs,
+                           uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                           void* dy_dx, uint32_t gridtype, uint32_t align_corners, uint32_t interp,
+                           uint32_t dtype, uint32_t out_layout, void* stream);
+
+/* replaces grid_encode_backward (gridencoder.h:13, gridencoder.cu:472-502; kernel_grid_backward :247-339,
+ * kernel_input_backward :342-368).
+ * grad: dtype, layout `grad_layout` (RN_LAYOUT_LBC as the reference passes it after grid.py:75, or
+ * RN_LAYOUT_BLC straight from autograd).  grad_embeddings [rows,C]: accumulated INTO (caller pre-zeroes,
+ * grid.py:77), element type `grad_emb_dtype` (RN_F32 accumulates in fp32 -- the product default -- or RN_F16
+ * for the reference's half2 atomics).  dy_dx/grad_inputs nullable together; grad_inputs [B,D] dtype. */
+int rn_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,
+                            void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                            uint32_t H, const void* dy_dx, void* grad_inputs, uint32_t gridtype,
+                            uint32_t align_corners, uint32_t interp, uint32_t dtype, uint32_t grad_layout,
+                            uint32_t grad_emb_dtype, void* stream);
+
+/* replaces grad_total_variation (gridencoder.h:15, gridencoder.cu:505-644).  inputs [B,D] dtype in [0,1];
+ * grad [rows,C] dtype accumulated into. */
+int rn_grad_total_variation(const void* inputs, const void* embeddings, void* grad, const int32_t* offsets,
+                            float weight, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                            uint32_t gridtype, uint32_t align_corners, uint32_t dtype, void* stream);
+
+/* helper (no reference counterpart): per-level `scale = exp2f(l*S)*H - 1` and `resolution = ceil(scale)+1`
+ * exactly as the device computes them (gridencoder.cu:138-139); lets a CPU checker pin its level geometry. */
+int rn_grid_level_geometry(float S, uint32_t H, uint32_t L, float* scales_out, uint32_t* resolutions_out,
+                           void* stream);
+
+/* ------------------------------------------------------------------ raymarching: utilities -------- */
+
+/* replaces near_far_from_aabb (raymarching.h:7, raymarching.cu:91-156). rays_o/d [N,3], aabb [6], nears/fars [N] */
+int rn_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                          float min_near, float* nears, float* fars, void* stream);
+/* replaces sph_from_ray (raymarching.h:8, raymarching.cu:162-209). coords [N,2] */
+int rn_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                    void* stream);
+/* replaces morton3D (raymarching.h:9, raymarching.cu:214-232). coords [N,3] i32 -> indices [N] i32 */
+int rn_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream);
+/* replaces morton3D_invert (raymarching.h:10, raymarching.cu:237-260). indices [N] -> coords [N,3] */
+int rn_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream);
+/* replaces packbits (raymarching.h:11, raymarching.cu:267-300). grid [8N] f32 -> bitfield [N] u8, LSB first */
+int rn_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream);
+/* replaces morton3D_dilation (raymarching.h:12, raymarching.cu:304-341). grid [C,H^3] f32 Morton-indexed */
+int rn_morton3D_dilation(const float* grid, uint32_t C, uint32_t H, float* grid_dilation, void* stream);
+
+/* ------------------------------------------------------------------ raymarching: training --------- */
+
+/* replaces march_rays_train (raymarching.h:14, raymarching.cu:352-528).
+ * xyzs/dirs [M,3], deltas [M,2] (caller pre-zeroes, raymarching.py:231-233), rays [N,3] i32 (id, offset, count),
+ * counter [2] i32 (points, rays) accumulated atomically, noises [N]. */
+int rn_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                        uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                        const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays,
+                        int32_t* counter, const float* noises, void* stream);
+/* replaces march_rays_train_backward (raymarching.h:15, raymarching.cu:535-593); grads accumulated into */
+int rn_march_rays_train_backward(const float* grad_xyzs, const float* grad_dirs, const int32_t* rays,
+                                 const float* deltas, uint32_t N, uint32_t M, float* grad_rays_o,
+                                 float* grad_rays_d, void* stream);
+/* replaces composite_rays_train_forward (raymarching.h:16, raymarching.cu:603-698) */
+int rn_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* ambient,
+                                    const float* deltas, const int32_t* rays, uint32_t M, uint32_t N,
+                                    float T_thresh, float* weights_sum, float* ambient_sum, float* depth,
+                                    float* image, void* stream);
+/* replaces composite_rays_train_backward (raymarching.h:17, raymarching.cu:711-820) */
+int rn_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_ambient_sum,
+                                     const float* grad_image, const float* sigmas, const float* rgbs,
+                                     const float* ambient, const float* deltas, const int32_t* rays,
+                                     const float* weights_sum, const float* ambient_sum, const float* image,
+                                     uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
+                                     float* grad_rgbs, float* grad_ambient, void* stream);
+
+/* ------------------------------------------------------------------ raymarching: inference -------- */
+
+/* replaces march_rays (raymarching.h:19, raymarching.cu:827-939). Slot layout n*n_step+k, caller pre-zeroes. */
+int rn_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                  const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                  uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars,
+                  float* xyzs, float* dirs, float* deltas, const float* noises, void* stream);
+/* replaces composite_rays (raymarching.h:20, raymarching.cu:942-1038); in-place on weights_sum/depth/image,
+ * rays_alive[n] = -1 marks a terminated ray, rays_t updated otherwise. */
+int rn_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                      const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                      float* depth, float* image, void* stream);
+
+/* ------------------------------------------------------------------ freqencoder / shencoder ------- */
+
+/* replaces freq_encode_forward (freqencoder.h:7, freqencoder.cu:30-58,96-110). outputs [B,C], C = D + 2*D*deg */
+int rn_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C, float* outputs,
+                           void* stream);
+/* replaces freq_encode_backward (freqencoder.h:9, freqencoder.cu:63-94,113-128). grad_inputs [B,D] written */
+int rn_freq_encode_backward(const float* grad, const float* outputs, uint32_t B, uint32_t D, uint32_t deg,
+                            uint32_t C, float* grad_inputs, void* stream);
+/* replaces sh_encode_forward (shencoder.h:8, shencoder.cu:27-356,400-417). inputs [B,3] f32, outputs [B,deg^2],
+ * dy_dx nullable [B,3*deg^2]; degree 1..8 */
+int rn_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D, uint32_t degree,
+                         float* dy_dx, void* stream);
+/* replaces sh_encode_backward (shencoder.h:9, shencoder.cu:358-383,419-439). grad_inputs [B,3] accumulated into */
+int rn_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t degree,
+                          const float* dy_dx, float* grad_inputs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADNERF_B200_H */

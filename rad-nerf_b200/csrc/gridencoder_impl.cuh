@@ -1,0 +1,562 @@
+// gridencoder.cu -- multi-resolution hash / tiled grid encoding for sm_100a.
+//
+// Replaces the reference's gridencoder extension (gridencoder/src/gridencoder.cu: kernel_grid :87-244,
+// kernel_grid_backward :247-339, kernel_input_backward :342-368, kernel_grad_tv :505-609) behind the C ABI in
+// include/radnerf_b200.h.  Not a port: the work decomposition is different.
+//
+//   reference : one thread per (sample, level), grid.y = level, scalar 2-byte loads, [L,B,C] output that the
+//               Python wrapper permutes/copies to [B,L*C]; backward = one atomic per (sample, level, corner, pair).
+//   here      : one thread per SAMPLE walking all levels in groups of 4 (32 independent gathers in flight per
+//               thread, coordinates read once instead of L times).  All lanes of a warp sit on the same level at
+//               the same time ("level-major"), so the lanes' gathers -- neighbouring samples of neighbouring
+//               rays -- fall into the same few 128-byte lines.  One vector load per corner row (half2 / float2 /
+//               float4 ...), per-level geometry computed once per CTA into shared memory, [B,L*C] rows written
+//               directly with 16-byte stores (no permute pass).  Backward accumulates in fp32 with vector
+//               red.global.add (v2/v4.f32) and fuses the input-gradient reduction.
+//
+// Numerics follow the reference exactly where it is deterministic: fp32 coordinates, FMA placement as nvcc
+// contracts the reference expressions, and in fp16 mode the per-corner rounding of c10::Half arithmetic
+// (product rounded to half, then a half add; gridencoder.cu:163,186) so forward results are bit-identical.
+#pragma once
+#include "common.cuh"
+
+namespace rn {
+namespace grid {
+
+constexpr int MAX_LEVELS = 64;
+constexpr int LG = 4;  // levels per unrolled group
+
+struct LevelMeta {
+    float scale;          // exp2f(l*S)*H - 1                      (gridencoder.cu:138)
+    uint32_t resolution;  // ceil(scale) + 1                       (gridencoder.cu:139)
+    uint32_t offset;      // first row of the level
+    uint32_t size;        // rows in the level ("hashmap_size", gridencoder.cu:137)
+    uint32_t stride[5];   // per-dimension stride; 0 once the running stride exceeded `size` (the :72 early exit)
+    uint32_t mode;        // bit0: index needs hashing; bits 1-2: 0 = no wrap needed, 1 = pow2 mask, 2 = generic %
+};
+
+__device__ __forceinline__ void make_level_meta(LevelMeta& m, uint32_t level, const int32_t* offsets, float S,
+                                                uint32_t H, uint32_t D, uint32_t gridtype, bool align_corners) {
+    const uint32_t off = (uint32_t)offsets[level];
+    const uint32_t size = (uint32_t)offsets[level + 1] - off;
+    const float scale = exp2f(level * S) * H - 1.0f;
+    const uint32_t res = (uint32_t)ceilf(scale) + 1;
+    m.scale = scale;
+    m.resolution = res;
+    m.offset = off;
+    m.size = size;
+    const uint32_t fac = align_corners ? res : res + 1;
+    uint32_t stride = 1;
+    bool stopped = false;
+    uint64_t span = 1;  // number of distinct lattice points if every dimension were indexed
+    for (uint32_t d = 0; d < 5; ++d) {
+        if (d < D && !stopped && stride <= size) {
+            m.stride[d] = stride;
+            stride *= fac;  // uint32 wrap exactly as the reference
+        } else {
+            if (d < D) stopped = true;
+            m.stride[d] = 0;
+        }
+        if (d < D) span = (span > (1ull << 40)) ? span : span * (uint64_t)(res + 1);
+    }
+    const bool overflow = stride > size;  // value of `stride > hashmap_size` after the loop (gridencoder.cu:79)
+    uint32_t mode = 0;
+    if (gridtype == 0 && overflow) mode |= 1u;
+    uint32_t wrap;
+    if (!(mode & 1u) && !align_corners && !stopped && span <= (uint64_t)size) wrap = 0;  // dense: index < size
+    else if ((size & (size - 1)) == 0) wrap = 1;
+    else wrap = 2;
+    m.mode = mode | (wrap << 1);
+}
+
+// spatial hash of the reference (gridencoder.cu:50-63): xor of coordinate * prime.
+template <int D>
+__device__ __forceinline__ uint32_t lattice_hash(const uint32_t (&p)[D]) {
+    constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) r ^= p[i] * primes[i];
+    return r;
+}
+
+__device__ __forceinline__ uint32_t wrap_index(uint32_t idx, const LevelMeta& m) {
+    const uint32_t w = m.mode >> 1;
+    if (w == 0) return idx;
+    if (w == 1) return idx & (m.size - 1);
+    return idx % m.size;
+}
+
+template <int D>
+__device__ __forceinline__ uint32_t corner_row(const LevelMeta& m, const uint32_t (&pg)[D], uint32_t corner) {
+    uint32_t p[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) p[d] = pg[d] + ((corner >> d) & 1u);
+    uint32_t idx;
+    if (m.mode & 1u) {
+        idx = lattice_hash<D>(p);
+    } else {
+        idx = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) idx += p[d] * m.stride[d];
+    }
+    return wrap_index(idx, m);
+}
+
+// ---- feature-row access: one vector load per corner ---------------------------------------------------
+template <typename T, int C>
+struct Row {
+    T v[C];
+};
+
+template <typename T, int C>
+__device__ __forceinline__ Row<T, C> load_row(const T* __restrict__ p) {
+    Row<T, C> r;
+    constexpr int BYTES = C * sizeof(T);
+    if constexpr (BYTES == 2) {
+        *reinterpret_cast<unsigned short*>(r.v) = __ldg(reinterpret_cast<const unsigned short*>(p));
+    } else if constexpr (BYTES == 4) {
+        *reinterpret_cast<unsigned int*>(r.v) = __ldg(reinterpret_cast<const unsigned int*>(p));
+    } else if constexpr (BYTES == 8) {
+        *reinterpret_cast<uint2*>(r.v) = __ldg(reinterpret_cast<const uint2*>(p));
+    } else if constexpr (BYTES == 16) {
+        *reinterpret_cast<uint4*>(r.v) = __ldg(reinterpret_cast<const uint4*>(p));
+    } else {  // 32 bytes
+        reinterpret_cast<uint4*>(r.v)[0] = __ldg(reinterpret_cast<const uint4*>(p));
+        reinterpret_cast<uint4*>(r.v)[1] = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    }
+    return r;
+}
+
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half_rn(x); }
+
+// acc += w * g with the reference's rounding: fp32 -> one FMA; fp16 -> round(w*g) to half, then half add.
+__device__ __forceinline__ void accum(float& acc, float w, float g) { acc = __fmaf_rn(w, g, acc); }
+__device__ __forceinline__ void accum(__half& acc, float w, __half g) {
+    acc = __hadd(acc, __float2half_rn(__fmul_rn(w, __half2float(g))));
+}
+// dy_dx accumulation: acc += w * (gr - gl) * pd           (gridencoder.cu:234)
+__device__ __forceinline__ void accum_diff(float& acc, float w, float gr, float gl, float pd) {
+    acc = __fmaf_rn(__fmul_rn(w, __fsub_rn(gr, gl)), pd, acc);
+}
+__device__ __forceinline__ void accum_diff(__half& acc, float w, __half gr, __half gl, float pd) {
+    const __half diff = __hsub(gr, gl);
+    acc = __hadd(acc, __float2half_rn(__fmul_rn(__fmul_rn(w, __half2float(diff)), pd)));
+}
+
+__device__ __forceinline__ float smoothstep_f(float v) { return v * v * (3.0f - 2.0f * v); }
+__device__ __forceinline__ float smoothstep_df(float v) { return 6 * v * (1.0f - v); }
+
+template <int D>
+struct Cell {
+    float frac[D];   // interpolation weight along d (after smoothstep if enabled)
+    float deriv[D];  // d(weight)/d(pos)
+    uint32_t pg[D];  // integer lattice coordinate
+};
+
+template <int D>
+__device__ __forceinline__ Cell<D> locate(const float (&x)[D], const LevelMeta& m, bool align_corners, uint32_t interp) {
+    Cell<D> c;
+    const float shift = align_corners ? 0.0f : 0.5f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        float pos = __fmaf_rn(x[d], m.scale, shift);
+        const float fl = floorf(pos);
+        c.pg[d] = (uint32_t)fl;
+        pos -= (float)c.pg[d];
+        if (interp == 1) {
+            c.deriv[d] = smoothstep_df(pos);
+            c.frac[d] = smoothstep_f(pos);
+        } else {
+            c.deriv[d] = 1.0f;
+            c.frac[d] = pos;
+        }
+    }
+    return c;
+}
+
+template <int D>
+__device__ __forceinline__ float corner_weight(const Cell<D>& c, uint32_t corner) {
+    float w = 1.0f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) w *= ((corner >> d) & 1u) ? c.frac[d] : (1.0f - c.frac[d]);
+    return w;
+}
+
+// ======================================================================================================
+// forward
+// ======================================================================================================
+template <typename T, int D, int C, bool VEC_OUT>
+__global__ void __launch_bounds__(256)
+grid_forward_kernel(const float* __restrict__ inputs, const T* __restrict__ table, const int32_t* __restrict__ offsets,
+                    T* __restrict__ outputs, T* __restrict__ dy_dx, uint32_t B, uint32_t L, float S, uint32_t H,
+                    uint32_t gridtype, uint32_t align_corners, uint32_t interp, uint32_t layout) {
+    __shared__ LevelMeta meta[MAX_LEVELS];
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x)
+        make_level_meta(meta[l], l, offsets, S, H, D, gridtype, align_corners != 0);
+    __syncthreads();
+
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        float x[D];
+        bool oob = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            x[d] = __ldg(inputs + (size_t)b * D + d);
+            if (x[d] < 0 || x[d] > 1) oob = true;
+        }
+
+        for (uint32_t l0 = 0; l0 < L; l0 += LG) {
+            union alignas(16) Group {
+                T v[LG][C];
+                uint4 q[(LG * C * sizeof(T) + 15) / 16];
+                uint2 d[(LG * C * sizeof(T) + 7) / 8];
+            } grp;
+            T (&res)[LG][C] = grp.v;
+#pragma unroll
+            for (int j = 0; j < LG; ++j) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) res[j][c] = from_f<T>(0.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < LG; ++j) {
+                const uint32_t l = l0 + j;
+                if (l >= L) break;
+                if (oob) {
+                    if (dy_dx) {
+                        T* g = dy_dx + ((size_t)b * L + l) * D * C;
+#pragma unroll
+                        for (int k = 0; k < D * C; ++k) g[k] = from_f<T>(0.0f);
+                    }
+                    continue;
+                }
+                const LevelMeta m = meta[l];
+                const T* __restrict__ tbl = table + (size_t)m.offset * C;
+                const Cell<D> cell = locate<D>(x, m, align_corners != 0, interp);
+
+                Row<T, C> rows[1 << D];
+#pragma unroll
+                for (uint32_t k = 0; k < (1u << D); ++k)
+                    rows[k] = load_row<T, C>(tbl + (size_t)corner_row<D>(m, cell.pg, k) * C);
+#pragma unroll
+                for (uint32_t k = 0; k < (1u << D); ++k) {
+                    const float w = corner_weight<D>(cell, k);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) accum(res[j][c], w, rows[k].v[c]);
+                }
+
+                if (dy_dx) {
+                    // analytic d(out)/d(x): for each axis, difference of the two faces (gridencoder.cu:200-243).
+                    // The 2^D rows are already in registers: corner k with bit gd set / cleared are the faces.
+                    T* g = dy_dx + ((size_t)b * L + l) * D * C;
+#pragma unroll
+                    for (int gd = 0; gd < D; ++gd) {
+                        T acc[C];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) acc[c] = from_f<T>(0.0f);
+#pragma unroll
+                        for (uint32_t idx = 0; idx < (1u << (D - 1)); ++idx) {
+                            float w = m.scale;
+                            uint32_t corner = 0;
+#pragma unroll
+                            for (int nd = 0; nd < D - 1; ++nd) {
+                                const int d = (nd >= gd) ? nd + 1 : nd;
+                                if ((idx >> nd) & 1u) {
+                                    w *= cell.frac[d];
+                                    corner |= 1u << d;
+                                } else {
+                                    w *= 1.0f - cell.frac[d];
+                                }
+                            }
+#pragma unroll
+                            for (int c = 0; c < C; ++c)
+                                accum_diff(acc[c], w, rows[corner | (1u << gd)].v[c], rows[corner].v[c], cell.deriv[gd]);
+                        }
+#pragma unroll
+                        for (int c = 0; c < C; ++c) g[gd * C + c] = acc[c];
+                    }
+                }
+            }
+
+            // ---- write the group ----
+            if (layout == RN_LAYOUT_BLC) {
+                T* o = outputs + (size_t)b * L * C + (size_t)l0 * C;
+                if (VEC_OUT && l0 + LG <= L) {
+                    constexpr int BYTES = LG * C * sizeof(T);
+                    if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+                        for (int q = 0; q < BYTES / 16; ++q) reinterpret_cast<uint4*>(o)[q] = grp.q[q];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < BYTES / 8; ++q) reinterpret_cast<uint2*>(o)[q] = grp.d[q];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < LG; ++j) {
+                        if (l0 + j < L) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c) o[j * C + c] = res[j][c];
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < LG; ++j) {
+                    if (l0 + j < L) {
+                        T* o = outputs + ((size_t)(l0 + j) * B + b) * C;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) o[c] = res[j][c];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ======================================================================================================
+// backward: table gradient (fp32 or fp16 accumulate target) + fused input gradient
+// ======================================================================================================
+__device__ __forceinline__ void red_add(float* p, float a) { atomicAdd(p, a); }
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add2(__half* p, float a, float b) {
+    const __half2 v = __floats2half2_rn(a, b);
+    atomicAdd(reinterpret_cast<__half2*>(p), v);
+}
+
+template <typename G, int C>
+__device__ __forceinline__ void scatter_row(G* __restrict__ p, const float (&v)[C]) {
+    if constexpr (sizeof(G) == 4) {
+        if constexpr (C == 1) red_add((float*)p, v[0]);
+        else if constexpr (C == 2) red_add2((float*)p, v[0], v[1]);
+        else {
+#pragma unroll
+            for (int c = 0; c < C; c += 4) red_add4((float*)p + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
+        }
+    } else {
+        if constexpr (C == 1) atomicAdd((__half*)p, __float2half_rn(v[0]));
+        else {
+#pragma unroll
+            for (int c = 0; c < C; c += 2) red_add2((__half*)p + c, v[c], v[c + 1]);
+        }
+    }
+}
+
+template <typename T, typename G, int D, int C>
+__global__ void __launch_bounds__(256)
+grid_backward_kernel(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
+                     G* __restrict__ grad_table, const T* __restrict__ dy_dx, T* __restrict__ grad_inputs, uint32_t B,
+                     uint32_t L, float S, uint32_t H, uint32_t gridtype, uint32_t align_corners, uint32_t interp,
+                     uint32_t layout) {
+    __shared__ LevelMeta meta[MAX_LEVELS];
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x)
+        make_level_meta(meta[l], l, offsets, S, H, D, gridtype, align_corners != 0);
+    __syncthreads();
+
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        float x[D];
+        bool oob = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            x[d] = __ldg(inputs + (size_t)b * D + d);
+            if (x[d] < 0 || x[d] > 1) oob = true;
+        }
+        float gin[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) gin[d] = 0.0f;
+
+        for (uint32_t l = 0; l < L; ++l) {
+            const T* gp = (layout == RN_LAYOUT_BLC) ? grad + (size_t)b * L * C + (size_t)l * C
+                                                    : grad + ((size_t)l * B + b) * C;
+            const Row<T, C> g = load_row<T, C>(gp);
+            if (dy_dx) {
+                // grad_inputs[b,d] = sum_{l,c} grad[l,b,c] * dy_dx[b,l,d,c]     (gridencoder.cu:342-368)
+                const T* dp = dy_dx + ((size_t)b * L + l) * D * C;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) gin[d] = __fmaf_rn(to_f(g.v[c]), to_f(__ldg(dp + d * C + c)), gin[d]);
+                }
+            }
+            if (oob) continue;  // reference returns before touching the table (gridencoder.cu:275-280)
+            const LevelMeta m = meta[l];
+            G* __restrict__ gt = grad_table + (size_t)m.offset * C;
+            const Cell<D> cell = locate<D>(x, m, align_corners != 0, interp);
+            float gf[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) gf[c] = to_f(g.v[c]);
+#pragma unroll
+            for (uint32_t k = 0; k < (1u << D); ++k) {
+                const float w = corner_weight<D>(cell, k);
+                float v[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) v[c] = w * gf[c];
+                scatter_row<G, C>(gt + (size_t)corner_row<D>(m, cell.pg, k) * C, v);
+            }
+        }
+        if (dy_dx && grad_inputs) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) grad_inputs[(size_t)b * D + d] = from_f<T>(gin[d]);
+        }
+    }
+}
+
+// ======================================================================================================
+// total-variation gradient (API parity; RAD-NeRF's trainer never calls it)   (gridencoder.cu:505-609)
+// ======================================================================================================
+template <typename T, int D, int C>
+__global__ void __launch_bounds__(256)
+grid_tv_kernel(const T* __restrict__ inputs, const T* __restrict__ table, T* __restrict__ grad,
+               const int32_t* __restrict__ offsets, float weight, uint32_t B, uint32_t L, float S, uint32_t H,
+               uint32_t gridtype, uint32_t align_corners) {
+    __shared__ LevelMeta meta[MAX_LEVELS];
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x)
+        make_level_meta(meta[l], l, offsets, S, H, D, gridtype, align_corners != 0);
+    __syncthreads();
+    const uint32_t level = blockIdx.y;
+    const LevelMeta m = meta[level];
+    const T* __restrict__ tbl = table + (size_t)m.offset * C;
+    T* __restrict__ gt = grad + (size_t)m.offset * C;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        float x[D];
+        bool oob = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            x[d] = to_f(inputs[(size_t)b * D + d]);
+            if (x[d] < 0 || x[d] > 1) oob = true;
+        }
+        if (oob) continue;
+        uint32_t pg[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) pg[d] = (uint32_t)floorf(__fmaf_rn(x[d], m.scale, align_corners ? 0.0f : 0.5f));
+        const uint32_t centre = corner_row<D>(m, pg, 0);
+        const Row<T, C> c0 = load_row<T, C>(tbl + (size_t)centre * C);
+        T sum[C], sq[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) sum[c] = sq[c] = from_f<T>(0.0f);
+        const T w = from_f<T>(weight / (2 * D));
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const uint32_t cur = pg[d];
+            if (cur < m.resolution) {
+                pg[d] = cur + 1;
+                const Row<T, C> n = load_row<T, C>(tbl + (size_t)corner_row<D>(m, pg, 0) * C);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const T dlt = from_f<T>(to_f(c0.v[c]) - to_f(n.v[c]));
+                    sum[c] = from_f<T>(to_f(sum[c]) + to_f(dlt));
+                    sq[c] = from_f<T>(to_f(sq[c]) + to_f(from_f<T>(to_f(dlt) * to_f(dlt))));
+                }
+            }
+            if (cur > 0) {
+                pg[d] = cur - 1;
+                const Row<T, C> n = load_row<T, C>(tbl + (size_t)corner_row<D>(m, pg, 0) * C);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const T dlt = from_f<T>(to_f(c0.v[c]) - to_f(n.v[c]));
+                    sum[c] = from_f<T>(to_f(sum[c]) + to_f(dlt));
+                    sq[c] = from_f<T>(to_f(sq[c]) + to_f(from_f<T>(to_f(dlt) * to_f(dlt))));
+                }
+            }
+            pg[d] = cur;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float ws = to_f(from_f<T>(to_f(w) * to_f(sum[c])));
+            const float v = ws * rsqrtf(to_f(sq[c]) + 1e-9f);
+            if constexpr (sizeof(T) == 4) atomicAdd((float*)gt + (size_t)centre * C + c, v);
+            else atomicAdd((__half*)gt + (size_t)centre * C + c, __float2half_rn(v));
+        }
+    }
+}
+
+static __global__ void level_geometry_kernel(float S, uint32_t H, uint32_t L, float* scales, uint32_t* res) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const float scale = exp2f(l * S) * H - 1.0f;
+    if (scales) scales[l] = scale;
+    if (res) res[l] = (uint32_t)ceilf(scale) + 1;
+}
+
+
+// ---- per-dimension dispatch (one translation unit per D keeps compile times short) -------------------
+struct FwdArgs {
+    const float* inputs; const void* emb; const int32_t* offsets; void* out; void* dy_dx;
+    uint32_t B, C, L; float S; uint32_t H, gridtype, ac, interp, dtype, layout; cudaStream_t st;
+};
+struct BwdArgs {
+    const void* grad; const float* inputs; const int32_t* offsets; void* gt; const void* dy_dx; void* gin;
+    uint32_t B, C, L; float S; uint32_t H, gridtype, ac, interp, dtype, layout, gdtype; cudaStream_t st;
+};
+struct TvArgs {
+    const void* inputs; const void* emb; void* grad; const int32_t* offsets; float weight;
+    uint32_t B, C, L; float S; uint32_t H, gridtype, ac, dtype; cudaStream_t st;
+};
+template <int D> int forward_d(const FwdArgs& a);
+template <int D> int backward_d(const BwdArgs& a);
+template <int D> int tv_d(const TvArgs& a);
+
+template <typename T, int D, int C>
+int launch_forward(const FwdArgs& a) {
+    const uint32_t threads = 256;
+    const uint32_t grid = wave_grid(a.B, threads, 32);
+    const bool vec = a.layout == RN_LAYOUT_BLC && ((uintptr_t)a.out % 16 == 0) && ((a.L * C * sizeof(T)) % 16 == 0);
+    if (vec)
+        grid_forward_kernel<T, D, C, true><<<grid, threads, 0, a.st>>>(a.inputs, (const T*)a.emb, a.offsets, (T*)a.out,
+            (T*)a.dy_dx, a.B, a.L, a.S, a.H, a.gridtype, a.ac, a.interp, a.layout);
+    else
+        grid_forward_kernel<T, D, C, false><<<grid, threads, 0, a.st>>>(a.inputs, (const T*)a.emb, a.offsets, (T*)a.out,
+            (T*)a.dy_dx, a.B, a.L, a.S, a.H, a.gridtype, a.ac, a.interp, a.layout);
+    return finish_launch("rn_grid_encode_forward");
+}
+
+template <typename T, typename G, int D, int C>
+int launch_backward(const BwdArgs& a) {
+    const uint32_t threads = 256;
+    const uint32_t grid = wave_grid(a.B, threads, 32);
+    grid_backward_kernel<T, G, D, C><<<grid, threads, 0, a.st>>>((const T*)a.grad, a.inputs, a.offsets, (G*)a.gt,
+        (const T*)a.dy_dx, (T*)a.gin, a.B, a.L, a.S, a.H, a.gridtype, a.ac, a.interp, a.layout);
+    return finish_launch("rn_grid_encode_backward");
+}
+
+template <typename T, int D, int C>
+int launch_tv(const TvArgs& a) {
+    const uint32_t threads = 256;
+    dim3 grid(wave_grid(a.B, threads, 8), a.L, 1);
+    grid_tv_kernel<T, D, C><<<grid, threads, 0, a.st>>>((const T*)a.inputs, (const T*)a.emb, (T*)a.grad, a.offsets,
+        a.weight, a.B, a.L, a.S, a.H, a.gridtype, a.ac);
+    return finish_launch("rn_grad_total_variation");
+}
+
+#define RN_SWITCH_C(C, EXPR)                               \
+    switch (C) {                                           \
+        case 1: { constexpr int kC = 1; return EXPR; }     \
+        case 2: { constexpr int kC = 2; return EXPR; }     \
+        case 4: { constexpr int kC = 4; return EXPR; }     \
+        case 8: { constexpr int kC = 8; return EXPR; }     \
+        default: return RN_E_UNSUPPORTED;                  \
+    }
+
+#define RN_GRID_DEFINE_D(DD)                                                                              \
+    template <> int forward_d<DD>(const FwdArgs& a) {                                                     \
+        if (a.dtype == RN_F16) { RN_SWITCH_C(a.C, (launch_forward<__half, DD, kC>(a))) }                  \
+        RN_SWITCH_C(a.C, (launch_forward<float, DD, kC>(a)))                                              \
+    }                                                                                                     \
+    template <> int backward_d<DD>(const BwdArgs& a) {                                                    \
+        if (a.dtype == RN_F16 && a.gdtype == RN_F32) { RN_SWITCH_C(a.C, (launch_backward<__half, float, DD, kC>(a))) } \
+        if (a.dtype == RN_F16) { RN_SWITCH_C(a.C, (launch_backward<__half, __half, DD, kC>(a))) }         \
+        RN_SWITCH_C(a.C, (launch_backward<float, float, DD, kC>(a)))                                      \
+    }                                                                                                     \
+    template <> int tv_d<DD>(const TvArgs& a) {                                                           \
+        if (a.dtype == RN_F16) { RN_SWITCH_C(a.C, (launch_tv<__half, DD, kC>(a))) }                       \
+        RN_SWITCH_C(a.C, (launch_tv<float, DD, kC>(a)))                                                   \
+    }
+
+}  // namespace grid
+}  // namespace rn
