@@ -265,9 +265,10 @@ def test_march_and_composite_train(oracle, name):
     xyzs, dirs, deltas = torch.zeros(M, 3, device=DEV), torch.zeros(M, 3, device=DEV), torch.zeros(M, 2, device=DEV)
     rays = torch.empty(N, 3, dtype=torch.int32, device=DEV)
     counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+    t_noise = T(c["noises"])
     L.check(L.lib().rn_march_rays_train(L.ptr(ro), L.ptr(rd), L.ptr(bf), c["bound"], c["dt_gamma"], c["max_steps"], N, c["C"],
                                         c["H"], M, L.ptr(nears), L.ptr(fars), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas),
-                                        L.ptr(rays), L.ptr(counter), L.ptr(T(c["noises"])), L.cur_stream()))
+                                        L.ptr(rays), L.ptr(counter), L.ptr(t_noise), L.cur_stream()))
     ids, counts, kept, cx, cd, cdl = gc.canonical_rays(N_(rays), N_(xyzs), N_(dirs), N_(deltas), M)
     # bit-exact against the reference kernel: ids, per-ray sample counts, every emitted float, the counters
     assert np.array_equal(ids, np.arange(N)) and np.array_equal(counts, g["train_counts"]) and np.array_equal(kept, g["train_kept"])
@@ -308,7 +309,8 @@ def test_march_and_composite_train(oracle, name):
     gxyz = np.random.default_rng(5).standard_normal((Mc, 3)).astype(np.float32)
     gdir = np.random.default_rng(6).standard_normal((Mc, 3)).astype(np.float32)
     go, gd_ = torch.zeros(N, 3, device=DEV), torch.zeros(N, 3, device=DEV)
-    L.check(L.lib().rn_march_rays_train_backward(L.ptr(T(gxyz)), L.ptr(T(gdir)), L.ptr(T(crays)), L.ptr(T(cdl)), N, Mc,
+    t_gxyz, t_gdir, t_crays, t_cdl = T(gxyz), T(gdir), T(crays), T(cdl)  # keep the device buffers alive across the call
+    L.check(L.lib().rn_march_rays_train_backward(L.ptr(t_gxyz), L.ptr(t_gdir), L.ptr(t_crays), L.ptr(t_cdl), N, Mc,
                                                  L.ptr(go), L.ptr(gd_), L.cur_stream()))
     assert maxabs(N_(go), g["mt_go"]) <= 1e-5 * max(1.0, float(np.abs(g["mt_go"]).max()))
     assert maxabs(N_(gd_), g["mt_gd"]) <= 1e-5 * max(1.0, float(np.abs(g["mt_gd"]).max()))
@@ -326,9 +328,10 @@ def test_march_and_composite_inference(oracle, name):
     Mi += 128 - (Mi % 128)
     alive, rays_t = T(c["rays_alive"]), nears.clone()
     xyzs, dirs, deltas = torch.zeros(Mi, 3, device=DEV), torch.zeros(Mi, 3, device=DEV), torch.zeros(Mi, 2, device=DEV)
+    t_noise = T(c["infer_noises"])
     L.check(L.lib().rn_march_rays(na, ns, L.ptr(alive), L.ptr(rays_t), L.ptr(ro), L.ptr(rd), c["bound"], c["dt_gamma"],
                                   c["max_steps"], c["C"], c["H"], L.ptr(bf), L.ptr(nears), L.ptr(fars), L.ptr(xyzs),
-                                  L.ptr(dirs), L.ptr(deltas), L.ptr(T(c["infer_noises"])), L.cur_stream()))
+                                  L.ptr(dirs), L.ptr(deltas), L.ptr(t_noise), L.cur_stream()))
     assert np.array_equal(N_(xyzs), g["inf_xyzs"]) and np.array_equal(N_(dirs), g["inf_dirs"]) and np.array_equal(N_(deltas), g["inf_deltas"])
     ox, od, odl = oracle.march_rays(na, ns, c["rays_alive"], g["nears"], c["rays_o"], c["rays_d"], c["bound"], c["bitfield"],
                                     c["C"], c["H"], g["nears"], g["fars"], 128, c["infer_noises"], c["dt_gamma"], c["max_steps"])
