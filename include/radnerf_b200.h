@@ -149,6 +149,21 @@ int rn_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32
 int rn_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t degree,
                           const float* dy_dx, float* grad_inputs, void* stream);
 
+/* ------------------------------------------------------------------ callers absorbed into the path ---- */
+
+/* replaces the per-frame torch-op chain of get_rays for full frames (nerf/utils.py:248-333):
+ * pixel p = (row j, col i) -> direction ((i+0.5-cx)/fx, (j+0.5-cy)/fy, 1) normalised and rotated by pose[:3,:3],
+ * origin pose[:3,3].  pose: device float[16] row-major cam2world.  pixel_ids (nullable) int32 [n]: the pixels to
+ * generate (row-major ids); NULL = all H*W pixels in order.  rays_o / rays_d [n,3]. */
+int rn_get_rays(const float* pose, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
+                const int32_t* pixel_ids, uint32_t n, float* rays_o, float* rays_d, void* stream);
+
+/* ------------------------------------------------------------------ diagnostics ---------------------- */
+
+/* one 128 x N x K fp16 GEMM tile through the hand-written tcgen05/TMEM path (out = A @ W^T, fp32 accumulate);
+ * A [128,K] fp16 row-major, W [N,K] fp16 row-major.  Validates descriptors/layouts in isolation. */
+int rn_selftest_umma(const void* A, const void* W, float* out, uint32_t K, uint32_t N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,184 @@
+"""Operator bundle over the REFERENCE's own compiled CUDA extensions (oracle/_ref/*.so).  TEST / BENCH INFRASTRUCTURE.
+
+bench.py uses it to time "the reference's kernels, called the way the reference's Python calls them" on the same GPU
+next to our numbers, and GPU tests use it as a live oracle when the .so files are present.  The host-side behaviour of
+the reference wrappers that costs time is reproduced: fresh zero-filled sample buffers per march call
+(raymarching.py:385-393), the per-call fp32->fp16 cast of the table under autocast (grid.py:43-44), the [L,B,C] kernel
+output followed by a permute+reshape copy (grid.py:47,57).  Inference only (no autograd).
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+_REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+_mods = {}
+
+
+def available():
+    return all(os.path.exists(os.path.join(_REF_DIR, n + ".so")) for n in
+               ("_gridencoder", "_raymarching_face", "_freqencoder", "_shencoder"))
+
+
+def backend(name):
+    if name not in _mods:
+        if _REF_DIR not in sys.path:
+            sys.path.insert(0, _REF_DIR)
+        _mods[name] = importlib.import_module(name)
+    return _mods[name]
+
+
+class _RM:
+    @staticmethod
+    def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2):
+        rays_o = rays_o.float().contiguous().view(-1, 3)
+        rays_d = rays_d.float().contiguous().view(-1, 3)
+        N = rays_o.shape[0]
+        nears = torch.empty(N, dtype=rays_o.dtype, device=rays_o.device)
+        fars = torch.empty(N, dtype=rays_o.dtype, device=rays_o.device)
+        backend("_raymarching_face").near_far_from_aabb(rays_o, rays_d, aabb, N, min_near, nears, fars)
+        return nears, fars
+
+    @staticmethod
+    def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, density_bitfield, C, H, near, far, align=-1,
+                   perturb=False, dt_gamma=0, max_steps=1024):
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        M = n_alive * n_step
+        if align > 0:
+            M += align - (M % align)
+        xyzs = torch.zeros(M, 3, dtype=rays_o.dtype, device=rays_o.device)
+        dirs = torch.zeros(M, 3, dtype=rays_o.dtype, device=rays_o.device)
+        deltas = torch.zeros(M, 2, dtype=rays_o.dtype, device=rays_o.device)
+        if perturb:
+            noises = torch.rand(n_alive, dtype=rays_o.dtype, device=rays_o.device)
+        else:
+            noises = torch.zeros(n_alive, dtype=rays_o.dtype, device=rays_o.device)
+        backend("_raymarching_face").march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps,
+                                                C, H, density_bitfield, near, far, xyzs, dirs, deltas, noises)
+        return xyzs, dirs, deltas
+
+    @staticmethod
+    def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2):
+        backend("_raymarching_face").composite_rays(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas.float(), rgbs.float(),
+                                                    deltas, weights_sum, depth, image)
+        return tuple()
+
+    @staticmethod
+    def morton3D(coords):
+        N = coords.shape[0]
+        indices = torch.empty(N, dtype=torch.int32, device=coords.device)
+        backend("_raymarching_face").morton3D(coords.int(), N, indices)
+        return indices
+
+    @staticmethod
+    def packbits(grid, thresh, bitfield=None):
+        grid = grid.float().contiguous()
+        N = grid.shape[0] * grid.shape[1] // 8
+        if bitfield is None:
+            bitfield = torch.empty(N, dtype=torch.uint8, device=grid.device)
+        backend("_raymarching_face").packbits(grid, N, thresh, bitfield)
+        return bitfield
+
+    @staticmethod
+    def morton3D_dilation(grid):
+        grid = grid.float().contiguous()
+        out = torch.empty_like(grid)
+        backend("_raymarching_face").morton3D_dilation(grid, grid.shape[0], int(round(grid.shape[1] ** (1 / 3))), out)
+        return out
+
+
+class GridEncoderRef(nn.Module):
+    def __init__(self, input_dim=3, num_levels=16, level_dim=2, per_level_scale=2, base_resolution=16, log2_hashmap_size=19,
+                 desired_resolution=None, gridtype='hash', align_corners=False, interpolation='linear'):
+        super().__init__()
+        from . import oracle as O
+        offsets, pls = O.grid_offsets(input_dim, num_levels, level_dim, base_resolution, log2_hashmap_size, desired_resolution,
+                                      per_level_scale, align_corners)
+        self.input_dim, self.num_levels, self.level_dim = input_dim, num_levels, level_dim
+        self.per_level_scale, self.base_resolution = pls, base_resolution
+        self.output_dim = num_levels * level_dim
+        self.gridtype_id = {'hash': 0, 'tiled': 1}[gridtype]
+        self.interp_id = {'linear': 0, 'smoothstep': 1}[interpolation]
+        self.align_corners = align_corners
+        self.register_buffer('offsets', torch.from_numpy(offsets))
+        self.embeddings = nn.Parameter(torch.empty(int(offsets[-1]), level_dim).uniform_(-1e-4, 1e-4))
+
+    def forward(self, inputs, bound=1):
+        inputs = (inputs + bound) / (2 * bound)
+        prefix = list(inputs.shape[:-1])
+        inputs = inputs.view(-1, self.input_dim).contiguous()
+        B, D = inputs.shape
+        L, C = self.num_levels, self.level_dim
+        emb = self.embeddings
+        if torch.is_autocast_enabled() and C % 2 == 0:
+            emb = emb.to(torch.half)
+        outputs = torch.empty(L, B, C, device=inputs.device, dtype=emb.dtype)
+        backend("_gridencoder").grid_encode_forward(inputs, emb, self.offsets, outputs, B, D, C, L,
+                                                    float(np.log2(self.per_level_scale)), self.base_resolution, None,
+                                                    self.gridtype_id, self.align_corners, self.interp_id)
+        outputs = outputs.permute(1, 0, 2).reshape(B, L * C)
+        return outputs.view(prefix + [self.output_dim])
+
+
+class FreqEncoderRef(nn.Module):
+    def __init__(self, input_dim=3, degree=4):
+        super().__init__()
+        self.input_dim, self.degree = input_dim, degree
+        self.output_dim = input_dim + input_dim * 2 * degree
+
+    def forward(self, inputs, **kw):
+        prefix = list(inputs.shape[:-1])
+        inputs = inputs.reshape(-1, self.input_dim).float().contiguous()
+        B = inputs.shape[0]
+        out = torch.empty(B, self.output_dim, dtype=inputs.dtype, device=inputs.device)
+        backend("_freqencoder").freq_encode_forward(inputs, B, self.input_dim, self.degree, self.output_dim, out)
+        return out.reshape(prefix + [self.output_dim])
+
+
+class SHEncoderRef(nn.Module):
+    def __init__(self, input_dim=3, degree=4):
+        super().__init__()
+        self.input_dim, self.degree, self.output_dim = input_dim, degree, degree ** 2
+
+    def forward(self, inputs, size=1):
+        inputs = inputs / size
+        prefix = list(inputs.shape[:-1])
+        inputs = inputs.reshape(-1, 3).float().contiguous()
+        B = inputs.shape[0]
+        out = torch.empty(B, self.output_dim, dtype=inputs.dtype, device=inputs.device)
+        backend("_shencoder").sh_encode_forward(inputs, out, B, 3, self.degree, None)
+        return out.reshape(prefix + [self.output_dim])
+
+
+def get_encoder(encoding, input_dim=3, multires=6, degree=4, num_levels=16, level_dim=2, base_resolution=16,
+                log2_hashmap_size=19, desired_resolution=2048, align_corners=False, **kwargs):
+    if encoding == 'frequency':
+        enc = FreqEncoderRef(input_dim=input_dim, degree=multires)
+    elif encoding == 'spherical_harmonics':
+        enc = SHEncoderRef(input_dim=input_dim, degree=degree)
+    elif encoding in ('hashgrid', 'tiledgrid'):
+        enc = GridEncoderRef(input_dim=input_dim, num_levels=num_levels, level_dim=level_dim, base_resolution=base_resolution,
+                             log2_hashmap_size=log2_hashmap_size, desired_resolution=desired_resolution,
+                             gridtype='hash' if encoding == 'hashgrid' else 'tiled', align_corners=align_corners,
+                             interpolation=kwargs.get('interpolation', 'linear'))
+    else:
+        raise NotImplementedError(encoding)
+    return enc, enc.output_dim
+
+
+class _TruncExp:
+    """activation.py:3-17, forward only: exp in fp32"""
+
+    def __call__(self, x):
+        return torch.exp(x.float())
+
+
+class RefOps:
+    def __init__(self):
+        self.rm = _RM
+        self.get_encoder = get_encoder
+        self.trunc_exp = _TruncExp()

@@ -15,6 +15,7 @@
 //   * packbits reads 32 cells per thread with two 128-bit loads... (see kernels) and writes one 32-bit word.
 //   * elementwise utilities use grid-stride loops sized to whole waves of the 148 SMs.
 #include "common.cuh"
+#include "march.cuh"
 #include <float.h>
 
 namespace rn {
@@ -166,95 +167,6 @@ dilation_kernel(const float* __restrict__ grid, uint32_t C, uint32_t H, float* _
 }
 
 }  // namespace
-
-// ------------------------------------------------------------------------------------------------------
-// the marcher: one DDA probe shared by the training and inference kernels (and by frame.cu)
-// ------------------------------------------------------------------------------------------------------
-struct MarchParams {
-    float bound, dt_gamma, dt_min, dt_max;
-    float Hf, halfH, Hm1f, rH, H3f, Cm1f;
-    const uint8_t* __restrict__ grid;
-};
-
-__host__ __device__ inline MarchParams make_march_params(float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
-                                                         uint32_t H, const uint8_t* grid) {
-    MarchParams p;
-    p.bound = bound;
-    p.dt_gamma = dt_gamma;
-    // dt_max = 2*sqrt3 * 2^(C-1) / H ; dt_min = min(dt_max, 2*sqrt3 / max_steps)      (raymarching.cu:386-387)
-    p.dt_max = ((float)(1 << (C - 1)) * 3.4641015529632568359f) / (float)H;
-    const float q = 3.4641015529632568359f / (float)max_steps;
-    p.dt_min = q < p.dt_max ? q : p.dt_max;  // fminf
-    p.Hf = (float)H;
-    p.halfH = 0.5f * (float)H;
-    p.Hm1f = (float)(H - 1);
-    p.rH = 1.0f / (float)H;
-    p.H3f = (float)(H * H * H);
-    p.Cm1f = (float)C - 1.0f;
-    p.grid = grid;
-    return p;
-}
-
-struct Ray {
-    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz, hsx, hsy, hsz;
-    __device__ __forceinline__ void load(const float* __restrict__ o, const float* __restrict__ d) {
-        ox = __ldg(o); oy = __ldg(o + 1); oz = __ldg(o + 2);
-        dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
-        rdx = 1 / dx; rdy = 1 / dy; rdz = 1 / dz;
-        hsx = copysignf(1.0f, dx); hsy = copysignf(1.0f, dy); hsz = copysignf(1.0f, dz);
-    }
-};
-
-__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }
-
-__device__ __forceinline__ float step_size(const MarchParams& p, float t) {
-    return clampf(__fmul_rn(t, p.dt_gamma), p.dt_min, p.dt_max);
-}
-
-__device__ __forceinline__ int cascade_of(float mx, float Cm1f) {
-    int e;
-    frexpf(mx, &e);  // [0,0.5) -> <=-1, [0.5,1) -> 0, [1,2) -> 1 ...        (raymarching.cu:42-54)
-    return (int)fminf(Cm1f, fmaxf(0.0f, (float)e));
-}
-
-// Probe the occupancy grid at parameter t.  Returns true when the cell is occupied (x,y,z,dt are then the sample);
-// otherwise advances t past the current voxel exactly as the reference's skip loop does.
-__device__ __forceinline__ bool march_probe(const MarchParams& p, const Ray& r, float& t, float& x, float& y, float& z,
-                                            float& dt) {
-    x = clampf(__fmaf_rn(r.dx, t, r.ox), -p.bound, p.bound);
-    y = clampf(__fmaf_rn(r.dy, t, r.oy), -p.bound, p.bound);
-    z = clampf(__fmaf_rn(r.dz, t, r.oz), -p.bound, p.bound);
-    dt = step_size(p, t);
-
-    const int lvl_pos = cascade_of(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), p.Cm1f);
-    const int lvl_dt = cascade_of(__fmul_rn(__fmul_rn(dt, p.Hf), 0.5f), p.Cm1f);
-    const int level = max(lvl_pos, lvl_dt);
-
-    const float mip_bound = fminf(__int_as_float((127 + level) << 23), p.bound);
-    const float mip_rbound = 1 / mip_bound;
-
-    const int nx = (int)clampf(__fmul_rn(__fmaf_rn(x, mip_rbound, 1.0f), p.halfH), 0.0f, p.Hm1f);
-    const int ny = (int)clampf(__fmul_rn(__fmaf_rn(y, mip_rbound, 1.0f), p.halfH), 0.0f, p.Hm1f);
-    const int nz = (int)clampf(__fmul_rn(__fmaf_rn(z, mip_rbound, 1.0f), p.halfH), 0.0f, p.Hm1f);
-
-    // level * H^3 + morton, evaluated in fp32 as the reference does (H3 is a float there, raymarching.cu:380,419)
-    const uint32_t index = (uint32_t)__fmaf_rn((float)level, p.H3f, (float)morton_encode(nx, ny, nz));
-    const bool occ = (__ldg(p.grid + (index >> 3)) >> (index & 7u)) & 1u;
-    if (occ) return true;
-
-    // distance to the next voxel boundary along each axis              (raymarching.cu:431-439)
-    const float ax = __fmaf_rn(r.hsx, 0.5f, (float)nx + 0.5f);
-    const float ay = __fmaf_rn(r.hsy, 0.5f, (float)ny + 0.5f);
-    const float az = __fmaf_rn(r.hsz, 0.5f, (float)nz + 0.5f);
-    const float tx = __fmul_rn(__fmaf_rn(mip_bound, __fmaf_rn(__fmul_rn(ax, p.rH), 2.0f, -1.0f), -x), r.rdx);
-    const float ty = __fmul_rn(__fmaf_rn(mip_bound, __fmaf_rn(__fmul_rn(ay, p.rH), 2.0f, -1.0f), -y), r.rdy);
-    const float tz = __fmul_rn(__fmaf_rn(mip_bound, __fmaf_rn(__fmul_rn(az, p.rH), 2.0f, -1.0f), -z), r.rdz);
-    const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
-    do {
-        t = __fadd_rn(step_size(p, t), t);
-    } while (t < tt);
-    return false;
-}
 
 namespace {
 

@@ -7,21 +7,9 @@
 // written with 16-byte stores when its length allows.
 #include "common.cuh"
 
+#include "sh.cuh"
+
 namespace rn {
-#include "sh_basis.inc"
-
-template <int DEG, bool GRAD>
-__device__ __forceinline__ void sh_eval(float x, float y, float z, float* Y, float* gx, float* gy, float* gz) {
-    sh_band0<GRAD>(x, y, z, Y, gx, gy, gz);
-    if constexpr (DEG > 1) sh_band1<GRAD>(x, y, z, Y, gx, gy, gz);
-    if constexpr (DEG > 2) sh_band2<GRAD>(x, y, z, Y, gx, gy, gz);
-    if constexpr (DEG > 3) sh_band3<GRAD>(x, y, z, Y, gx, gy, gz);
-    if constexpr (DEG > 4) sh_band4<GRAD>(x, y, z, Y, gx, gy, gz);
-    if constexpr (DEG > 5) sh_band5<GRAD>(x, y, z, Y, gx, gy, gz);
-    if constexpr (DEG > 6) sh_band6<GRAD>(x, y, z, Y, gx, gy, gz);
-    if constexpr (DEG > 7) sh_band7<GRAD>(x, y, z, Y, gx, gy, gz);
-}
-
 namespace {
 
 template <int N>

@@ -1,0 +1,129 @@
+// umma.cuh -- hand-written tcgen05 / TMEM / mbarrier helpers for the fused MLP kernels (sm_100a).
+//
+// Operand convention used everywhere in this library ("interleaved", i.e. UMMA LayoutType::SWIZZLE_NONE, K-major):
+// a [rows x K] fp16 operand is stored as 8-row x 16-byte core matrices,
+//      byte_offset(r, k) = (r / 8) * SBO + (k / 8) * LBO + (r % 8) * 16 + (k % 8) * 2,   LBO = 128, SBO = 128 * (K / 8)
+// so the K/8 core matrices of one 8-row group are contiguous.  A thread that owns row r writes its K halves as K/8
+// 16-byte stores; lanes r..r+7 cover 128 contiguous bytes per store phase (bank-conflict free).  nn.Linear weights
+// [out, in] are exactly the B operand (N x K, K-major) in this layout.
+// One tcgen05.mma consumes K = 16 (two core matrices along K): the descriptor for k-step s starts at base + s * 2 * LBO.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace rn {
+namespace umma {
+
+constexpr uint32_t LBO_BYTES = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of element (r, k) of an interleaved [rows x K] fp16 operand
+__host__ __device__ __forceinline__ uint32_t il_offset(uint32_t r, uint32_t k, uint32_t K) {
+    return (r >> 3) * (LBO_BYTES * (K >> 3)) + (k >> 3) * LBO_BYTES + (r & 7) * 16 + (k & 7) * 2;
+}
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout_type [61,64) = 0 (no swizzle)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t K) {
+    const uint32_t sbo = LBO_BYTES * (K >> 3);
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(LBO_BYTES >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// instruction descriptor for kind::f16, A/B = fp16 K-major, D = fp32, M = 128 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4)              // c_format = F32
+           | (0u << 7)            // a_format = F16
+           | (0u << 10)           // b_format = F16
+           | (0u << 15) | (0u << 16)  // K-major A and B
+           | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// D[128 x N] (+)= A[128 x K] * B[N x K]^T for K a multiple of 16; issued by ONE thread
+__device__ __forceinline__ void gemm_issue(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t K_a_total,
+                                           uint32_t K_b_total, uint32_t k_begin, uint32_t k_count, uint32_t N, bool accumulate) {
+    const uint32_t idesc = make_idesc_f16(128, N);
+    for (uint32_t s = 0; s < k_count; s += 16) {
+        const uint64_t da = make_desc(a_smem + ((k_begin + s) >> 3) * LBO_BYTES, K_a_total);
+        const uint64_t db = make_desc(b_smem + ((k_begin + s) >> 3) * LBO_BYTES, K_b_total);
+        mma_f16_ss(tmem_d, da, db, idesc, (accumulate || s > 0) ? 1u : 0u);
+    }
+}
+
+__device__ __forceinline__ void commit(uint64_t* mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy st.shared -> visible to the async proxy (tensor core operand fetch)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM allocation (one full warp) ---------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- TMEM -> registers: warp w (w % 4) may only touch lanes [32*(w%4), +32); each thread gets its lane's columns -----
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- mbarrier -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* mbar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(mbar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded spin: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(mbar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+
+// sub-CTA barrier for one 128-thread tile group
+__device__ __forceinline__ void group_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace umma
+}  // namespace rn

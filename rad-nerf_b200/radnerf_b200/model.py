@@ -1,0 +1,519 @@
+"""Host-side mirror of the reference's model/renderer for the hot path (NeRFNetwork + NeRFRenderer).
+
+Why this file exists: the reference's nerf/network.py and nerf/renderer.py run unchanged on top of the drop-in operator
+packages in this directory, but they cannot travel to a box without /root/reference, they import seven pip packages that
+are absent offline, and they only know the op-by-op execution order.  This module restates the same model:
+
+  * identical parameter / buffer names and shapes, so a reference checkpoint's `model` state-dict loads as is
+    (nerf/network.py:91-167, nerf/renderer.py:84-133);
+  * `render(rays_o, rays_d, auds, bg_coords, poses, **kw)` with the reference's keyword contract and result keys
+    (nerf/renderer.py:158-316, 504-537); `update_extra_state`, `mark_untrained_grid` (renderer.py:318-501);
+  * two execution paths:  `path="ops"`  -- the reference's op-by-op order on the drop-in operators + torch Linear layers
+    (the parity yardstick and the autograd/training path);  `path="fused"` -- one call into the fused sm_100a frame
+    renderer (radnerf_b200.frame), no per-iteration host sync.
+
+`ops` can be swapped for a bundle that calls the reference's own compiled kernels (oracle/ref_backend.py) -- bench.py
+uses that as the reference-CUDA comparison arm.
+"""
+import math
+import random
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+@dataclass
+class Options:
+    """The subset of the reference's argparse namespace (main.py:12-120, test.py) that reaches the hot path."""
+    bound: float = 1.0
+    min_near: float = 0.05
+    density_thresh: float = 10.0
+    density_thresh_torso: float = 0.01
+    dt_gamma: float = 1 / 256
+    max_steps: int = 16
+    exp_eye: bool = True          # -O
+    fp16: bool = True             # -O
+    torso: bool = False
+    smooth_lips: bool = False     # set by --test
+    test_train: bool = False
+    cuda_ray: bool = True
+    train_camera: bool = False
+    att: int = 2
+    emb: bool = False
+    ind_num: int = 10000
+    ind_dim: int = 4
+    ind_dim_torso: int = 8
+    amb_dim: int = 2
+    torso_shrink: float = 0.8
+    asr_model: str = "cpierse/wav2vec2-large-xlsr-53-esperanto"
+    num_rays: int = 4096 * 16
+    update_extra_interval: int = 16
+
+    def render_kwargs(self):
+        """what `**vars(opt)` contributes to run_cuda's signature (renderer.py:158)"""
+        return dict(dt_gamma=self.dt_gamma, max_steps=self.max_steps)
+
+
+class DefaultOps:
+    """operator bundle = this repo's drop-in packages"""
+
+    def __init__(self):
+        import raymarching
+        from encoding import get_encoder
+        from activation import trunc_exp
+        self.rm = raymarching
+        self.get_encoder = get_encoder
+        self.trunc_exp = trunc_exp
+
+
+# ------------------------------------------------------------------------------------------- audio nets / MLP
+def _conv_stack(chans, stride):
+    layers = []
+    for cin, cout in zip(chans[:-1], chans[1:]):
+        layers += [nn.Conv1d(cin, cout, kernel_size=3, stride=stride, padding=1, bias=True), nn.LeakyReLU(0.02, True)]
+    return nn.Sequential(*layers)
+
+
+class AudioAttNet(nn.Module):
+    """attention over the 8-frame window (network.py:10-37): 5 x Conv1d(k3) 64->16->8->4->2->1, Linear(8,8)+softmax."""
+
+    def __init__(self, dim_aud=64, seq_len=8):
+        super().__init__()
+        self.seq_len, self.dim_aud = seq_len, dim_aud
+        self.attentionConvNet = _conv_stack([dim_aud, 16, 8, 4, 2, 1], stride=1)
+        self.attentionNet = nn.Sequential(nn.Linear(seq_len, seq_len, bias=True), nn.Softmax(dim=1))
+
+    def forward(self, x):  # x [1, seq_len, dim_aud]
+        y = self.attentionConvNet(x.permute(0, 2, 1))
+        y = self.attentionNet(y.view(1, self.seq_len)).view(1, self.seq_len, 1)
+        return torch.sum(y * x, dim=1)
+
+
+class AudioNet(nn.Module):
+    """per-frame audio feature CNN (network.py:41-67): 4 x Conv1d(k3,s2) dim_in->32->32->64->64 over a 16-wide window,
+    then Linear 64->64->dim_aud with LeakyReLU(0.02)."""
+
+    def __init__(self, dim_in=29, dim_aud=64, win_size=16):
+        super().__init__()
+        self.win_size, self.dim_aud = win_size, dim_aud
+        self.encoder_conv = _conv_stack([dim_in, 32, 32, 64, 64], stride=2)
+        self.encoder_fc1 = nn.Sequential(nn.Linear(64, 64), nn.LeakyReLU(0.02, True), nn.Linear(64, dim_aud))
+
+    def forward(self, x):
+        half_w = int(self.win_size / 2)
+        x = x[:, :, 8 - half_w:8 + half_w]
+        return self.encoder_fc1(self.encoder_conv(x).squeeze(-1))
+
+
+class MLP(nn.Module):
+    """bias-free Linear stack with ReLU between layers (network.py:69-88)."""
+
+    def __init__(self, dim_in, dim_out, dim_hidden, num_layers):
+        super().__init__()
+        self.dim_in, self.dim_out, self.dim_hidden, self.num_layers = dim_in, dim_out, dim_hidden, num_layers
+        self.net = nn.ModuleList([
+            nn.Linear(dim_in if l == 0 else dim_hidden, dim_out if l == num_layers - 1 else dim_hidden, bias=False)
+            for l in range(num_layers)])
+
+    def forward(self, x):
+        for l, layer in enumerate(self.net):
+            x = layer(x)
+            if l != self.num_layers - 1:
+                x = F.relu(x, inplace=True)
+        return x
+
+
+# ------------------------------------------------------------------------------------------- the model
+class NeRFNetwork(nn.Module):
+    def __init__(self, opt: Options = None, ops=None, num_layers=3, hidden_dim=64, geo_feat_dim=64, num_layers_color=2,
+                 hidden_dim_color=64, audio_dim=64, num_layers_ambient=3, hidden_dim_ambient=64, ambient_dim=2):
+        super().__init__()
+        self.opt = opt = opt or Options()
+        self.ops = ops or DefaultOps()
+        get_encoder = self.ops.get_encoder
+
+        # ---- renderer state (renderer.py:63-133)
+        self.bound = opt.bound
+        self.cascade = 1 + math.ceil(math.log2(opt.bound))
+        self.grid_size = 128
+        self.density_scale = 1
+        self.min_near, self.density_thresh, self.density_thresh_torso = opt.min_near, opt.density_thresh, opt.density_thresh_torso
+        self.exp_eye, self.test_train, self.smooth_lips = opt.exp_eye, opt.test_train, opt.smooth_lips
+        self.torso, self.cuda_ray, self.train_camera = opt.torso, opt.cuda_ray, opt.train_camera
+        b = opt.bound
+        aabb = torch.tensor([-b, -b / 2, -b, b, b / 2, b], dtype=torch.float32)
+        self.register_buffer('aabb_train', aabb)
+        self.register_buffer('aabb_infer', aabb.clone())
+        self.individual_num, self.individual_dim = opt.ind_num, opt.ind_dim
+        if self.individual_dim > 0:
+            self.individual_codes = nn.Parameter(torch.randn(self.individual_num, self.individual_dim) * 0.1)
+        if self.torso:
+            self.individual_dim_torso = opt.ind_dim_torso
+            if self.individual_dim_torso > 0:
+                self.individual_codes_torso = nn.Parameter(torch.randn(self.individual_num, self.individual_dim_torso) * 0.1)
+        if self.train_camera:
+            self.camera_dR = nn.Parameter(torch.zeros(self.individual_num, 3))
+            self.camera_dT = nn.Parameter(torch.zeros(self.individual_num, 3))
+        self.register_buffer('density_grid', torch.zeros([self.cascade, self.grid_size ** 3]))
+        self.register_buffer('density_bitfield', torch.zeros(self.cascade * self.grid_size ** 3 // 8, dtype=torch.uint8))
+        self.mean_density = 0
+        self.iter_density = 0
+        if self.torso:
+            self.register_buffer('density_grid_torso', torch.zeros([self.grid_size ** 2]))
+        self.mean_density_torso = 0
+        self.register_buffer('step_counter', torch.zeros(16, 2, dtype=torch.int32))
+        self.mean_count = 0
+        self.local_step = 0
+        if self.smooth_lips:
+            self.enc_a = None
+
+        # ---- networks (network.py:111-167)
+        self.emb = opt.emb
+        if 'esperanto' in opt.asr_model:
+            self.audio_in_dim = 44
+        elif 'deepspeech' in opt.asr_model:
+            self.audio_in_dim = 29
+        else:
+            self.audio_in_dim = 32
+        if self.emb:
+            self.embedding = nn.Embedding(self.audio_in_dim, self.audio_in_dim)
+        self.audio_dim = audio_dim
+        self.audio_net = AudioNet(self.audio_in_dim, self.audio_dim)
+        self.att = opt.att
+        if self.att > 0:
+            self.audio_att_net = AudioAttNet(self.audio_dim)
+
+        grid = dict(num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=16, interpolation='linear')
+        self.encoder, self.in_dim = get_encoder('tiledgrid', input_dim=3, desired_resolution=2048 * self.bound, **grid)
+        self.encoder_ambient, self.in_dim_ambient = get_encoder('tiledgrid', input_dim=ambient_dim, desired_resolution=2048, **grid)
+        self.num_layers_ambient, self.hidden_dim_ambient, self.ambient_dim = num_layers_ambient, hidden_dim_ambient, ambient_dim
+        self.ambient_net = MLP(self.in_dim + self.audio_dim, self.ambient_dim, self.hidden_dim_ambient, self.num_layers_ambient)
+
+        self.num_layers, self.hidden_dim, self.geo_feat_dim = num_layers, hidden_dim, geo_feat_dim
+        self.eye_dim = 1 if self.exp_eye else 0
+        self.sigma_net = MLP(self.in_dim + self.in_dim_ambient + self.eye_dim, 1 + self.geo_feat_dim, self.hidden_dim, self.num_layers)
+
+        self.num_layers_color, self.hidden_dim_color = num_layers_color, hidden_dim_color
+        self.encoder_dir, self.in_dim_dir = get_encoder('spherical_harmonics')
+        self.color_net = MLP(self.in_dim_dir + self.geo_feat_dim + self.individual_dim, 3, self.hidden_dim_color, self.num_layers_color)
+
+        if self.torso:
+            self.torso_deform_encoder, self.torso_deform_in_dim = get_encoder('frequency', input_dim=2, multires=10)
+            self.pose_encoder, self.pose_in_dim = get_encoder('frequency', input_dim=6, multires=4)
+            self.torso_deform_net = MLP(self.torso_deform_in_dim + self.pose_in_dim + self.individual_dim_torso, 2, 64, 3)
+            self.torso_encoder, self.torso_in_dim = get_encoder('tiledgrid', input_dim=2, desired_resolution=2048, **grid)
+            self.torso_net = MLP(self.torso_in_dim + self.torso_deform_in_dim + self.pose_in_dim + self.individual_dim_torso, 4, 32, 3)
+
+        # data-dependent statistics the occupancy update samples from (set by the data provider in the reference)
+        self.aud_features = None  # [n, dim, 16]
+        self.eye_area = None      # [n, 1]
+        self.poses = None         # [n, 4, 4]
+
+    # ------------------------------------------------------------------------------------- network pieces
+    def encode_audio(self, a):
+        """[8, dim, 16] window -> [1, 64] (network.py:170-185)"""
+        if a is None:
+            return None
+        if self.emb:
+            a = self.embedding(a).transpose(-1, -2).contiguous()
+        enc_a = self.audio_net(a)
+        if self.att > 0:
+            enc_a = self.audio_att_net(enc_a.unsqueeze(0))
+        return enc_a
+
+    def _ambient_and_features(self, x, enc_a):
+        if enc_a is None:
+            ambient = torch.zeros_like(x[:, :self.ambient_dim])
+            enc_x = self.encoder(x, bound=self.bound)
+            enc_w = self.encoder_ambient(ambient, bound=1)
+        else:
+            enc_a = enc_a.repeat(x.shape[0], 1)
+            enc_x = self.encoder(x, bound=self.bound)
+            ambient = torch.cat([enc_x, enc_a], dim=1)
+            ambient = self.ambient_net(ambient).float()
+            ambient = torch.tanh(ambient)  # audio-driven 2-D coordinate in [-1, 1]
+            enc_w = self.encoder_ambient(ambient, bound=1)
+        return ambient, enc_x, enc_w
+
+    def _sigma_head(self, enc_x, enc_w, e, n):
+        if e is not None:
+            h = torch.cat([enc_x, enc_w, e.repeat(n, 1)], dim=-1)
+        else:
+            h = torch.cat([enc_x, enc_w], dim=-1)
+        h = self.sigma_net(h)
+        return self.ops.trunc_exp(h[..., 0]), h[..., 1:]
+
+    def forward(self, x, d, enc_a, c, e=None):
+        """x [N,3] in [-bound,bound]; d [N,3]; enc_a [1,64]; c [ind_dim]; e [1,1] -> sigma [N], color [N,3], ambient [N,2]
+        (network.py:222-283)"""
+        ambient, enc_x, enc_w = self._ambient_and_features(x, enc_a)
+        sigma, geo_feat = self._sigma_head(enc_x, enc_w, e, x.shape[0])
+        enc_d = self.encoder_dir(d)
+        if c is not None:
+            h = torch.cat([enc_d, geo_feat, c.repeat(x.shape[0], 1)], dim=-1)
+        else:
+            h = torch.cat([enc_d, geo_feat], dim=-1)
+        color = torch.sigmoid(self.color_net(h))
+        return sigma, color, ambient
+
+    def density(self, x, enc_a, e=None):
+        """(network.py:286-325)"""
+        _, enc_x, enc_w = self._ambient_and_features(x, enc_a)
+        sigma, geo_feat = self._sigma_head(enc_x, enc_w, e, x.shape[0])
+        return {'sigma': sigma, 'geo_feat': geo_feat}
+
+    def forward_torso(self, x, poses, enc_a, c=None):
+        """x [N,2] in [-1,1]; poses [1,6] -> alpha [N,1], color [N,3], dx [N,2] (network.py:188-219)"""
+        x = x * self.opt.torso_shrink
+        enc_pose = self.pose_encoder(poses)
+        enc_x = self.torso_deform_encoder(x)
+        if c is not None:
+            h = torch.cat([enc_x, enc_pose.repeat(x.shape[0], 1), c.repeat(x.shape[0], 1)], dim=-1)
+        else:
+            h = torch.cat([enc_x, enc_pose.repeat(x.shape[0], 1)], dim=-1)
+        dx = self.torso_deform_net(h)
+        x = (x + dx).clamp(-1, 1)
+        x = self.torso_encoder(x, bound=1)
+        h = self.torso_net(torch.cat([x, h], dim=-1))
+        return torch.sigmoid(h[..., :1]), torch.sigmoid(h[..., 1:]), dx
+
+    def get_params(self, lr, lr_net, wd=0):
+        """optimizer groups (network.py:329-361)"""
+        if self.torso:
+            params = [{'params': self.torso_encoder.parameters(), 'lr': lr},
+                      {'params': self.torso_net.parameters(), 'lr': lr_net, 'weight_decay': wd},
+                      {'params': self.torso_deform_net.parameters(), 'lr': lr_net, 'weight_decay': wd}]
+            if self.individual_dim_torso > 0:
+                params.append({'params': self.individual_codes_torso, 'lr': lr_net, 'weight_decay': wd})
+            return params
+        params = [{'params': self.audio_net.parameters(), 'lr': lr_net, 'weight_decay': wd},
+                  {'params': self.encoder.parameters(), 'lr': lr},
+                  {'params': self.encoder_ambient.parameters(), 'lr': lr},
+                  {'params': self.ambient_net.parameters(), 'lr': lr_net, 'weight_decay': wd},
+                  {'params': self.sigma_net.parameters(), 'lr': lr_net, 'weight_decay': wd},
+                  {'params': self.color_net.parameters(), 'lr': lr_net, 'weight_decay': wd}]
+        if self.att > 0:
+            params.append({'params': self.audio_att_net.parameters(), 'lr': lr_net * 5, 'weight_decay': wd})
+        if self.emb:
+            params.append({'params': self.embedding.parameters(), 'lr': lr})
+        if self.individual_dim > 0:
+            params.append({'params': self.individual_codes, 'lr': lr_net, 'weight_decay': wd})
+        if self.train_camera:
+            params.append({'params': self.camera_dT, 'lr': 1e-5, 'weight_decay': 0})
+            params.append({'params': self.camera_dR, 'lr': 1e-5, 'weight_decay': 0})
+        return params
+
+    # ------------------------------------------------------------------------------------- renderer
+    def reset_extra_state(self):
+        self.density_grid.zero_()
+        self.mean_density = 0
+        self.iter_density = 0
+        self.step_counter.zero_()
+        self.mean_count = 0
+        self.local_step = 0
+
+    def _frame_conditioning(self, auds, index):
+        """per-frame constants: smoothed audio code and the individual code (renderer.py:187-204)"""
+        enc_a = self.encode_audio(auds)
+        if enc_a is not None and self.smooth_lips:
+            if self.enc_a is not None:
+                _lambda = 0.35
+                enc_a = _lambda * self.enc_a + (1 - _lambda) * enc_a
+            self.enc_a = enc_a
+        ind_code = None
+        if self.individual_dim > 0:
+            ind_code = self.individual_codes[index] if self.training else self.individual_codes[0]
+        return enc_a, ind_code
+
+    def run_cuda(self, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=0, dt_gamma=0, bg_color=None, perturb=False,
+                 force_all_rays=False, max_steps=1024, T_thresh=1e-4, **kwargs):
+        """op-by-op frame / training batch, in the reference's order (renderer.py:158-316)."""
+        rm = self.ops.rm
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        bg_coords = bg_coords.contiguous().view(-1, 2)
+        N = rays_o.shape[0]
+        device = rays_o.device
+        results = {}
+
+        nears, fars = rm.near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer, self.min_near)
+        nears, fars = nears.detach(), fars.detach()
+        enc_a, ind_code = self._frame_conditioning(auds, index)
+
+        if self.training:
+            counter = self.step_counter[self.local_step % 16]
+            counter.zero_()
+            self.local_step += 1
+            xyzs, dirs, deltas, rays = rm.march_rays_train(rays_o, rays_d, self.bound, self.density_bitfield, self.cascade,
+                                                           self.grid_size, nears, fars, counter, self.mean_count, perturb, 128,
+                                                           force_all_rays, dt_gamma, max_steps)
+            sigmas, rgbs, ambient = self(xyzs, dirs, enc_a, ind_code, eye)
+            sigmas = self.density_scale * sigmas
+            weights_sum, ambient_sum, depth, image = rm.composite_rays_train(sigmas, rgbs, ambient.abs().sum(-1), deltas, rays)
+            results['weights_sum'] = weights_sum
+            results['ambient'] = ambient_sum
+        else:
+            weights_sum = torch.zeros(N, dtype=torch.float32, device=device)
+            depth = torch.zeros(N, dtype=torch.float32, device=device)
+            image = torch.zeros(N, 3, dtype=torch.float32, device=device)
+            rays_alive = torch.arange(N, dtype=torch.int32, device=device)
+            rays_t = nears.clone()
+            step = 0
+            self.last_frame_stats = []
+            while step < max_steps:
+                n_alive = rays_alive.shape[0]
+                if n_alive <= 0:
+                    break
+                n_step = max(min(N // n_alive, 8), 1)
+                xyzs, dirs, deltas = rm.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
+                                                   self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128,
+                                                   perturb if step == 0 else False, dt_gamma, max_steps)
+                sigmas, rgbs, ambient = self(xyzs, dirs, enc_a, ind_code, eye)
+                sigmas = self.density_scale * sigmas
+                rm.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh)
+                rays_alive = rays_alive[rays_alive >= 0]  # host sync: the new length is needed on the CPU
+                self.last_frame_stats.append((n_alive, n_step, xyzs.shape[0]))
+                step += n_step
+
+        if bg_color is None:
+            bg_color = 1
+
+        if self.torso:
+            ind_code_torso = None
+            if self.individual_dim_torso > 0:
+                ind_code_torso = self.individual_codes_torso[index] if self.training else self.individual_codes_torso[0]
+            density_thresh_torso = min(self.density_thresh_torso, self.mean_density_torso)
+            occupancy = F.grid_sample(self.density_grid_torso.view(1, 1, self.grid_size, self.grid_size),
+                                      bg_coords.view(1, -1, 1, 2), align_corners=True).view(-1)
+            mask = occupancy > density_thresh_torso
+            torso_alpha = torch.zeros([N, 1], device=device)
+            torso_color = torch.zeros([N, 3], device=device)
+            if mask.any():
+                torso_alpha_mask, torso_color_mask, deform = self.forward_torso(bg_coords[mask], poses, enc_a, ind_code_torso)
+                torso_alpha[mask] = torso_alpha_mask.float()
+                torso_color[mask] = torso_color_mask.float()
+                results['deform'] = deform
+            bg_color = torso_color * torso_alpha + bg_color * (1 - torso_alpha)
+            results['torso_alpha'] = torso_alpha
+            results['torso_color'] = bg_color
+
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        image = image.view(*prefix, 3).clamp(0, 1)
+        depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+        results['depth'] = depth.view(*prefix)
+        results['image'] = image
+        return results
+
+    def render(self, rays_o, rays_d, auds, bg_coords, poses, staged=False, max_ray_batch=4096, path="ops", **kwargs):
+        """entry point with the reference's contract (renderer.py:504-537); cuda_ray never stages.
+        path="fused" (inference only) runs the whole frame inside the fused sm_100a renderer."""
+        if path == "fused" and not self.training:
+            from . import frame
+            return frame.render_frame(self, rays_o, rays_d, auds, bg_coords, poses, **kwargs)
+        return self.run_cuda(rays_o, rays_d, auds, bg_coords, poses, **kwargs)
+
+    # ------------------------------------------------------------------------------------- occupancy maintenance
+    @torch.no_grad()
+    def mark_untrained_grid(self, poses, intrinsic, S=64):
+        """cells no training camera sees get density -1 (renderer.py:318-381)"""
+        rm = self.ops.rm
+        if isinstance(poses, np.ndarray):
+            poses = torch.from_numpy(poses)
+        B = poses.shape[0]
+        fx, fy, cx, cy = intrinsic
+        dev = self.density_bitfield.device
+        axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
+        count = torch.zeros_like(self.density_grid)
+        poses = poses.to(dev)
+        for xs in axis:
+            for ys in axis:
+                for zs in axis:
+                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
+                    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+                    indices = rm.morton3D(coords).long()
+                    world_xyzs = (2 * coords.float() / (self.grid_size - 1) - 1).unsqueeze(0)
+                    for cas in range(self.cascade):
+                        bound = min(2 ** cas, self.bound)
+                        half_grid_size = bound / self.grid_size
+                        cas_world_xyzs = world_xyzs * (bound - half_grid_size)
+                        head = 0
+                        while head < B:
+                            tail = min(head + S, B)
+                            cam_xyzs = cas_world_xyzs - poses[head:tail, :3, 3].unsqueeze(1)
+                            cam_xyzs = cam_xyzs @ poses[head:tail, :3, :3]
+                            mask_z = cam_xyzs[:, :, 2] > 0
+                            mask_x = torch.abs(cam_xyzs[:, :, 0]) < cx / fx * cam_xyzs[:, :, 2] + half_grid_size * 2
+                            mask_y = torch.abs(cam_xyzs[:, :, 1]) < cy / fy * cam_xyzs[:, :, 2] + half_grid_size * 2
+                            count[cas, indices] += (mask_z & mask_x & mask_y).sum(0).reshape(-1)
+                            head += S
+        self.density_grid[count == 0] = -1
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128):
+        """occupancy EMA + bitfield rebuild + mean sample count (renderer.py:383-501)"""
+        rm = self.ops.rm
+        dev = self.density_bitfield.device
+        rand_idx = random.randint(0, self.aud_features.shape[0] - 1)
+        from .synthetic import audio_window
+        auds = torch.as_tensor(audio_window(np.asarray(self.aud_features.cpu()) if torch.is_tensor(self.aud_features)
+                                            else self.aud_features, rand_idx, self.att)).to(dev)
+        enc_a = self.encode_audio(auds)
+
+        if not self.torso:
+            tmp_grid = torch.zeros_like(self.density_grid)
+            eye = self.eye_area[[rand_idx]].to(dev) if self.exp_eye else None
+            axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
+            for xs in axis:
+                for ys in axis:
+                    for zs in axis:
+                        xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
+                        coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+                        indices = rm.morton3D(coords).long()
+                        xyzs = 2 * coords.float() / (self.grid_size - 1) - 1
+                        for cas in range(self.cascade):
+                            bound = min(2 ** cas, self.bound)
+                            half_grid_size = bound / self.grid_size
+                            cas_xyzs = xyzs * (bound - half_grid_size)
+                            cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half_grid_size
+                            sigmas = self.density(cas_xyzs, enc_a, eye)['sigma'].reshape(-1).detach().to(tmp_grid.dtype)
+                            sigmas *= self.density_scale
+                            tmp_grid[cas, indices] = sigmas
+            tmp_grid = rm.morton3D_dilation(tmp_grid)
+            valid_mask = (self.density_grid >= 0) & (tmp_grid >= 0)
+            self.density_grid[valid_mask] = torch.maximum(self.density_grid[valid_mask] * decay, tmp_grid[valid_mask])
+            self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
+            self.iter_density += 1
+            density_thresh = min(self.mean_density, self.density_thresh)
+            self.density_bitfield = rm.packbits(self.density_grid, density_thresh, self.density_bitfield)
+
+        if self.torso:
+            from .posemath import convert_poses
+            tmp_grid_torso = torch.zeros_like(self.density_grid_torso)
+            rand_idx = random.randint(0, self.poses.shape[0] - 1)
+            pose = convert_poses(self.poses[[rand_idx]]).to(dev)
+            ind_code = self.individual_codes_torso[[rand_idx]] if self.opt.ind_dim_torso > 0 else None
+            axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
+            half_grid_size = 1 / self.grid_size
+            for xs in axis:
+                for ys in axis:
+                    xx, yy = torch.meshgrid(xs, ys, indexing='ij')
+                    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1)], dim=-1)
+                    indices = (coords[:, 1] * self.grid_size + coords[:, 0]).long()  # x/y transposed, as the reference
+                    xys = 2 * coords.float() / (self.grid_size - 1) - 1
+                    xys = xys * (1 - half_grid_size)
+                    xys += (torch.rand_like(xys) * 2 - 1) * half_grid_size
+                    alphas, _, _ = self.forward_torso(xys, pose, enc_a, ind_code)
+                    tmp_grid_torso[indices] = alphas.squeeze(1).float()
+            tmp_grid_torso = F.max_pool2d(tmp_grid_torso.view(1, 1, self.grid_size, self.grid_size), kernel_size=5, stride=1,
+                                          padding=2).view(-1)
+            self.density_grid_torso = torch.maximum(self.density_grid_torso * decay, tmp_grid_torso)
+            self.mean_density_torso = torch.mean(self.density_grid_torso).item()
+
+        total_step = min(16, self.local_step)
+        if total_step > 0:
+            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        self.local_step = 0
