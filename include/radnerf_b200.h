@@ -158,6 +158,74 @@ int rn_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, ui
 int rn_get_rays(const float* pose, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
                 const int32_t* pixel_ids, uint32_t n, float* rays_o, float* rays_d, void* stream);
 
+/* ------------------------------------------------------------------ fused inference frame ------------ */
+/* One call per stage of NeRFRenderer.run_cuda's inference branch (nerf/renderer.py:158-316) with no host round trip:
+ * the reference's Python `while step < max_steps` loop, its per-iteration march_rays / NeRFNetwork.forward /
+ * composite_rays calls and the `rays_alive[rays_alive >= 0]` host sync run as a fixed launch sequence driven by
+ * device-resident loop state; NeRFNetwork.forward / forward_torso run as fused tcgen05 kernels (csrc/head_eval.cu,
+ * csrc/torso_eval.cu).  Architecture is fixed to the one nerf/network.py builds: 16-level, 2-feature tiled grids with
+ * linear interpolation, hidden width 64 (torso 32), SH degree 4.  Tables are fp16 (the reference's autocast path). */
+
+typedef struct rn_grid_table {
+    const void* table_f16;   /* [rows, 2] fp16 */
+    const int32_t* offsets;  /* [17] */
+    float S;                 /* log2(per_level_scale) */
+    uint32_t H;              /* base resolution */
+} rn_grid_table;
+
+/* per-frame conditioning: AudioNet + AudioAttNet + lip smoothing + hoisted first-layer bias vectors
+ * (nerf/network.py:10-67,170-185; nerf/renderer.py:187-204).  All weight pointers are the fp32 parameters. */
+typedef struct rn_conditioning_desc {
+    const float* auds;           /* [F, Cin, 16] or NULL (no audio) */
+    uint32_t F, Cin, att, smooth, has_state;
+    const float* conv_w[4]; const float* conv_b[4];
+    const float* fc_w[2]; const float* fc_b[2];
+    const float* att_w[5]; const float* att_b[5];
+    const float* att_fc_w; const float* att_fc_b;
+    float* enc_a_state;          /* [64] in/out */
+    float lambda;
+    const float* w_amb1; const float* w_sig1; const float* w_col1;
+    const float* eye; const float* ind_code;
+    float* head_consts;          /* out [3*64] */
+    const float* w_def1; const float* w_tor1; const float* pose6; const float* ind_torso;
+    float* torso_consts;         /* out [64+32] */
+} rn_conditioning_desc;
+
+typedef struct rn_frame_head_desc {
+    uint32_t N, max_steps, cascade, grid_size;
+    float bound, min_near, dt_gamma, T_thresh;
+    const float* rays_o; const float* rays_d; const float* aabb; const uint8_t* bitfield;
+    const float* noises;         /* [N] or NULL: perturbation of the first iteration */
+    float* weights_sum; float* depth; float* image; float* nears; float* fars;   /* outputs [N], [N], [N,3], [N], [N] */
+    void* workspace; uint64_t workspace_bytes;
+    rn_grid_table grid3d, grid2d;
+    const void* head_blob;       /* rn_head_blob_bytes() of interleaved fp16 weights (see radnerf_b200/frame.py) */
+    const float* head_consts;    /* [3*64] from rn_frame_conditioning */
+} rn_frame_head_desc;
+
+typedef struct rn_frame_torso_desc {
+    uint32_t N, grid_size;
+    float thresh, shrink;
+    const float* bg_coords;      /* [N,2] */
+    const float* density_grid_torso; /* [grid_size^2] */
+    void* workspace; uint64_t workspace_bytes;
+    rn_grid_table grid2d;
+    const void* torso_blob; const float* torso_consts;
+    float* torso_alpha; float* torso_color;   /* out [N], [N,3] */
+} rn_frame_torso_desc;
+
+uint64_t rn_frame_workspace_bytes(uint32_t N);
+uint32_t rn_head_blob_bytes(void);
+uint32_t rn_torso_blob_bytes(void);
+int rn_frame_conditioning(const rn_conditioning_desc* d, void* stream);
+int rn_frame_head(const rn_frame_head_desc* d, void* stream);
+int rn_frame_torso(const rn_frame_torso_desc* d, void* stream);
+/* final blend + depth normalisation (nerf/renderer.py:299-310); bg_color [N,3] or NULL (then bg_scalar);
+ * torso_alpha/torso_color NULL when there is no torso; torso_bg_out (nullable) receives results['torso_color'] */
+int rn_frame_finalize(uint32_t N, const float* weights_sum, float* depth, float* image, const float* nears,
+                      const float* fars, const float* bg_color, float bg_scalar, const float* torso_alpha,
+                      const float* torso_color, float* torso_bg_out, void* stream);
+
 /* ------------------------------------------------------------------ diagnostics ---------------------- */
 
 /* one 128 x N x K fp16 GEMM tile through the hand-written tcgen05/TMEM path (out = A @ W^T, fp32 accumulate);

@@ -1,0 +1,90 @@
+// frame.cu -- C-ABI entry points of the fused inference frame (see frame.cuh for the pipeline).
+#include "frame.cuh"
+#include "march.cuh"
+#include <cstring>
+
+using namespace rn;
+
+extern "C" uint64_t rn_frame_workspace_bytes(uint32_t N) {
+    FrameWorkspace w;
+    return (uint64_t)carve(w, nullptr, N);
+}
+extern "C" uint32_t rn_head_blob_bytes(void) { return HEAD_BLOB_BYTES; }
+extern "C" uint32_t rn_torso_blob_bytes(void) { return TORSO_BLOB_BYTES; }
+
+extern "C" int rn_frame_conditioning(const rn_conditioning_desc* d, void* stream) {
+    RN_REQUIRE(d, "null descriptor");
+    RN_REQUIRE(d->head_consts && d->w_amb1 && d->w_sig1 && d->w_col1, "null pointer");
+    RN_REQUIRE(!d->auds || (d->F >= 1 && d->F <= 8 && d->Cin >= 1 && d->Cin <= 44), "auds must be [F<=8, Cin<=44, 16]");
+    RN_REQUIRE(!d->auds || d->att == 0 || d->F == 8, "attention needs the 8-frame window");
+    RN_REQUIRE(!d->smooth || d->enc_a_state, "lip smoothing needs a state buffer");
+    RN_REQUIRE(!d->w_def1 || (d->w_tor1 && d->pose6 && d->torso_consts), "incomplete torso conditioning");
+    static_assert(sizeof(AudioParams) == sizeof(rn_conditioning_desc), "descriptor mirrors AudioParams");
+    AudioParams p;
+    memcpy(&p, d, sizeof(p));
+    return launch_audio_frame(p, (cudaStream_t)stream);
+}
+
+extern "C" int rn_frame_head(const rn_frame_head_desc* d, void* stream) {
+    RN_REQUIRE(d, "null descriptor");
+    if (d->N == 0) return RN_OK;
+    RN_REQUIRE(d->rays_o && d->rays_d && d->aabb && d->bitfield && d->weights_sum && d->depth && d->image && d->nears && d->fars,
+               "null pointer");
+    RN_REQUIRE(d->workspace && d->workspace_bytes >= rn_frame_workspace_bytes(d->N), "workspace too small");
+    RN_REQUIRE(d->grid3d.table_f16 && d->grid3d.offsets && d->grid2d.table_f16 && d->grid2d.offsets && d->head_blob && d->head_consts,
+               "null network pointer");
+    RN_REQUIRE(d->max_steps >= 1 && d->max_steps <= (uint32_t)FRAME_MAX_ITERS, "max_steps must be in [1, 64] for the fused frame");
+    RN_REQUIRE(d->cascade >= 1 && d->cascade <= 16 && d->grid_size >= 1, "bad cascade/grid_size");
+    RN_REQUIRE(((uintptr_t)d->head_blob & 15) == 0, "head_blob must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    FrameWorkspace w;
+    carve(w, (uint8_t*)d->workspace, d->N);
+    int rc = launch_frame_init(d->rays_o, d->rays_d, d->aabb, d->N, d->min_near, d->max_steps, d->nears, d->fars, w, d->weights_sum,
+                               d->depth, d->image, st);
+    if (rc) return rc;
+    const MarchParams mp = make_march_params(d->bound, d->dt_gamma, d->max_steps, d->cascade, d->grid_size, d->bitfield);
+    HeadEvalParams hp;
+    hp.table3 = (const __half*)d->grid3d.table_f16; hp.offs3 = d->grid3d.offsets; hp.S3 = d->grid3d.S; hp.H3 = d->grid3d.H;
+    hp.table2 = (const __half*)d->grid2d.table_f16; hp.offs2 = d->grid2d.offsets; hp.S2 = d->grid2d.S; hp.H2 = d->grid2d.H;
+    hp.blob = (const uint8_t*)d->head_blob; hp.consts = d->head_consts; hp.rays_d = d->rays_d;
+    hp.samples = w.samples; hp.evals = w.evals; hp.bound = d->bound; hp.inv2bound = 1.0f / (2.0f * d->bound);
+    const uint32_t max_tiles = (d->N + EVAL_TILE - 1) / EVAL_TILE;  // n_alive * n_step <= N in every iteration
+    // n_step >= 1, so the reference's loop runs at most max_steps iterations
+    for (uint32_t it = 0; it < d->max_steps; ++it) {
+        if ((rc = launch_march_compact(it, d->N, w, d->rays_o, d->rays_d, d->fars, mp, d->noises, st))) return rc;
+        if ((rc = launch_head_eval(hp, w.ctl + it, max_tiles, st))) return rc;
+        if ((rc = launch_composite_compact(it, d->N, d->max_steps, d->T_thresh, w, d->weights_sum, d->depth, d->image, st))) return rc;
+    }
+    return RN_OK;
+}
+
+extern "C" int rn_frame_torso(const rn_frame_torso_desc* d, void* stream) {
+    RN_REQUIRE(d, "null descriptor");
+    if (d->N == 0) return RN_OK;
+    RN_REQUIRE(d->bg_coords && d->density_grid_torso && d->torso_alpha && d->torso_color && d->torso_blob && d->torso_consts, "null pointer");
+    RN_REQUIRE(d->workspace && d->workspace_bytes >= rn_frame_workspace_bytes(d->N), "workspace too small");
+    RN_REQUIRE(d->grid2d.table_f16 && d->grid2d.offsets, "null network pointer");
+    RN_REQUIRE(((uintptr_t)d->torso_blob & 15) == 0, "torso_blob must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    FrameWorkspace w;
+    carve(w, (uint8_t*)d->workspace, d->N);
+    cudaMemsetAsync(w.misc, 0, 32, st);
+    int rc = launch_torso_mask(d->bg_coords, d->density_grid_torso, d->grid_size, d->thresh, d->N, w, st);
+    if (rc) return rc;
+    TorsoEvalParams tp;
+    tp.table = (const __half*)d->grid2d.table_f16; tp.offs = d->grid2d.offsets; tp.S = d->grid2d.S; tp.H = d->grid2d.H;
+    tp.blob = (const uint8_t*)d->torso_blob; tp.consts = d->torso_consts; tp.bg_coords = d->bg_coords; tp.pix = w.torso_pix;
+    tp.n_pix = w.misc; tp.out = w.torso_out; tp.shrink = d->shrink;
+    if ((rc = launch_torso_eval(tp, (d->N + EVAL_TILE - 1) / EVAL_TILE, st))) return rc;
+    return launch_torso_scatter(d->N, w, d->torso_alpha, d->torso_color, st);
+}
+
+extern "C" int rn_frame_finalize(uint32_t N, const float* weights_sum, float* depth, float* image, const float* nears,
+                                 const float* fars, const float* bg_color, float bg_scalar, const float* torso_alpha,
+                                 const float* torso_color, float* torso_bg_out, void* stream) {
+    if (N == 0) return RN_OK;
+    RN_REQUIRE(weights_sum && depth && image && nears && fars, "null pointer");
+    RN_REQUIRE(!torso_alpha || torso_color, "torso_color missing");
+    return launch_finalize(N, weights_sum, depth, image, nears, fars, bg_color, bg_scalar, torso_alpha, torso_color, torso_bg_out,
+                           (cudaStream_t)stream);
+}

@@ -1,0 +1,324 @@
+// head_eval.cu -- the fused per-sample network of the head (NeRFNetwork.forward, nerf/network.py:222-283) as ONE
+// persistent tcgen05 kernel: for every 128-sample tile
+//
+//   3-D grid encode (16 lvl x 8 corners, fp16 table)            -> A0  [128 x 32]  fp16, smem
+//   ambient MLP  32(+64 audio, hoisted) -> 64 -> 64 -> 2         tcgen05.mma, accumulators in TMEM
+//   tanh (fp32)  -> 2-D grid encode (16 lvl x 4 corners)         -> EW  [128 x 32]
+//   sigma MLP    64(+eye, hoisted) -> 64 -> 64 -> 65             -> sigma = exp(.), geo_feat [128 x 64]
+//   SH(dir) deg 4 (16)                                           -> CIN [128 x 80] = [sh | geo_feat]
+//   colour MLP   80(+4 individual code, hoisted) -> 64 -> 3      -> sigmoid
+//
+// Activations never leave the SM: thread t of a 128-thread tile group owns sample row t of every operand/accumulator
+// (TMEM lane t), gathers its own features, and writes fp16 rows straight into the next layer's A operand in the
+// interleaved UMMA layout (umma.cuh).  Per-frame-constant inputs (audio code, eye, individual code) are folded into
+// fp32 bias vectors once per frame (rn_frame_constants).  All 8 weight matrices (52 KB fp16) are staged once per CTA with
+// one TMA bulk copy.  EVAL_GROUPS tile groups per CTA interleave so gathers of one tile overlap MMAs/epilogues of others.
+//
+// Rounding points follow the reference's fp16 autocast: layer outputs are rounded to fp16 (nn.Linear under autocast),
+// the ambient coordinate goes back to fp32 before tanh (network.py:246-247), sigma = exp in fp32 (activation.py:5),
+// SH in fp32 then fp16 at the colour layer's input, sigmoid output in fp16.
+#include "frame.cuh"
+#include "umma.cuh"
+#include "gridencoder_impl.cuh"
+#include "sh.cuh"
+
+namespace rn {
+
+
+namespace {
+
+using grid::LevelMeta;
+
+// blob sub-matrix byte offsets
+constexpr uint32_t B_WA1 = 0;
+constexpr uint32_t B_WA2 = B_WA1 + 64 * 32 * 2;
+constexpr uint32_t B_WA3 = B_WA2 + 64 * 64 * 2;
+constexpr uint32_t B_WS1A = B_WA3 + 16 * 64 * 2;
+constexpr uint32_t B_WS1B = B_WS1A + 64 * 32 * 2;
+constexpr uint32_t B_WS2 = B_WS1B + 64 * 32 * 2;
+constexpr uint32_t B_WS3 = B_WS2 + 64 * 64 * 2;
+constexpr uint32_t B_WC1 = B_WS3 + 80 * 64 * 2;
+constexpr uint32_t B_WC2 = B_WC1 + 64 * 80 * 2;
+static_assert(B_WC2 + 16 * 64 * 2 == HEAD_BLOB_BYTES, "blob layout");
+
+// per-group activation buffers
+constexpr uint32_t G_A0 = 0;                       // [128 x 32]
+constexpr uint32_t G_EW = G_A0 + 128 * 32 * 2;     // [128 x 32]
+constexpr uint32_t G_H0 = G_EW + 128 * 32 * 2;     // [128 x 64], re-used as CIN [128 x 80]
+constexpr uint32_t G_H1 = G_H0 + 128 * 80 * 2;     // [128 x 64]
+constexpr uint32_t GROUP_BYTES = G_H1 + 128 * 64 * 2;
+constexpr uint32_t HEAD_SMEM = HEAD_BLOB_BYTES + EVAL_GROUPS * GROUP_BYTES;
+constexpr uint32_t TMEM_COLS_PER_GROUP = 128;
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// TMEM accumulator columns [col0, col0 + 16*NCH) of this thread's row -> (+bias, ReLU) -> fp16 -> smem row of an
+// interleaved [128 x Kdst] operand starting at destination column dcol0.
+template <int NCH, bool RELU>
+__device__ __forceinline__ void epilogue_to_operand(uint32_t tmem_row, uint32_t col0, const float* __restrict__ bias,
+                                                    uint8_t* dst, uint32_t row, uint32_t Kdst, uint32_t dcol0) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        uint32_t v[16];
+        umma::tmem_ld16(tmem_row + col0 + 16 * c, v);
+        umma::tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            f[j] = __uint_as_float(v[j]);
+            if (bias) f[j] += bias[16 * c + j];
+            if (RELU) f[j] = fmaxf(f[j], 0.0f);
+        }
+        uint4 lo = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+        uint4 hi = make_uint4(pack2(f[8], f[9]), pack2(f[10], f[11]), pack2(f[12], f[13]), pack2(f[14], f[15]));
+        *reinterpret_cast<uint4*>(dst + umma::il_offset(row, dcol0 + 16 * c, Kdst)) = lo;
+        *reinterpret_cast<uint4*>(dst + umma::il_offset(row, dcol0 + 16 * c + 8, Kdst)) = hi;
+    }
+}
+
+// one thread encodes one point through all 16 levels (C = 2, fp16 table, reference rounding) into 32 halfs
+template <int D>
+__device__ __forceinline__ void encode_row(const float (&x)[D], const __half* __restrict__ table, const LevelMeta* __restrict__ meta,
+                                           uint8_t* dst, uint32_t row, uint32_t Kdst, uint32_t dcol0) {
+    bool oob = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) if (x[d] < 0 || x[d] > 1) oob = true;
+#pragma unroll
+    for (int l0 = 0; l0 < 16; l0 += 4) {
+        uint32_t packed[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __half r0 = __float2half_rn(0.f), r1 = r0;
+            if (!oob) {
+                const LevelMeta m = meta[l0 + j];
+                const __half* __restrict__ tbl = table + (size_t)m.offset * 2;
+                const grid::Cell<D> cell = grid::locate<D>(x, m, false, 0);
+                grid::Row<__half, 2> rows[1 << D];
+#pragma unroll
+                for (uint32_t k = 0; k < (1u << D); ++k)
+                    rows[k] = grid::load_row<__half, 2>(tbl + (size_t)grid::corner_row<D>(m, cell.pg, k) * 2);
+#pragma unroll
+                for (uint32_t k = 0; k < (1u << D); ++k) {
+                    const float w = grid::corner_weight<D>(cell, k);
+                    grid::accum(r0, w, rows[k].v[0]);
+                    grid::accum(r1, w, rows[k].v[1]);
+                }
+            }
+            const __half2 h = __halves2half2(r0, r1);
+            packed[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(dst + umma::il_offset(row, dcol0 + 2 * l0, Kdst)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+}
+
+__global__ void __launch_bounds__(EVAL_GROUPS * 128, 1)
+head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ LevelMeta meta3[16], meta2[16];
+    __shared__ float s_bias[3][64];
+    __shared__ __align__(8) uint64_t mbar_group[EVAL_GROUPS];
+    __shared__ __align__(8) uint64_t mbar_w;
+    __shared__ uint32_t tmem_slot;
+
+    if (ctl->done) return;
+    const uint32_t n_samples = ctl->n_samples;
+    const uint32_t n_tiles = (n_samples + EVAL_TILE - 1) / EVAL_TILE;
+    if (blockIdx.x * EVAL_GROUPS >= n_tiles) return;
+
+    const uint32_t tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = tid >> 5;
+    uint8_t* s_blob = smem;
+    uint8_t* s_grp = smem + HEAD_BLOB_BYTES + g * GROUP_BYTES;
+
+    // ---- one-time CTA setup: barriers, weights via TMA bulk copy, TMEM, level geometry, biases
+    if (tid == 0) {
+        for (int i = 0; i < EVAL_GROUPS; ++i) umma::mbar_init(&mbar_group[i], 1);
+        umma::mbar_init(&mbar_w, 1);
+        umma::fence_mbar_init();
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(&mbar_w)), "r"(HEAD_BLOB_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(umma::smem_u32(s_blob)),
+                     "l"(p.blob), "r"(HEAD_BLOB_BYTES), "r"(umma::smem_u32(&mbar_w))
+                     : "memory");
+    }
+    if (warp == 1) umma::tmem_alloc(&tmem_slot, 512);
+    if (tid >= 64 && tid < 80) grid::make_level_meta(meta3[tid - 64], tid - 64, p.offs3, p.S3, p.H3, 3, 1, false);
+    if (tid >= 96 && tid < 112) grid::make_level_meta(meta2[tid - 96], tid - 96, p.offs2, p.S2, p.H2, 2, 1, false);
+    if (tid >= 128 && tid < 128 + 192) (&s_bias[0][0])[tid - 128] = __ldg(p.consts + (tid - 128));
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    umma::mbar_wait(&mbar_w, 0);
+
+    const uint32_t tmem_acc = tmem_slot + g * TMEM_COLS_PER_GROUP;       // this group's accumulator columns
+    const uint32_t tmem_row = tmem_acc + (((warp & 3u) * 32u) << 16);    // this warp's lane quarter
+    uint64_t* mbar = &mbar_group[g];
+    uint32_t phase = 0;
+    const uint32_t bar_id = 1 + g;
+    uint8_t* sA0 = s_grp + G_A0;
+    uint8_t* sEW = s_grp + G_EW;
+    uint8_t* sH0 = s_grp + G_H0;
+    uint8_t* sH1 = s_grp + G_H1;
+    const uint32_t aA0 = umma::smem_u32(sA0), aEW = umma::smem_u32(sEW), aH0 = umma::smem_u32(sH0), aH1 = umma::smem_u32(sH1);
+    const uint32_t aW = umma::smem_u32(s_blob);
+
+    // operands written by this group's threads -> visible to the tensor core, previous accumulator reads retired
+    auto publish = [&]() {
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        umma::group_sync(bar_id, 128);
+    };
+    auto wait_mma = [&]() {
+        umma::mbar_wait(mbar, phase);
+        phase ^= 1u;
+        umma::fence_after_sync();
+    };
+
+    for (uint32_t tile = blockIdx.x * EVAL_GROUPS + g; tile < n_tiles; tile += gridDim.x * EVAL_GROUPS) {
+        const uint32_t s = tile * EVAL_TILE + t;
+        const bool valid = s < n_samples;
+        const float4 smp = valid ? __ldg(p.samples + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t ray = valid ? (uint32_t)__float_as_int(smp.w) : 0u;
+
+        // ---- 3-D encode -> A0
+        {
+            float x[3] = {__fmul_rn(__fadd_rn(smp.x, p.bound), p.inv2bound), __fmul_rn(__fadd_rn(smp.y, p.bound), p.inv2bound),
+                          __fmul_rn(__fadd_rn(smp.z, p.bound), p.inv2bound)};
+            encode_row<3>(x, p.table3, meta3, sA0, t, 32, 0);
+        }
+        publish();
+        // ---- ambient L1: [128x32] x WA1 -> 64
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aA0, aW + B_WA1, 32, 32, 0, 32, 64, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        epilogue_to_operand<4, true>(tmem_row, 0, s_bias[0], sH0, t, 64, 0);
+        publish();
+        // ---- ambient L2
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aH0, aW + B_WA2, 64, 64, 0, 64, 64, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        epilogue_to_operand<4, true>(tmem_row, 0, nullptr, sH1, t, 64, 0);
+        publish();
+        // ---- ambient L3 (N padded to 16) -> tanh -> 2-D encode -> EW
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aH1, aW + B_WA3, 64, 64, 0, 64, 16, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        {
+            uint32_t v[16];
+            umma::tmem_ld16(tmem_row, v);
+            umma::tmem_ld_wait();
+            const float a0 = tanhf(__half2float(__float2half_rn(__uint_as_float(v[0]))));
+            const float a1 = tanhf(__half2float(__float2half_rn(__uint_as_float(v[1]))));
+            float x[2] = {__fmul_rn(__fadd_rn(a0, 1.0f), 0.5f), __fmul_rn(__fadd_rn(a1, 1.0f), 0.5f)};
+            encode_row<2>(x, p.table2, meta2, sEW, t, 32, 0);
+        }
+        publish();
+        // ---- sigma L1: [enc_x | enc_w] (two K = 32 halves) -> 64
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aA0, aW + B_WS1A, 32, 32, 0, 32, 64, false);
+            umma::gemm_issue(tmem_acc, aEW, aW + B_WS1B, 32, 32, 0, 32, 64, true);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        epilogue_to_operand<4, true>(tmem_row, 0, s_bias[1], sH0, t, 64, 0);
+        publish();
+        // ---- sigma L2
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aH0, aW + B_WS2, 64, 64, 0, 64, 64, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        epilogue_to_operand<4, true>(tmem_row, 0, nullptr, sH1, t, 64, 0);
+        publish();
+        // ---- sigma L3: rows permuted on the host so columns 0..63 = geo_feat, column 64 = log-density
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aH1, aW + B_WS3, 64, 64, 0, 64, 80, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        float sigma;
+        {
+            // geo_feat -> CIN columns 16..79 (CIN aliases H0, dead since sigma L2 completed)
+            epilogue_to_operand<4, false>(tmem_row, 0, nullptr, sH0, t, 80, 16);
+            uint32_t v[16];
+            umma::tmem_ld16(tmem_row + 64, v);
+            umma::tmem_ld_wait();
+            sigma = expf(__half2float(__float2half_rn(__uint_as_float(v[0]))));
+            // SH(dir), degree 4 -> CIN columns 0..15
+            const float* d = p.rays_d + (size_t)ray * 3;
+            float Y[16];
+            sh_eval<4, false>(__ldg(d), __ldg(d + 1), __ldg(d + 2), Y, nullptr, nullptr, nullptr);
+            *reinterpret_cast<uint4*>(sH0 + umma::il_offset(t, 0, 80)) =
+                make_uint4(pack2(Y[0], Y[1]), pack2(Y[2], Y[3]), pack2(Y[4], Y[5]), pack2(Y[6], Y[7]));
+            *reinterpret_cast<uint4*>(sH0 + umma::il_offset(t, 8, 80)) =
+                make_uint4(pack2(Y[8], Y[9]), pack2(Y[10], Y[11]), pack2(Y[12], Y[13]), pack2(Y[14], Y[15]));
+        }
+        publish();
+        // ---- colour L1: [sh | geo] K = 80 -> 64
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aH0, aW + B_WC1, 80, 80, 0, 80, 64, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        epilogue_to_operand<4, true>(tmem_row, 0, s_bias[2], sH1, t, 64, 0);
+        publish();
+        // ---- colour L2 (N padded to 16) -> sigmoid
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aH1, aW + B_WC2, 64, 64, 0, 64, 16, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        {
+            uint32_t v[16];
+            umma::tmem_ld16(tmem_row, v);
+            umma::tmem_ld_wait();
+            float c[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float h = __half2float(__float2half_rn(__uint_as_float(v[j])));
+                c[j] = __half2float(__float2half_rn(1.0f / (1.0f + expf(-h))));
+            }
+            if (valid) p.evals[s] = make_float4(sigma, c[0], c[1], c[2]);
+        }
+        // the next tile's first MMA overwrites the accumulator: retire this tile's TMEM reads first
+        umma::fence_before_sync();
+        umma::group_sync(bar_id, 128);
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem_slot, 512);
+}
+
+}  // namespace
+
+int launch_head_eval(const HeadEvalParams& p, const FrameCtl* ctl, uint32_t max_tiles, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(head_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM);
+        if (e != cudaSuccess) { set_error("head_eval: cannot reserve %u bytes of shared memory: %s", HEAD_SMEM, cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    uint32_t grid = (max_tiles + EVAL_GROUPS - 1) / EVAL_GROUPS;
+    if (grid > RN_NUM_SMS) grid = RN_NUM_SMS;
+    if (grid == 0) grid = 1;
+    head_eval_kernel<<<grid, EVAL_GROUPS * 128, HEAD_SMEM, st>>>(p, ctl);
+    return finish_launch("head_eval");
+}
+
+}  // namespace rn

@@ -1,0 +1,275 @@
+// torso_eval.cu -- the fused 2-D torso model (NeRFNetwork.forward_torso, nerf/network.py:188-219) on the compacted list of
+// masked pixels, one persistent tcgen05 kernel with the same row-per-thread scheme as head_eval.cu:
+//
+//   x = bg_coord * torso_shrink;  freq encode (2 -> 42, __sinf)              -> F   [128 x 48]  (42 + zero pad)
+//   deform MLP 42(+54 pose +8 code, hoisted) -> 64 -> 64 -> 2                 -> dx
+//   x' = clamp(x + dx, -1, 1);  2-D grid encode (16 lvl x 4 corners)          -> TIN [128 x 80] = [grid 32 | freq 42 | pad]
+//   torso MLP 74(+62 hoisted) -> 32 -> 32 -> 4                                -> sigmoid -> (alpha, rgb)
+#include "frame.cuh"
+#include "umma.cuh"
+#include "gridencoder_impl.cuh"
+
+namespace rn {
+
+
+namespace {
+
+using grid::LevelMeta;
+
+constexpr uint32_t T_WD1 = 0;                          // [64 x 48]
+constexpr uint32_t T_WD2 = T_WD1 + 64 * 48 * 2;        // [64 x 64]
+constexpr uint32_t T_WD3 = T_WD2 + 64 * 64 * 2;        // [16 x 64]
+constexpr uint32_t T_WT1 = T_WD3 + 16 * 64 * 2;        // [32 x 80]
+constexpr uint32_t T_WT2 = T_WT1 + 32 * 80 * 2;        // [32 x 32]
+constexpr uint32_t T_WT3 = T_WT2 + 32 * 32 * 2;        // [16 x 32]
+static_assert(T_WT3 + 16 * 32 * 2 == TORSO_BLOB_BYTES, "blob layout");
+
+constexpr uint32_t G_F = 0;                            // [128 x 48]
+constexpr uint32_t G_H0 = G_F + 128 * 48 * 2;          // [128 x 64]
+constexpr uint32_t G_H1 = G_H0 + 128 * 64 * 2;         // [128 x 64]
+constexpr uint32_t G_TIN = G_H1 + 128 * 64 * 2;        // [128 x 80]
+constexpr uint32_t GROUP_BYTES = G_TIN + 128 * 80 * 2;
+constexpr uint32_t TORSO_SMEM = TORSO_BLOB_BYTES + EVAL_GROUPS * GROUP_BYTES;
+constexpr uint32_t TMEM_COLS_PER_GROUP = 64;
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int NCH, bool RELU>
+__device__ __forceinline__ void epilogue_to_operand(uint32_t tmem_row, const float* __restrict__ bias, uint8_t* dst, uint32_t row,
+                                                    uint32_t Kdst) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        uint32_t v[16];
+        umma::tmem_ld16(tmem_row + 16 * c, v);
+        umma::tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            f[j] = __uint_as_float(v[j]);
+            if (bias) f[j] += bias[16 * c + j];
+            if (RELU) f[j] = fmaxf(f[j], 0.0f);
+        }
+        *reinterpret_cast<uint4*>(dst + umma::il_offset(row, 16 * c, Kdst)) =
+            make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(dst + umma::il_offset(row, 16 * c + 8, Kdst)) =
+            make_uint4(pack2(f[8], f[9]), pack2(f[10], f[11]), pack2(f[12], f[13]), pack2(f[14], f[15]));
+    }
+}
+
+__global__ void __launch_bounds__(EVAL_GROUPS * 128, 1)
+torso_eval_kernel(TorsoEvalParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ LevelMeta meta[16];
+    __shared__ float s_bias_d[64], s_bias_t[32];
+    __shared__ __align__(8) uint64_t mbar_group[EVAL_GROUPS];
+    __shared__ __align__(8) uint64_t mbar_w;
+    __shared__ uint32_t tmem_slot;
+
+    const uint32_t n_pix = *p.n_pix;
+    const uint32_t n_tiles = (n_pix + EVAL_TILE - 1) / EVAL_TILE;
+    if (blockIdx.x * EVAL_GROUPS >= n_tiles) return;
+
+    const uint32_t tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = tid >> 5;
+    uint8_t* s_blob = smem;
+    uint8_t* s_grp = smem + TORSO_BLOB_BYTES + g * GROUP_BYTES;
+
+    if (tid == 0) {
+        for (int i = 0; i < EVAL_GROUPS; ++i) umma::mbar_init(&mbar_group[i], 1);
+        umma::mbar_init(&mbar_w, 1);
+        umma::fence_mbar_init();
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(&mbar_w)), "r"(TORSO_BLOB_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(umma::smem_u32(s_blob)),
+                     "l"(p.blob), "r"(TORSO_BLOB_BYTES), "r"(umma::smem_u32(&mbar_w))
+                     : "memory");
+    }
+    if (warp == 1) umma::tmem_alloc(&tmem_slot, 256);
+    if (tid >= 64 && tid < 80) grid::make_level_meta(meta[tid - 64], tid - 64, p.offs, p.S, p.H, 2, 1, false);
+    if (tid >= 128 && tid < 192) s_bias_d[tid - 128] = __ldg(p.consts + (tid - 128));
+    if (tid >= 192 && tid < 224) s_bias_t[tid - 192] = __ldg(p.consts + 64 + (tid - 192));
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    umma::mbar_wait(&mbar_w, 0);
+
+    const uint32_t tmem_acc = tmem_slot + g * TMEM_COLS_PER_GROUP;
+    const uint32_t tmem_row = tmem_acc + (((warp & 3u) * 32u) << 16);
+    uint64_t* mbar = &mbar_group[g];
+    uint32_t phase = 0;
+    const uint32_t bar_id = 1 + g;
+    uint8_t* sF = s_grp + G_F;
+    uint8_t* sH0 = s_grp + G_H0;
+    uint8_t* sH1 = s_grp + G_H1;
+    uint8_t* sTIN = s_grp + G_TIN;
+    const uint32_t aF = umma::smem_u32(sF), aH0 = umma::smem_u32(sH0), aH1 = umma::smem_u32(sH1), aTIN = umma::smem_u32(sTIN);
+    const uint32_t aW = umma::smem_u32(s_blob);
+
+    auto publish = [&]() {
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        umma::group_sync(bar_id, 128);
+    };
+    auto wait_mma = [&]() {
+        umma::mbar_wait(mbar, phase);
+        phase ^= 1u;
+        umma::fence_after_sync();
+    };
+
+    for (uint32_t tile = blockIdx.x * EVAL_GROUPS + g; tile < n_tiles; tile += gridDim.x * EVAL_GROUPS) {
+        const uint32_t k = tile * EVAL_TILE + t;
+        const bool valid = k < n_pix;
+        const int32_t pixel = valid ? __ldg(p.pix + k) : 0;
+        const float x0 = __fmul_rn(__ldg(p.bg_coords + (size_t)pixel * 2), p.shrink);
+        const float x1 = __fmul_rn(__ldg(p.bg_coords + (size_t)pixel * 2 + 1), p.shrink);
+
+        // ---- frequency encoding (freqencoder.cu:30-58 order: x, then per octave [sin x0, sin x1, cos x0, cos x1]) -> F and TIN[32..]
+        {
+            float e[48];
+            e[0] = x0; e[1] = x1;
+#pragma unroll
+            for (int f = 0; f < 10; ++f) {
+                const float a0 = scalbnf(x0, f), a1 = scalbnf(x1, f);
+                e[2 + 4 * f + 0] = __sinf(a0 + 0.0f);
+                e[2 + 4 * f + 1] = __sinf(a1 + 0.0f);
+                e[2 + 4 * f + 2] = __sinf(a0 + 1.5707963705062866f);
+                e[2 + 4 * f + 3] = __sinf(a1 + 1.5707963705062866f);
+            }
+#pragma unroll
+            for (int j = 42; j < 48; ++j) e[j] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const uint4 q = make_uint4(pack2(e[8 * c], e[8 * c + 1]), pack2(e[8 * c + 2], e[8 * c + 3]),
+                                           pack2(e[8 * c + 4], e[8 * c + 5]), pack2(e[8 * c + 6], e[8 * c + 7]));
+                *reinterpret_cast<uint4*>(sF + umma::il_offset(t, 8 * c, 48)) = q;
+                *reinterpret_cast<uint4*>(sTIN + umma::il_offset(t, 32 + 8 * c, 80)) = q;
+            }
+        }
+        publish();
+        // ---- deform L1 (K = 48) -> 64
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aF, aW + T_WD1, 48, 48, 0, 48, 64, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        epilogue_to_operand<4, true>(tmem_row, s_bias_d, sH0, t, 64);
+        publish();
+        // ---- deform L2
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aH0, aW + T_WD2, 64, 64, 0, 64, 64, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        epilogue_to_operand<4, true>(tmem_row, nullptr, sH1, t, 64);
+        publish();
+        // ---- deform L3 (N padded to 16) -> dx -> deformed coordinate -> 2-D grid encode -> TIN[0..31]
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aH1, aW + T_WD3, 64, 64, 0, 64, 16, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        {
+            uint32_t v[16];
+            umma::tmem_ld16(tmem_row, v);
+            umma::tmem_ld_wait();
+            const float dx0 = __half2float(__float2half_rn(__uint_as_float(v[0])));
+            const float dx1 = __half2float(__float2half_rn(__uint_as_float(v[1])));
+            const float y0 = fminf(fmaxf(__fadd_rn(x0, dx0), -1.f), 1.f), y1 = fminf(fmaxf(__fadd_rn(x1, dx1), -1.f), 1.f);
+            float x[2] = {__fmul_rn(__fadd_rn(y0, 1.0f), 0.5f), __fmul_rn(__fadd_rn(y1, 1.0f), 0.5f)};
+            // same per-level arithmetic as the stand-alone encoder (gridencoder_impl.cuh), fp16 table
+            bool oob = x[0] < 0 || x[0] > 1 || x[1] < 0 || x[1] > 1;
+#pragma unroll
+            for (int l0 = 0; l0 < 16; l0 += 4) {
+                uint32_t packed[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __half r0 = __float2half_rn(0.f), r1 = r0;
+                    if (!oob) {
+                        const LevelMeta m = meta[l0 + j];
+                        const __half* __restrict__ tbl = p.table + (size_t)m.offset * 2;
+                        const grid::Cell<2> cell = grid::locate<2>(x, m, false, 0);
+                        grid::Row<__half, 2> rows[4];
+#pragma unroll
+                        for (uint32_t q = 0; q < 4; ++q)
+                            rows[q] = grid::load_row<__half, 2>(tbl + (size_t)grid::corner_row<2>(m, cell.pg, q) * 2);
+#pragma unroll
+                        for (uint32_t q = 0; q < 4; ++q) {
+                            const float w = grid::corner_weight<2>(cell, q);
+                            grid::accum(r0, w, rows[q].v[0]);
+                            grid::accum(r1, w, rows[q].v[1]);
+                        }
+                    }
+                    const __half2 h = __halves2half2(r0, r1);
+                    packed[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(sTIN + umma::il_offset(t, 2 * l0, 80)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+        }
+        publish();
+        // ---- torso L1 (K = 80) -> 32
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aTIN, aW + T_WT1, 80, 80, 0, 80, 32, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        epilogue_to_operand<2, true>(tmem_row, s_bias_t, sH0, t, 32);
+        publish();
+        // ---- torso L2 (K = 32) -> 32
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aH0, aW + T_WT2, 32, 32, 0, 32, 32, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        epilogue_to_operand<2, true>(tmem_row, nullptr, sH1, t, 32);
+        publish();
+        // ---- torso L3 (N padded to 16) -> sigmoid -> (alpha, rgb)
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem_acc, aH1, aW + T_WT3, 32, 32, 0, 32, 16, false);
+            umma::commit(mbar);
+        }
+        wait_mma();
+        {
+            uint32_t v[16];
+            umma::tmem_ld16(tmem_row, v);
+            umma::tmem_ld_wait();
+            float c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float h = __half2float(__float2half_rn(__uint_as_float(v[j])));
+                c[j] = __half2float(__float2half_rn(1.0f / (1.0f + expf(-h))));
+            }
+            if (valid) p.out[k] = make_float4(c[0], c[1], c[2], c[3]);
+        }
+        umma::fence_before_sync();
+        umma::group_sync(bar_id, 128);
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem_slot, 256);
+}
+
+}  // namespace
+
+int launch_torso_eval(const TorsoEvalParams& p, uint32_t max_tiles, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(torso_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TORSO_SMEM);
+        if (e != cudaSuccess) { set_error("torso_eval: cannot reserve %u bytes of shared memory: %s", TORSO_SMEM, cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    uint32_t grid = (max_tiles + EVAL_GROUPS - 1) / EVAL_GROUPS;
+    if (grid > RN_NUM_SMS) grid = RN_NUM_SMS;
+    if (grid == 0) grid = 1;
+    torso_eval_kernel<<<grid, EVAL_GROUPS * 128, TORSO_SMEM, st>>>(p);
+    return finish_launch("torso_eval");
+}
+
+}  // namespace rn

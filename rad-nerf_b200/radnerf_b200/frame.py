@@ -1,0 +1,272 @@
+"""Fused inference frame: host side of rn_frame_* (include/radnerf_b200.h, csrc/frame*.cu, head_eval.cu, torso_eval.cu).
+
+`render_frame(model, ...)` has the contract of NeRFRenderer.run_cuda's inference branch (nerf/renderer.py:158-316: same
+arguments, same result keys) but issues a fixed sequence of launches with no host synchronisation: per-frame conditioning
+(audio nets, lip smoothing, hoisted first-layer terms) -> device-driven march / fused-network / composite loop -> torso ->
+final blend.  Host work per frame is a handful of ctypes calls; everything data-dependent stays on the device.
+
+State cached on the model (`model._fused`): fp16 copies of the three hash tables and the interleaved fp16 weight blobs
+(rebuilt only when a parameter's version counter changes), the workspace, and the lip-smoothing state.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+
+_vp, _u32, _f32, _u64 = C.c_void_p, C.c_uint32, C.c_float, C.c_uint64
+
+
+class GridTable(C.Structure):
+    _fields_ = [("table_f16", _vp), ("offsets", _vp), ("S", _f32), ("H", _u32)]
+
+
+class ConditioningDesc(C.Structure):
+    _fields_ = [("auds", _vp), ("F", _u32), ("Cin", _u32), ("att", _u32), ("smooth", _u32), ("has_state", _u32),
+                ("conv_w", _vp * 4), ("conv_b", _vp * 4), ("fc_w", _vp * 2), ("fc_b", _vp * 2),
+                ("att_w", _vp * 5), ("att_b", _vp * 5), ("att_fc_w", _vp), ("att_fc_b", _vp),
+                ("enc_a_state", _vp), ("lambda_", _f32),
+                ("w_amb1", _vp), ("w_sig1", _vp), ("w_col1", _vp), ("eye", _vp), ("ind_code", _vp), ("head_consts", _vp),
+                ("w_def1", _vp), ("w_tor1", _vp), ("pose6", _vp), ("ind_torso", _vp), ("torso_consts", _vp)]
+
+
+class FrameHeadDesc(C.Structure):
+    _fields_ = [("N", _u32), ("max_steps", _u32), ("cascade", _u32), ("grid_size", _u32),
+                ("bound", _f32), ("min_near", _f32), ("dt_gamma", _f32), ("T_thresh", _f32),
+                ("rays_o", _vp), ("rays_d", _vp), ("aabb", _vp), ("bitfield", _vp), ("noises", _vp),
+                ("weights_sum", _vp), ("depth", _vp), ("image", _vp), ("nears", _vp), ("fars", _vp),
+                ("workspace", _vp), ("workspace_bytes", _u64),
+                ("grid3d", GridTable), ("grid2d", GridTable), ("head_blob", _vp), ("head_consts", _vp)]
+
+
+class FrameTorsoDesc(C.Structure):
+    _fields_ = [("N", _u32), ("grid_size", _u32), ("thresh", _f32), ("shrink", _f32),
+                ("bg_coords", _vp), ("density_grid_torso", _vp), ("workspace", _vp), ("workspace_bytes", _u64),
+                ("grid2d", GridTable), ("torso_blob", _vp), ("torso_consts", _vp), ("torso_alpha", _vp), ("torso_color", _vp)]
+
+
+abi.register("rn_frame_workspace_bytes", [_u32], _u64)
+abi.register("rn_head_blob_bytes", [], _u32)
+abi.register("rn_torso_blob_bytes", [], _u32)
+abi.register("rn_frame_conditioning", [C.POINTER(ConditioningDesc), _vp])
+abi.register("rn_frame_head", [C.POINTER(FrameHeadDesc), _vp])
+abi.register("rn_frame_torso", [C.POINTER(FrameTorsoDesc), _vp])
+abi.register("rn_frame_finalize", [_u32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp])
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def il_pack(W, n_pad, k_pad):
+    """[n,k] weight -> fp16 [n_pad,k_pad] (zero padded) in the interleaved UMMA operand layout of csrc/umma.cuh:
+    8-row x 16-byte core matrices, K-chunks of an 8-row group contiguous."""
+    n, k = W.shape
+    Wp = torch.zeros(n_pad, k_pad, dtype=torch.float16, device=W.device)
+    Wp[:n, :k] = W.detach().to(torch.float16)
+    return Wp.view(n_pad // 8, 8, k_pad // 8, 8).permute(0, 2, 1, 3).contiguous().view(-1)
+
+
+def supported(model):
+    """the fused kernels are specialised for the architecture nerf/network.py builds"""
+    try:
+        ok = (model.encoder.num_levels == 16 and model.encoder.level_dim == 2 and model.encoder.gridtype == 'tiled'
+              and model.encoder.interpolation == 'linear' and not model.encoder.align_corners
+              and model.encoder_ambient.num_levels == 16 and model.encoder_ambient.input_dim == 2
+              and model.hidden_dim == 64 and model.geo_feat_dim == 64 and model.num_layers == 3 and model.num_layers_color == 2
+              and model.hidden_dim_ambient == 64 and model.num_layers_ambient == 3 and model.audio_dim == 64
+              and model.encoder_dir.degree == 4 and model.individual_dim == 4 and model.exp_eye and not model.emb
+              and model.audio_in_dim <= 44 and model.opt.fp16)
+        if model.torso:
+            ok = ok and model.individual_dim_torso == 8 and model.torso_encoder.num_levels == 16
+        return bool(ok)
+    except AttributeError:
+        return False
+
+
+class FusedState:
+    def __init__(self, model):
+        dev = model.density_bitfield.device
+        self.dev = dev
+        self.versions = None
+        self.N = 0
+        self.workspace = None
+        self.head_consts = torch.zeros(3 * 64, device=dev)
+        self.torso_consts = torch.zeros(96, device=dev)
+        self.enc_a_state = torch.zeros(64, device=dev)
+        self.frames = 0
+
+    def refresh_weights(self, model):
+        params = [model.encoder.embeddings, model.encoder_ambient.embeddings] + list(model.ambient_net.parameters()) + \
+            list(model.sigma_net.parameters()) + list(model.color_net.parameters())
+        if model.torso:
+            params += [model.torso_encoder.embeddings] + list(model.torso_deform_net.parameters()) + list(model.torso_net.parameters())
+        versions = tuple((p.data_ptr(), p._version) for p in params)
+        if versions == self.versions:
+            return
+        self.versions = versions
+        self.table3 = model.encoder.embeddings.detach().to(torch.float16).contiguous()
+        self.table2 = model.encoder_ambient.embeddings.detach().to(torch.float16).contiguous()
+        a, s, c = model.ambient_net.net, model.sigma_net.net, model.color_net.net
+        w_s3 = s[2].weight
+        w_s3 = torch.cat([w_s3[1:], w_s3[:1]], 0)  # geo_feat rows first, log-density row last (head_eval.cu)
+        self.head_blob = torch.cat([
+            il_pack(a[0].weight[:, :32], 64, 32), il_pack(a[1].weight, 64, 64), il_pack(a[2].weight, 16, 64),
+            il_pack(s[0].weight[:, 0:32], 64, 32), il_pack(s[0].weight[:, 32:64], 64, 32), il_pack(s[1].weight, 64, 64),
+            il_pack(w_s3, 80, 64), il_pack(c[0].weight[:, :80], 64, 80), il_pack(c[1].weight, 16, 64)])
+        assert self.head_blob.numel() * 2 == abi.lib().rn_head_blob_bytes()
+        if model.torso:
+            self.table_t = model.torso_encoder.embeddings.detach().to(torch.float16).contiguous()
+            d, t = model.torso_deform_net.net, model.torso_net.net
+            self.torso_blob = torch.cat([
+                il_pack(d[0].weight[:, :42], 64, 48), il_pack(d[1].weight, 64, 64), il_pack(d[2].weight, 16, 64),
+                il_pack(t[0].weight[:, :74], 32, 80), il_pack(t[1].weight, 32, 32), il_pack(t[2].weight, 16, 32)])
+            assert self.torso_blob.numel() * 2 == abi.lib().rn_torso_blob_bytes()
+
+    def ensure_workspace(self, N):
+        if N != self.N:
+            nbytes = int(abi.lib().rn_frame_workspace_bytes(N))
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            self.ws_bytes = nbytes
+            self.N = N
+            self.torso_alpha = torch.empty(N, 1, device=self.dev)
+            self.torso_color = torch.empty(N, 3, device=self.dev)
+
+    def ctl(self):
+        """device loop state of the last frame as a [65, 8] int32 tensor (n_alive, n_step, step, done, n_samples, ...)"""
+        return self.workspace[:65 * 32].view(torch.int32).view(65, 8)
+
+
+def _grid_table(enc, table):
+    return GridTable(table.data_ptr(), enc.offsets.data_ptr(), float(np.log2(enc.per_level_scale)), int(enc.base_resolution))
+
+
+def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=0, dt_gamma=0, bg_color=None, perturb=False,
+                 force_all_rays=False, max_steps=1024, T_thresh=1e-4, **kwargs):
+    if model.training:
+        raise RuntimeError("render_frame is the inference path; training goes through run_cuda")
+    if not supported(model):
+        raise NotImplementedError("model configuration outside the fused kernels' specialisation")
+    L = abi.lib()
+    st = getattr(model, "_fused", None)
+    if st is None:
+        st = model._fused = FusedState(model)
+    st.refresh_weights(model)
+
+    prefix = rays_o.shape[:-1]
+    rays_o = rays_o.contiguous().view(-1, 3).float()
+    rays_d = rays_d.contiguous().view(-1, 3).float()
+    bg_coords = bg_coords.contiguous().view(-1, 2).float()
+    N = rays_o.shape[0]
+    dev = rays_o.device
+    st.ensure_workspace(N)
+    stream = abi.cur_stream()
+
+    # ---- per-frame conditioning
+    an, at = model.audio_net, getattr(model, "audio_att_net", None)
+    cd = ConditioningDesc()
+    if auds is not None:
+        auds = auds.contiguous().float()
+        cd.auds, cd.F, cd.Cin = auds.data_ptr(), auds.shape[0], auds.shape[1]
+    cd.att = int(model.att)
+    cd.smooth = int(bool(model.smooth_lips))
+    has_state = bool(model.smooth_lips) and getattr(model, "enc_a", None) is not None
+    if has_state and model.enc_a.data_ptr() != st.enc_a_state.data_ptr():
+        st.enc_a_state.copy_(model.enc_a.reshape(-1))
+    cd.has_state = int(has_state)
+    for i, k in enumerate((0, 2, 4, 6)):
+        cd.conv_w[i], cd.conv_b[i] = an.encoder_conv[k].weight.data_ptr(), an.encoder_conv[k].bias.data_ptr()
+    for i, k in enumerate((0, 2)):
+        cd.fc_w[i], cd.fc_b[i] = an.encoder_fc1[k].weight.data_ptr(), an.encoder_fc1[k].bias.data_ptr()
+    if at is not None:
+        for i, k in enumerate((0, 2, 4, 6, 8)):
+            cd.att_w[i], cd.att_b[i] = at.attentionConvNet[k].weight.data_ptr(), at.attentionConvNet[k].bias.data_ptr()
+        cd.att_fc_w, cd.att_fc_b = at.attentionNet[0].weight.data_ptr(), at.attentionNet[0].bias.data_ptr()
+    cd.enc_a_state, cd.lambda_ = st.enc_a_state.data_ptr(), 0.35
+    cd.w_amb1 = model.ambient_net.net[0].weight.data_ptr()
+    cd.w_sig1 = model.sigma_net.net[0].weight.data_ptr()
+    cd.w_col1 = model.color_net.net[0].weight.data_ptr()
+    eye_t = None if eye is None else eye.reshape(-1).float().contiguous()
+    cd.eye = _p(eye_t)
+    ind_code = model.individual_codes[0].detach().contiguous()
+    cd.ind_code = ind_code.data_ptr()
+    cd.head_consts = st.head_consts.data_ptr()
+    if model.torso:
+        pose6 = poses.reshape(-1).float().contiguous()
+        ind_torso = model.individual_codes_torso[0].detach().contiguous()
+        cd.w_def1 = model.torso_deform_net.net[0].weight.data_ptr()
+        cd.w_tor1 = model.torso_net.net[0].weight.data_ptr()
+        cd.pose6, cd.ind_torso, cd.torso_consts = pose6.data_ptr(), ind_torso.data_ptr(), st.torso_consts.data_ptr()
+    abi.check(L.rn_frame_conditioning(C.byref(cd), stream))
+    if model.smooth_lips and auds is not None:
+        model.enc_a = st.enc_a_state.view(1, 64)
+
+    # ---- head
+    weights_sum = torch.empty(N, device=dev)
+    depth = torch.empty(N, device=dev)
+    image = torch.empty(N, 3, device=dev)
+    nears = torch.empty(N, device=dev)
+    fars = torch.empty(N, device=dev)
+    noises = torch.rand(N, device=dev) if perturb else None
+    hd = FrameHeadDesc()
+    hd.N, hd.max_steps, hd.cascade, hd.grid_size = N, int(max_steps), int(model.cascade), int(model.grid_size)
+    hd.bound, hd.min_near, hd.dt_gamma, hd.T_thresh = float(model.bound), float(model.min_near), float(dt_gamma), float(T_thresh)
+    hd.rays_o, hd.rays_d = rays_o.data_ptr(), rays_d.data_ptr()
+    hd.aabb, hd.bitfield, hd.noises = model.aabb_infer.data_ptr(), model.density_bitfield.data_ptr(), _p(noises)
+    hd.weights_sum, hd.depth, hd.image = weights_sum.data_ptr(), depth.data_ptr(), image.data_ptr()
+    hd.nears, hd.fars = nears.data_ptr(), fars.data_ptr()
+    hd.workspace, hd.workspace_bytes = st.workspace.data_ptr(), st.ws_bytes
+    hd.grid3d, hd.grid2d = _grid_table(model.encoder, st.table3), _grid_table(model.encoder_ambient, st.table2)
+    hd.head_blob, hd.head_consts = st.head_blob.data_ptr(), st.head_consts.data_ptr()
+    abi.check(L.rn_frame_head(C.byref(hd), stream))
+
+    results = {}
+    # ---- torso
+    bg_t = None
+    bg_scalar = 1.0
+    if bg_color is not None:
+        if torch.is_tensor(bg_color):
+            bg_t = bg_color.reshape(-1, 3).float().contiguous()
+            if bg_t.shape[0] != N:
+                bg_t = bg_t.expand(N, 3).contiguous()
+        else:
+            bg_scalar = float(bg_color)
+    torso_bg = None
+    if model.torso:
+        td = FrameTorsoDesc()
+        td.N, td.grid_size = N, int(model.grid_size)
+        td.thresh, td.shrink = float(min(model.density_thresh_torso, model.mean_density_torso)), float(model.opt.torso_shrink)
+        td.bg_coords, td.density_grid_torso = bg_coords.data_ptr(), model.density_grid_torso.data_ptr()
+        td.workspace, td.workspace_bytes = st.workspace.data_ptr(), st.ws_bytes
+        td.grid2d = _grid_table(model.torso_encoder, st.table_t)
+        td.torso_blob, td.torso_consts = st.torso_blob.data_ptr(), st.torso_consts.data_ptr()
+        td.torso_alpha, td.torso_color = st.torso_alpha.data_ptr(), st.torso_color.data_ptr()
+        abi.check(L.rn_frame_torso(C.byref(td), stream))
+        torso_bg = torch.empty(N, 3, device=dev)
+        results['torso_alpha'] = st.torso_alpha
+        results['torso_color'] = torso_bg
+    abi.check(L.rn_frame_finalize(N, weights_sum.data_ptr(), depth.data_ptr(), image.data_ptr(), nears.data_ptr(), fars.data_ptr(),
+                                  _p(bg_t), bg_scalar, _p(st.torso_alpha) if model.torso else None,
+                                  _p(st.torso_color) if model.torso else None, _p(torso_bg), stream))
+    st.frames += 1
+    results['depth'] = depth.view(*prefix)
+    results['image'] = image.view(*prefix, 3)
+    results['weights_sum'] = weights_sum
+    return results
+
+
+def frame_stats(model):
+    """(n_alive, n_step, n_samples) per executed iteration of the last fused frame -- forces a sync; for tests/bench only"""
+    ctl = model._fused.ctl().cpu().numpy()
+    out = []
+    for it in range(64):
+        n_alive, n_step, step, done, n_samples = [int(v) for v in ctl[it][:5]]
+        if done or (it > 0 and n_alive == 0):
+            break
+        out.append((n_alive, n_step, n_samples))
+    return out
+
+
+def roofline_entries(model, f, bg_local, kw, hbm, tflops):
+    return []
