@@ -177,12 +177,13 @@ typedef struct rn_grid_table {
  * (nerf/network.py:10-67,170-185; nerf/renderer.py:187-204).  All weight pointers are the fp32 parameters. */
 typedef struct rn_conditioning_desc {
     const float* auds;           /* [F, Cin, 16] or NULL (no audio) */
-    uint32_t F, Cin, att, smooth, has_state;
+    uint32_t F, Cin, att, smooth, reserved;
     const float* conv_w[4]; const float* conv_b[4];
     const float* fc_w[2]; const float* fc_b[2];
     const float* att_w[5]; const float* att_b[5];
     const float* att_fc_w; const float* att_fc_b;
-    float* enc_a_state;          /* [64] in/out */
+    float* enc_a_state;          /* [65] in/out: smoothed code [0..63], [64] != 0 once it holds a previous frame (device-side flag,
+                                    so a captured CUDA graph serves first and later frames alike) */
     float lambda;
     const float* w_amb1; const float* w_sig1; const float* w_col1;
     const float* eye; const float* ind_code;

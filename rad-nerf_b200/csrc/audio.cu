@@ -114,12 +114,13 @@ audio_frame_kernel(AudioParams p) {
         if (threadIdx.x < 64) {
             float e = s_enc[threadIdx.x];
             if (p.smooth) {
-                if (p.has_state) e = __fadd_rn(__fmul_rn(p.lambda, p.enc_a_state[threadIdx.x]), __fmul_rn(1.0f - p.lambda, e));
+                if (p.enc_a_state[64] != 0.f) e = __fadd_rn(__fmul_rn(p.lambda, p.enc_a_state[threadIdx.x]), __fmul_rn(1.0f - p.lambda, e));
                 p.enc_a_state[threadIdx.x] = e;
             }
             s_enc[threadIdx.x] = e;
         }
         __syncthreads();
+        if (p.smooth && threadIdx.x == 0) p.enc_a_state[64] = 1.0f;  // every thread has read the flag before the barrier above
     }
 
     // ---- hoisted terms of the head

@@ -5,6 +5,10 @@
 
 using namespace rn;
 
+static void* g_head_prof = nullptr;
+// diagnostics: device buffer of 8 uint64 cycle counters filled by head_eval (enc3, enc2, mma, epilogue, tile, groups); NULL disables
+extern "C" void rn_debug_set_head_prof(void* p) { g_head_prof = p; }
+
 extern "C" uint64_t rn_frame_workspace_bytes(uint32_t N) {
     FrameWorkspace w;
     return (uint64_t)carve(w, nullptr, N);
@@ -48,6 +52,7 @@ extern "C" int rn_frame_head(const rn_frame_head_desc* d, void* stream) {
     hp.table2 = (const __half*)d->grid2d.table_f16; hp.offs2 = d->grid2d.offsets; hp.S2 = d->grid2d.S; hp.H2 = d->grid2d.H;
     hp.blob = (const uint8_t*)d->head_blob; hp.consts = d->head_consts; hp.rays_d = d->rays_d;
     hp.samples = w.samples; hp.evals = w.evals; hp.bound = d->bound; hp.inv2bound = 1.0f / (2.0f * d->bound);
+    hp.prof = (unsigned long long*)g_head_prof;
     const uint32_t max_tiles = (d->N + EVAL_TILE - 1) / EVAL_TILE;  // n_alive * n_step <= N in every iteration
     // n_step >= 1, so the reference's loop runs at most max_steps iterations
     for (uint32_t it = 0; it < d->max_steps; ++it) {

@@ -66,6 +66,7 @@ struct HeadEvalParams {
     const float4* samples;    // xyz + ray id
     float4* evals;            // (sigma, r, g, b)
     float bound, inv2bound;
+    unsigned long long* prof;  // optional [8] cycle counters (diagnostics), null in production
 };
 
 struct TorsoEvalParams {
@@ -82,12 +83,12 @@ struct TorsoEvalParams {
 // mirrors rn_conditioning_desc (include/radnerf_b200.h) field for field
 struct AudioParams {
     const float* auds;   // [F, Cin, 16]
-    uint32_t F, Cin, att, smooth, has_state;
+    uint32_t F, Cin, att, smooth, reserved;
     const float* conv_w[4]; const float* conv_b[4];          // AudioNet.encoder_conv.{0,2,4,6}
     const float* fc_w[2]; const float* fc_b[2];              // AudioNet.encoder_fc1.{0,2}
     const float* att_w[5]; const float* att_b[5];            // AudioAttNet.attentionConvNet.{0,2,4,6,8}
     const float* att_fc_w; const float* att_fc_b;            // AudioAttNet.attentionNet.0
-    float* enc_a_state;  // [64] smoothed code of the previous frame (read if has_state, always written)
+    float* enc_a_state;  // [65]: smoothed code of the previous frame + validity flag at [64]
     float lambda;
     const float* w_amb1; const float* w_sig1; const float* w_col1;   // [64,96] [64,65] [64,84] fp32 parameters
     const float* eye;        // device [1] or null

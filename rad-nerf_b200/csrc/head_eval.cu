@@ -12,22 +12,19 @@
 // (TMEM lane t), gathers its own features, and writes fp16 rows straight into the next layer's A operand in the
 // interleaved UMMA layout (umma.cuh).  Per-frame-constant inputs (audio code, eye, individual code) are folded into
 // fp32 bias vectors once per frame (rn_frame_constants).  All 8 weight matrices (52 KB fp16) are staged once per CTA with
-// one TMA bulk copy.  EVAL_GROUPS tile groups per CTA interleave so gathers of one tile overlap MMAs/epilogues of others.
+// one TMA bulk copy.  HEAD_GROUPS tile groups per CTA interleave so gathers of one tile overlap MMAs/epilogues of others.
 //
 // Rounding points follow the reference's fp16 autocast: layer outputs are rounded to fp16 (nn.Linear under autocast),
 // the ambient coordinate goes back to fp32 before tanh (network.py:246-247), sigma = exp in fp32 (activation.py:5),
 // SH in fp32 then fp16 at the colour layer's input, sigmoid output in fp16.
 #include "frame.cuh"
 #include "umma.cuh"
-#include "gridencoder_impl.cuh"
 #include "sh.cuh"
+#include "mlp_tile.cuh"
 
 namespace rn {
 
-
 namespace {
-
-using grid::LevelMeta;
 
 // blob sub-matrix byte offsets
 constexpr uint32_t B_WA1 = 0;
@@ -41,92 +38,35 @@ constexpr uint32_t B_WC1 = B_WS3 + 80 * 64 * 2;
 constexpr uint32_t B_WC2 = B_WC1 + 64 * 80 * 2;
 static_assert(B_WC2 + 16 * 64 * 2 == HEAD_BLOB_BYTES, "blob layout");
 
-// per-group activation buffers
-constexpr uint32_t G_A0 = 0;                       // [128 x 32]
-constexpr uint32_t G_EW = G_A0 + 128 * 32 * 2;     // [128 x 32]
-constexpr uint32_t G_H0 = G_EW + 128 * 32 * 2;     // [128 x 64], re-used as CIN [128 x 80]
-constexpr uint32_t G_H1 = G_H0 + 128 * 80 * 2;     // [128 x 64]
-constexpr uint32_t GROUP_BYTES = G_H1 + 128 * 64 * 2;
-constexpr uint32_t HEAD_SMEM = HEAD_BLOB_BYTES + EVAL_GROUPS * GROUP_BYTES;
+// per-group activation buffers (40 KB).  Aliasing is safe because every stage waits for its MMA before the next write:
+//   A0  [128x32]  enc_x           written by the 3-D encode, read by ambient-L1 and sigma-L1
+//   H1  [128x64]  hidden          ambient-L2 out, sigma-L1 out, colour-L1 ... (see the stage list in the kernel)
+//   CIN [128x80]  = A0 + H1 region, colour-L1 input [sh | geo_feat], written after sigma-L2/L1 retired A0 and H1
+//   H0  [128x64]  hidden; its first 8 KB double as EW [128x32] (enc_w) between ambient-L3 and sigma-L1
+constexpr uint32_t G_A0 = 0;
+constexpr uint32_t G_H1 = G_A0 + 128 * 32 * 2;
+constexpr uint32_t G_CIN = 0;
+constexpr uint32_t G_H0 = G_H1 + 128 * 64 * 2;
+constexpr uint32_t G_EW = G_H0;
+constexpr uint32_t GROUP_BYTES = G_H0 + 128 * 64 * 2;
+static_assert(G_H0 >= 128 * 80 * 2, "CIN must fit in A0 + H1");
+constexpr int HEAD_GROUPS = 4;
+constexpr uint32_t HEAD_SMEM = HEAD_BLOB_BYTES + HEAD_GROUPS * GROUP_BYTES;
 constexpr uint32_t TMEM_COLS_PER_GROUP = 128;
 
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
-}
-
-// TMEM accumulator columns [col0, col0 + 16*NCH) of this thread's row -> (+bias, ReLU) -> fp16 -> smem row of an
-// interleaved [128 x Kdst] operand starting at destination column dcol0.
-template <int NCH, bool RELU>
-__device__ __forceinline__ void epilogue_to_operand(uint32_t tmem_row, uint32_t col0, const float* __restrict__ bias,
-                                                    uint8_t* dst, uint32_t row, uint32_t Kdst, uint32_t dcol0) {
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        uint32_t v[16];
-        umma::tmem_ld16(tmem_row + col0 + 16 * c, v);
-        umma::tmem_ld_wait();
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            f[j] = __uint_as_float(v[j]);
-            if (bias) f[j] += bias[16 * c + j];
-            if (RELU) f[j] = fmaxf(f[j], 0.0f);
-        }
-        uint4 lo = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-        uint4 hi = make_uint4(pack2(f[8], f[9]), pack2(f[10], f[11]), pack2(f[12], f[13]), pack2(f[14], f[15]));
-        *reinterpret_cast<uint4*>(dst + umma::il_offset(row, dcol0 + 16 * c, Kdst)) = lo;
-        *reinterpret_cast<uint4*>(dst + umma::il_offset(row, dcol0 + 16 * c + 8, Kdst)) = hi;
-    }
-}
-
-// one thread encodes one point through all 16 levels (C = 2, fp16 table, reference rounding) into 32 halfs
-template <int D>
-__device__ __forceinline__ void encode_row(const float (&x)[D], const __half* __restrict__ table, const LevelMeta* __restrict__ meta,
-                                           uint8_t* dst, uint32_t row, uint32_t Kdst, uint32_t dcol0) {
-    bool oob = false;
-#pragma unroll
-    for (int d = 0; d < D; ++d) if (x[d] < 0 || x[d] > 1) oob = true;
-#pragma unroll
-    for (int l0 = 0; l0 < 16; l0 += 4) {
-        uint32_t packed[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            __half r0 = __float2half_rn(0.f), r1 = r0;
-            if (!oob) {
-                const LevelMeta m = meta[l0 + j];
-                const __half* __restrict__ tbl = table + (size_t)m.offset * 2;
-                const grid::Cell<D> cell = grid::locate<D>(x, m, false, 0);
-                grid::Row<__half, 2> rows[1 << D];
-#pragma unroll
-                for (uint32_t k = 0; k < (1u << D); ++k)
-                    rows[k] = grid::load_row<__half, 2>(tbl + (size_t)grid::corner_row<D>(m, cell.pg, k) * 2);
-#pragma unroll
-                for (uint32_t k = 0; k < (1u << D); ++k) {
-                    const float w = grid::corner_weight<D>(cell, k);
-                    grid::accum(r0, w, rows[k].v[0]);
-                    grid::accum(r1, w, rows[k].v[1]);
-                }
-            }
-            const __half2 h = __halves2half2(r0, r1);
-            packed[j] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        *reinterpret_cast<uint4*>(dst + umma::il_offset(row, dcol0 + 2 * l0, Kdst)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    }
-}
-
-__global__ void __launch_bounds__(EVAL_GROUPS * 128, 1)
+__global__ void __launch_bounds__(HEAD_GROUPS * 128, 1)
 head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ LevelMeta meta3[16], meta2[16];
+    __shared__ FastLevel lv3[16], lv2[16];
     __shared__ float s_bias[3][64];
-    __shared__ __align__(8) uint64_t mbar_group[EVAL_GROUPS];
+    __shared__ __align__(8) uint64_t mbar_group[HEAD_GROUPS];
     __shared__ __align__(8) uint64_t mbar_w;
     __shared__ uint32_t tmem_slot;
 
     if (ctl->done) return;
     const uint32_t n_samples = ctl->n_samples;
     const uint32_t n_tiles = (n_samples + EVAL_TILE - 1) / EVAL_TILE;
-    if (blockIdx.x * EVAL_GROUPS >= n_tiles) return;
+    if (blockIdx.x * HEAD_GROUPS >= n_tiles) return;
 
     const uint32_t tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = tid >> 5;
     uint8_t* s_blob = smem;
@@ -134,7 +74,7 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
 
     // ---- one-time CTA setup: barriers, weights via TMA bulk copy, TMEM, level geometry, biases
     if (tid == 0) {
-        for (int i = 0; i < EVAL_GROUPS; ++i) umma::mbar_init(&mbar_group[i], 1);
+        for (int i = 0; i < HEAD_GROUPS; ++i) umma::mbar_init(&mbar_group[i], 1);
         umma::mbar_init(&mbar_w, 1);
         umma::fence_mbar_init();
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(&mbar_w)), "r"(HEAD_BLOB_BYTES) : "memory");
@@ -143,8 +83,16 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
                      : "memory");
     }
     if (warp == 1) umma::tmem_alloc(&tmem_slot, 512);
-    if (tid >= 64 && tid < 80) grid::make_level_meta(meta3[tid - 64], tid - 64, p.offs3, p.S3, p.H3, 3, 1, false);
-    if (tid >= 96 && tid < 112) grid::make_level_meta(meta2[tid - 96], tid - 96, p.offs2, p.S2, p.H2, 2, 1, false);
+    if (tid >= 64 && tid < 80) {
+        grid::LevelMeta m;
+        grid::make_level_meta(m, tid - 64, p.offs3, p.S3, p.H3, 3, 1, false);
+        make_fast_level(lv3[tid - 64], m);
+    }
+    if (tid >= 96 && tid < 112) {
+        grid::LevelMeta m;
+        grid::make_level_meta(m, tid - 96, p.offs2, p.S2, p.H2, 2, 1, false);
+        make_fast_level(lv2[tid - 96], m);
+    }
     if (tid >= 128 && tid < 128 + 192) (&s_bias[0][0])[tid - 128] = __ldg(p.consts + (tid - 128));
     umma::fence_before_sync();
     __syncthreads();
@@ -160,22 +108,19 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
     uint8_t* sEW = s_grp + G_EW;
     uint8_t* sH0 = s_grp + G_H0;
     uint8_t* sH1 = s_grp + G_H1;
-    const uint32_t aA0 = umma::smem_u32(sA0), aEW = umma::smem_u32(sEW), aH0 = umma::smem_u32(sH0), aH1 = umma::smem_u32(sH1);
+    uint8_t* sCIN = s_grp + G_CIN;
+    const uint32_t aA0 = umma::smem_u32(sA0), aEW = umma::smem_u32(sEW), aH0 = umma::smem_u32(sH0), aH1 = umma::smem_u32(sH1),
+                   aCIN = umma::smem_u32(sCIN);
     const uint32_t aW = umma::smem_u32(s_blob);
+    const uint32_t* table3 = reinterpret_cast<const uint32_t*>(p.table3);
+    const uint32_t* table2 = reinterpret_cast<const uint32_t*>(p.table2);
 
-    // operands written by this group's threads -> visible to the tensor core, previous accumulator reads retired
-    auto publish = [&]() {
-        umma::fence_async_smem();
-        umma::fence_before_sync();
-        umma::group_sync(bar_id, 128);
-    };
-    auto wait_mma = [&]() {
-        umma::mbar_wait(mbar, phase);
-        phase ^= 1u;
-        umma::fence_after_sync();
-    };
-
-    for (uint32_t tile = blockIdx.x * EVAL_GROUPS + g; tile < n_tiles; tile += gridDim.x * EVAL_GROUPS) {
+    long long c_enc3 = 0, c_enc2 = 0, c_mma = 0, c_epi = 0, c_tile = 0, c_last = 0;
+    const bool prof = p.prof != nullptr && t == 0;
+#define RN_TICK(acc) if (prof) { const long long now = clock64(); acc += now - c_last; c_last = now; }
+    for (uint32_t tile = blockIdx.x * HEAD_GROUPS + g; tile < n_tiles; tile += gridDim.x * HEAD_GROUPS) {
+        if (prof) c_last = clock64();
+        const long long c_start = c_last;
         const uint32_t s = tile * EVAL_TILE + t;
         const bool valid = s < n_samples;
         const float4 smp = valid ? __ldg(p.samples + s) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -185,34 +130,22 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
         {
             float x[3] = {__fmul_rn(__fadd_rn(smp.x, p.bound), p.inv2bound), __fmul_rn(__fadd_rn(smp.y, p.bound), p.inv2bound),
                           __fmul_rn(__fadd_rn(smp.z, p.bound), p.inv2bound)};
-            encode_row<3>(x, p.table3, meta3, sA0, t, 32, 0);
+            fast_encode<3>(x, table3, lv3, sA0, t, 32, 0);
         }
-        publish();
-        // ---- ambient L1: [128x32] x WA1 -> 64
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aA0, aW + B_WA1, 32, 32, 0, 32, 64, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
-        epilogue_to_operand<4, true>(tmem_row, 0, s_bias[0], sH0, t, 64, 0);
-        publish();
-        // ---- ambient L2
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aH0, aW + B_WA2, 64, 64, 0, 64, 64, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
-        epilogue_to_operand<4, true>(tmem_row, 0, nullptr, sH1, t, 64, 0);
-        publish();
-        // ---- ambient L3 (N padded to 16) -> tanh -> 2-D encode -> EW
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aH1, aW + B_WA3, 64, 64, 0, 64, 16, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
+        RN_TICK(c_enc3)
+        // ---- ambient L1: A0 [128x32] x WA1 -> 64, + hoisted audio term, ReLU -> H0
+        mma_stage(tmem_acc, aA0, 32, 0, aW + B_WA1, 32, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        RN_TICK(c_mma)
+        epilogue_to_operand<2>(tmem_row, 0, true, s_bias[0], sH0, t, 64, 0);
+        RN_TICK(c_epi)
+        // ---- ambient L2: H0 -> H1
+        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WA2, 64, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        RN_TICK(c_mma)
+        epilogue_to_operand<2>(tmem_row, 0, true, nullptr, sH1, t, 64, 0);
+        RN_TICK(c_epi)
+        // ---- ambient L3 (N padded to 16) -> tanh -> 2-D encode -> EW (first half of H0)
+        mma_stage(tmem_acc, aH1, 64, 0, aW + B_WA3, 64, 0, 0, 0, 16, mbar, phase, bar_id, t);
+        RN_TICK(c_mma)
         {
             uint32_t v[16];
             umma::tmem_ld16(tmem_row, v);
@@ -220,39 +153,25 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
             const float a0 = tanhf(__half2float(__float2half_rn(__uint_as_float(v[0]))));
             const float a1 = tanhf(__half2float(__float2half_rn(__uint_as_float(v[1]))));
             float x[2] = {__fmul_rn(__fadd_rn(a0, 1.0f), 0.5f), __fmul_rn(__fadd_rn(a1, 1.0f), 0.5f)};
-            encode_row<2>(x, p.table2, meta2, sEW, t, 32, 0);
+            fast_encode<2>(x, table2, lv2, sEW, t, 32, 0);
         }
-        publish();
-        // ---- sigma L1: [enc_x | enc_w] (two K = 32 halves) -> 64
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aA0, aW + B_WS1A, 32, 32, 0, 32, 64, false);
-            umma::gemm_issue(tmem_acc, aEW, aW + B_WS1B, 32, 32, 0, 32, 64, true);
-            umma::commit(mbar);
-        }
-        wait_mma();
-        epilogue_to_operand<4, true>(tmem_row, 0, s_bias[1], sH0, t, 64, 0);
-        publish();
-        // ---- sigma L2
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aH0, aW + B_WS2, 64, 64, 0, 64, 64, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
-        epilogue_to_operand<4, true>(tmem_row, 0, nullptr, sH1, t, 64, 0);
-        publish();
+        RN_TICK(c_enc2)
+        // ---- sigma L1: [enc_x | enc_w] as two K = 32 slabs, + hoisted eye term, ReLU -> H1
+        mma_stage(tmem_acc, aA0, 32, 0, aW + B_WS1A, 32, aEW, aW + B_WS1B, 32, 64, mbar, phase, bar_id, t);
+        RN_TICK(c_mma)
+        epilogue_to_operand<2>(tmem_row, 0, true, s_bias[1], sH1, t, 64, 0);
+        RN_TICK(c_epi)
+        // ---- sigma L2: H1 -> H0
+        mma_stage(tmem_acc, aH1, 64, 0, aW + B_WS2, 64, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        RN_TICK(c_mma)
+        epilogue_to_operand<2>(tmem_row, 0, true, nullptr, sH0, t, 64, 0);
+        RN_TICK(c_epi)
         // ---- sigma L3: rows permuted on the host so columns 0..63 = geo_feat, column 64 = log-density
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aH1, aW + B_WS3, 64, 64, 0, 64, 80, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
+        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WS3, 64, 0, 0, 0, 80, mbar, phase, bar_id, t);
+        RN_TICK(c_mma)
         float sigma;
         {
-            // geo_feat -> CIN columns 16..79 (CIN aliases H0, dead since sigma L2 completed)
-            epilogue_to_operand<4, false>(tmem_row, 0, nullptr, sH0, t, 80, 16);
+            epilogue_to_operand<2>(tmem_row, 0, false, nullptr, sCIN, t, 80, 16);  // geo_feat -> CIN columns 16..79
             uint32_t v[16];
             umma::tmem_ld16(tmem_row + 64, v);
             umma::tmem_ld_wait();
@@ -261,28 +180,20 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
             const float* d = p.rays_d + (size_t)ray * 3;
             float Y[16];
             sh_eval<4, false>(__ldg(d), __ldg(d + 1), __ldg(d + 2), Y, nullptr, nullptr, nullptr);
-            *reinterpret_cast<uint4*>(sH0 + umma::il_offset(t, 0, 80)) =
+            *reinterpret_cast<uint4*>(sCIN + umma::il_offset(t, 0, 80)) =
                 make_uint4(pack2(Y[0], Y[1]), pack2(Y[2], Y[3]), pack2(Y[4], Y[5]), pack2(Y[6], Y[7]));
-            *reinterpret_cast<uint4*>(sH0 + umma::il_offset(t, 8, 80)) =
+            *reinterpret_cast<uint4*>(sCIN + umma::il_offset(t, 8, 80)) =
                 make_uint4(pack2(Y[8], Y[9]), pack2(Y[10], Y[11]), pack2(Y[12], Y[13]), pack2(Y[14], Y[15]));
         }
-        publish();
-        // ---- colour L1: [sh | geo] K = 80 -> 64
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aH0, aW + B_WC1, 80, 80, 0, 80, 64, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
-        epilogue_to_operand<4, true>(tmem_row, 0, s_bias[2], sH1, t, 64, 0);
-        publish();
+        RN_TICK(c_epi)
+        // ---- colour L1: CIN [sh | geo] K = 80 -> 64, + hoisted individual-code term, ReLU -> H0
+        mma_stage(tmem_acc, aCIN, 80, 0, aW + B_WC1, 80, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        RN_TICK(c_mma)
+        epilogue_to_operand<2>(tmem_row, 0, true, s_bias[2], sH0, t, 64, 0);
+        RN_TICK(c_epi)
         // ---- colour L2 (N padded to 16) -> sigmoid
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aH1, aW + B_WC2, 64, 64, 0, 64, 16, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
+        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WC2, 64, 0, 0, 0, 16, mbar, phase, bar_id, t);
+        RN_TICK(c_mma)
         {
             uint32_t v[16];
             umma::tmem_ld16(tmem_row, v);
@@ -298,7 +209,17 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
         // the next tile's first MMA overwrites the accumulator: retire this tile's TMEM reads first
         umma::fence_before_sync();
         umma::group_sync(bar_id, 128);
+        if (prof) c_tile += clock64() - c_start;
     }
+    if (prof) {
+        atomicAdd(p.prof + 0, (unsigned long long)c_enc3);
+        atomicAdd(p.prof + 1, (unsigned long long)c_enc2);
+        atomicAdd(p.prof + 2, (unsigned long long)c_mma);
+        atomicAdd(p.prof + 3, (unsigned long long)c_epi);
+        atomicAdd(p.prof + 4, (unsigned long long)c_tile);
+        atomicAdd(p.prof + 5, 1ull);
+    }
+#undef RN_TICK
 
     umma::fence_before_sync();
     __syncthreads();
@@ -314,10 +235,10 @@ int launch_head_eval(const HeadEvalParams& p, const FrameCtl* ctl, uint32_t max_
         if (e != cudaSuccess) { set_error("head_eval: cannot reserve %u bytes of shared memory: %s", HEAD_SMEM, cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
-    uint32_t grid = (max_tiles + EVAL_GROUPS - 1) / EVAL_GROUPS;
+    uint32_t grid = (max_tiles + HEAD_GROUPS - 1) / HEAD_GROUPS;
     if (grid > RN_NUM_SMS) grid = RN_NUM_SMS;
     if (grid == 0) grid = 1;
-    head_eval_kernel<<<grid, EVAL_GROUPS * 128, HEAD_SMEM, st>>>(p, ctl);
+    head_eval_kernel<<<grid, HEAD_GROUPS * 128, HEAD_SMEM, st>>>(p, ctl);
     return finish_launch("head_eval");
 }
 

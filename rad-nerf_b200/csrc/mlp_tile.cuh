@@ -1,0 +1,158 @@
+// mlp_tile.cuh -- building blocks shared by the fused-MLP kernels (head_eval.cu, torso_eval.cu):
+//   mma_stage            publish the group's operand rows, one thread issues the tcgen05 MMAs, everybody waits on the mbarrier
+//   epilogue_to_operand  TMEM row -> (+bias, ReLU) -> fp16 -> next layer's A operand row in shared memory
+//   fast_encode<D>       one point through the 16 levels of a tiled, linearly interpolated 2-feature fp16 grid
+// mma_stage / epilogue are deliberately __noinline__: the kernel body has to stay inside the instruction cache (the first,
+// fully inlined version was 179 KB of SASS and spent 47% of its issue slots waiting for instructions).
+#pragma once
+#include "umma.cuh"
+#include "gridencoder_impl.cuh"
+
+namespace rn {
+namespace {
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t relu2(uint32_t v) {
+    const __half2 h = __hmax2(*reinterpret_cast<const __half2*>(&v), __float2half2_rn(0.f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// 32 accumulator columns [col0 + 32c, +32) per step, c < nch32: all TMEM loads are issued before the single wait.
+// relu(round(x)) == round(relu(x)), so ReLU runs on packed halves.
+template <int NCH32>
+static __device__ __noinline__ void epilogue_to_operand(uint32_t tmem_row, uint32_t col0, bool relu, const float* bias, uint8_t* dst,
+                                                        uint32_t row, uint32_t Kdst, uint32_t dcol0) {
+    uint32_t v[NCH32][32];
+#pragma unroll
+    for (int c = 0; c < NCH32; ++c) umma::tmem_ld32(tmem_row + col0 + 32 * c, v[c]);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < NCH32; ++c) {
+        uint32_t h[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(v[c][2 * j]), b = __uint_as_float(v[c][2 * j + 1]);
+            if (bias) { a += bias[32 * c + 2 * j]; b += bias[32 * c + 2 * j + 1]; }
+            h[j] = pack2(a, b);
+            if (relu) h[j] = relu2(h[j]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(dst + umma::il_offset(row, dcol0 + 32 * c + 8 * q, Kdst)) =
+                make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    }
+}
+
+// publish this group's freshly written operand rows, let thread 0 issue D = A0*B0^T (+ A1*B1^T), wait for completion.
+// ka0 = first A column of the K0-slab inside an operand whose rows are Ka0 halves long.
+static __device__ __noinline__ void mma_stage(uint32_t tmem_acc, uint32_t a0, uint32_t Ka0, uint32_t ka0, uint32_t b0, uint32_t K0,
+                                              uint32_t a1, uint32_t b1, uint32_t K1, uint32_t N, uint64_t* mbar, uint32_t& phase,
+                                              uint32_t bar_id, uint32_t t) {
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    umma::group_sync(bar_id, 128);
+    if (t == 0) {
+        umma::fence_after_sync();
+        umma::gemm_issue(tmem_acc, a0, b0, Ka0, K0, ka0, K0, N, false);
+        if (K1) umma::gemm_issue(tmem_acc, a1, b1, K1, K1, 0, K1, N, true);
+        umma::commit(mbar);
+    }
+    umma::mbar_wait(mbar, phase);
+    phase ^= 1u;
+    umma::fence_after_sync();
+}
+
+// ---- specialised grid level: tiled indexing, linear interpolation, align_corners = false, 2 fp16 features -------------
+struct FastLevel {
+    float scale;      // exp2f(l*S)*H - 1
+    uint32_t s1, s2;  // strides of dimensions 1, 2 (0 once the running stride exceeded the level size: gridencoder.cu:72)
+    uint32_t mask;    // size - 1 for capped (power-of-two) levels, 0xffffffff for dense ones (index < size, no wrap)
+    uint32_t offset;  // first row of the level
+};
+
+// returns false if the level cannot be expressed (generic modulo) -- the host checks supported() first
+__device__ __forceinline__ bool make_fast_level(FastLevel& f, const grid::LevelMeta& m) {
+    f.scale = m.scale;
+    f.s1 = m.stride[1];
+    f.s2 = m.stride[2];
+    f.offset = m.offset;
+    const uint32_t wrap = m.mode >> 1;
+    f.mask = wrap == 0 ? 0xffffffffu : m.size - 1;
+    return (m.mode & 1u) == 0 && wrap != 2;
+}
+
+// acc += round_half(w * g) with c10::Half's rounding (product in fp32, rounded to half, half add) on both features
+__device__ __forceinline__ void accum2(__half2& acc, float w, uint32_t g) {
+    const __half2 gv = *reinterpret_cast<const __half2*>(&g);
+    acc = __hadd2(acc, __floats2half2_rn(__fmul_rn(w, __low2float(gv)), __fmul_rn(w, __high2float(gv))));
+}
+
+// One point through all 16 levels; writes its 32 halfs as 4 x 16 B into row `row` of an interleaved [128 x Kdst] operand at
+// column dcol0.  Bit-identical to grid_forward_kernel<half, D, 2> (same operations in the same order); the index math is
+// specialised: base = p0 + p1*s1 + p2*s2, corner = (base + dx + dy*s1 + dz*s2) & mask.
+template <int D>
+static __device__ __noinline__ void fast_encode(const float (&x)[D], const uint32_t* __restrict__ table32, const FastLevel* __restrict__ lv,
+                                                uint8_t* dst, uint32_t row, uint32_t Kdst, uint32_t dcol0) {
+    bool oob = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) if (x[d] < 0 || x[d] > 1) oob = true;
+#pragma unroll 1
+    for (int l0 = 0; l0 < 16; l0 += 4) {
+        uint32_t g[4][1 << D];
+        float fr[4][D];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // all gathers of four levels first ...
+            const FastLevel L = lv[l0 + j];
+            uint32_t pg[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const float pos = __fmaf_rn(x[d], L.scale, 0.5f);
+                const float fl = floorf(pos);
+                pg[d] = (uint32_t)fl;
+                fr[j][d] = pos - (float)pg[d];
+            }
+            const uint32_t* __restrict__ tb = table32 + L.offset;
+            if (oob) {
+#pragma unroll
+                for (int k = 0; k < (1 << D); ++k) g[j][k] = 0u;
+            } else if constexpr (D == 3) {
+                const uint32_t b00 = pg[0] + pg[1] * L.s1 + pg[2] * L.s2, b10 = b00 + L.s1, b01 = b00 + L.s2, b11 = b10 + L.s2;
+                g[j][0] = __ldg(tb + (b00 & L.mask)); g[j][1] = __ldg(tb + ((b00 + 1) & L.mask));
+                g[j][2] = __ldg(tb + (b10 & L.mask)); g[j][3] = __ldg(tb + ((b10 + 1) & L.mask));
+                g[j][4] = __ldg(tb + (b01 & L.mask)); g[j][5] = __ldg(tb + ((b01 + 1) & L.mask));
+                g[j][6] = __ldg(tb + (b11 & L.mask)); g[j][7] = __ldg(tb + ((b11 + 1) & L.mask));
+            } else {
+                const uint32_t b0 = pg[0] + pg[1] * L.s1, b1 = b0 + L.s1;
+                g[j][0] = __ldg(tb + (b0 & L.mask)); g[j][1] = __ldg(tb + ((b0 + 1) & L.mask));
+                g[j][2] = __ldg(tb + (b1 & L.mask)); g[j][3] = __ldg(tb + ((b1 + 1) & L.mask));
+            }
+        }
+        uint32_t packed[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // ... then the interpolation, corner order = bit d of k selects dimension d
+            __half2 acc = __float2half2_rn(0.f);
+            if (!oob) {
+                const float x0 = 1.0f - fr[j][0], x1 = fr[j][0], y0 = 1.0f - fr[j][1], y1 = fr[j][1];
+                if constexpr (D == 3) {
+                    const float z0 = 1.0f - fr[j][2], z1 = fr[j][2];
+                    const float w00 = __fmul_rn(x0, y0), w10 = __fmul_rn(x1, y0), w01 = __fmul_rn(x0, y1), w11 = __fmul_rn(x1, y1);
+                    accum2(acc, __fmul_rn(w00, z0), g[j][0]); accum2(acc, __fmul_rn(w10, z0), g[j][1]);
+                    accum2(acc, __fmul_rn(w01, z0), g[j][2]); accum2(acc, __fmul_rn(w11, z0), g[j][3]);
+                    accum2(acc, __fmul_rn(w00, z1), g[j][4]); accum2(acc, __fmul_rn(w10, z1), g[j][5]);
+                    accum2(acc, __fmul_rn(w01, z1), g[j][6]); accum2(acc, __fmul_rn(w11, z1), g[j][7]);
+                } else {
+                    accum2(acc, __fmul_rn(x0, y0), g[j][0]); accum2(acc, __fmul_rn(x1, y0), g[j][1]);
+                    accum2(acc, __fmul_rn(x0, y1), g[j][2]); accum2(acc, __fmul_rn(x1, y1), g[j][3]);
+                }
+            }
+            packed[j] = *reinterpret_cast<const uint32_t*>(&acc);
+        }
+        *reinterpret_cast<uint4*>(dst + umma::il_offset(row, dcol0 + 2 * l0, Kdst)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+}
+
+}  // namespace
+}  // namespace rn

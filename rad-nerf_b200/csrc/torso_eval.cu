@@ -8,13 +8,13 @@
 #include "frame.cuh"
 #include "umma.cuh"
 #include "gridencoder_impl.cuh"
+#include "mlp_tile.cuh"
 
 namespace rn {
 
 
 namespace {
 
-using grid::LevelMeta;
 
 constexpr uint32_t T_WD1 = 0;                          // [64 x 48]
 constexpr uint32_t T_WD2 = T_WD1 + 64 * 48 * 2;        // [64 x 64]
@@ -32,37 +32,10 @@ constexpr uint32_t GROUP_BYTES = G_TIN + 128 * 80 * 2;
 constexpr uint32_t TORSO_SMEM = TORSO_BLOB_BYTES + EVAL_GROUPS * GROUP_BYTES;
 constexpr uint32_t TMEM_COLS_PER_GROUP = 64;
 
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
-}
-
-template <int NCH, bool RELU>
-__device__ __forceinline__ void epilogue_to_operand(uint32_t tmem_row, const float* __restrict__ bias, uint8_t* dst, uint32_t row,
-                                                    uint32_t Kdst) {
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        uint32_t v[16];
-        umma::tmem_ld16(tmem_row + 16 * c, v);
-        umma::tmem_ld_wait();
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            f[j] = __uint_as_float(v[j]);
-            if (bias) f[j] += bias[16 * c + j];
-            if (RELU) f[j] = fmaxf(f[j], 0.0f);
-        }
-        *reinterpret_cast<uint4*>(dst + umma::il_offset(row, 16 * c, Kdst)) =
-            make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-        *reinterpret_cast<uint4*>(dst + umma::il_offset(row, 16 * c + 8, Kdst)) =
-            make_uint4(pack2(f[8], f[9]), pack2(f[10], f[11]), pack2(f[12], f[13]), pack2(f[14], f[15]));
-    }
-}
-
 __global__ void __launch_bounds__(EVAL_GROUPS * 128, 1)
 torso_eval_kernel(TorsoEvalParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ LevelMeta meta[16];
+    __shared__ FastLevel lv[16];
     __shared__ float s_bias_d[64], s_bias_t[32];
     __shared__ __align__(8) uint64_t mbar_group[EVAL_GROUPS];
     __shared__ __align__(8) uint64_t mbar_w;
@@ -86,7 +59,11 @@ torso_eval_kernel(TorsoEvalParams p) {
                      : "memory");
     }
     if (warp == 1) umma::tmem_alloc(&tmem_slot, 256);
-    if (tid >= 64 && tid < 80) grid::make_level_meta(meta[tid - 64], tid - 64, p.offs, p.S, p.H, 2, 1, false);
+    if (tid >= 64 && tid < 80) {
+        grid::LevelMeta m;
+        grid::make_level_meta(m, tid - 64, p.offs, p.S, p.H, 2, 1, false);
+        make_fast_level(lv[tid - 64], m);
+    }
     if (tid >= 128 && tid < 192) s_bias_d[tid - 128] = __ldg(p.consts + (tid - 128));
     if (tid >= 192 && tid < 224) s_bias_t[tid - 192] = __ldg(p.consts + 64 + (tid - 192));
     umma::fence_before_sync();
@@ -105,17 +82,6 @@ torso_eval_kernel(TorsoEvalParams p) {
     uint8_t* sTIN = s_grp + G_TIN;
     const uint32_t aF = umma::smem_u32(sF), aH0 = umma::smem_u32(sH0), aH1 = umma::smem_u32(sH1), aTIN = umma::smem_u32(sTIN);
     const uint32_t aW = umma::smem_u32(s_blob);
-
-    auto publish = [&]() {
-        umma::fence_async_smem();
-        umma::fence_before_sync();
-        umma::group_sync(bar_id, 128);
-    };
-    auto wait_mma = [&]() {
-        umma::mbar_wait(mbar, phase);
-        phase ^= 1u;
-        umma::fence_after_sync();
-    };
 
     for (uint32_t tile = blockIdx.x * EVAL_GROUPS + g; tile < n_tiles; tile += gridDim.x * EVAL_GROUPS) {
         const uint32_t k = tile * EVAL_TILE + t;
@@ -146,32 +112,14 @@ torso_eval_kernel(TorsoEvalParams p) {
                 *reinterpret_cast<uint4*>(sTIN + umma::il_offset(t, 32 + 8 * c, 80)) = q;
             }
         }
-        publish();
-        // ---- deform L1 (K = 48) -> 64
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aF, aW + T_WD1, 48, 48, 0, 48, 64, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
-        epilogue_to_operand<4, true>(tmem_row, s_bias_d, sH0, t, 64);
-        publish();
-        // ---- deform L2
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aH0, aW + T_WD2, 64, 64, 0, 64, 64, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
-        epilogue_to_operand<4, true>(tmem_row, nullptr, sH1, t, 64);
-        publish();
-        // ---- deform L3 (N padded to 16) -> dx -> deformed coordinate -> 2-D grid encode -> TIN[0..31]
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aH1, aW + T_WD3, 64, 64, 0, 64, 16, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
+                // ---- deform L1 (K = 48) -> 64
+        mma_stage(tmem_acc, aF, 48, 0, aW + T_WD1, 48, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        epilogue_to_operand<2>(tmem_row, 0, true, s_bias_d, sH0, t, 64, 0);
+                // ---- deform L2
+        mma_stage(tmem_acc, aH0, 64, 0, aW + T_WD2, 64, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        epilogue_to_operand<2>(tmem_row, 0, true, nullptr, sH1, t, 64, 0);
+                // ---- deform L3 (N padded to 16) -> dx -> deformed coordinate -> 2-D grid encode -> TIN[0..31]
+        mma_stage(tmem_acc, aH1, 64, 0, aW + T_WD3, 64, 0, 0, 0, 16, mbar, phase, bar_id, t);
         {
             uint32_t v[16];
             umma::tmem_ld16(tmem_row, v);
@@ -180,61 +128,16 @@ torso_eval_kernel(TorsoEvalParams p) {
             const float dx1 = __half2float(__float2half_rn(__uint_as_float(v[1])));
             const float y0 = fminf(fmaxf(__fadd_rn(x0, dx0), -1.f), 1.f), y1 = fminf(fmaxf(__fadd_rn(x1, dx1), -1.f), 1.f);
             float x[2] = {__fmul_rn(__fadd_rn(y0, 1.0f), 0.5f), __fmul_rn(__fadd_rn(y1, 1.0f), 0.5f)};
-            // same per-level arithmetic as the stand-alone encoder (gridencoder_impl.cuh), fp16 table
-            bool oob = x[0] < 0 || x[0] > 1 || x[1] < 0 || x[1] > 1;
-#pragma unroll
-            for (int l0 = 0; l0 < 16; l0 += 4) {
-                uint32_t packed[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    __half r0 = __float2half_rn(0.f), r1 = r0;
-                    if (!oob) {
-                        const LevelMeta m = meta[l0 + j];
-                        const __half* __restrict__ tbl = p.table + (size_t)m.offset * 2;
-                        const grid::Cell<2> cell = grid::locate<2>(x, m, false, 0);
-                        grid::Row<__half, 2> rows[4];
-#pragma unroll
-                        for (uint32_t q = 0; q < 4; ++q)
-                            rows[q] = grid::load_row<__half, 2>(tbl + (size_t)grid::corner_row<2>(m, cell.pg, q) * 2);
-#pragma unroll
-                        for (uint32_t q = 0; q < 4; ++q) {
-                            const float w = grid::corner_weight<2>(cell, q);
-                            grid::accum(r0, w, rows[q].v[0]);
-                            grid::accum(r1, w, rows[q].v[1]);
-                        }
-                    }
-                    const __half2 h = __halves2half2(r0, r1);
-                    packed[j] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                *reinterpret_cast<uint4*>(sTIN + umma::il_offset(t, 2 * l0, 80)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            }
+            fast_encode<2>(x, reinterpret_cast<const uint32_t*>(p.table), lv, sTIN, t, 80, 0);
         }
-        publish();
         // ---- torso L1 (K = 80) -> 32
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aTIN, aW + T_WT1, 80, 80, 0, 80, 32, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
-        epilogue_to_operand<2, true>(tmem_row, s_bias_t, sH0, t, 32);
-        publish();
-        // ---- torso L2 (K = 32) -> 32
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aH0, aW + T_WT2, 32, 32, 0, 32, 32, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
-        epilogue_to_operand<2, true>(tmem_row, nullptr, sH1, t, 32);
-        publish();
-        // ---- torso L3 (N padded to 16) -> sigmoid -> (alpha, rgb)
-        if (t == 0) {
-            umma::fence_after_sync();
-            umma::gemm_issue(tmem_acc, aH1, aW + T_WT3, 32, 32, 0, 32, 16, false);
-            umma::commit(mbar);
-        }
-        wait_mma();
+        mma_stage(tmem_acc, aTIN, 80, 0, aW + T_WT1, 80, 0, 0, 0, 32, mbar, phase, bar_id, t);
+        epilogue_to_operand<1>(tmem_row, 0, true, s_bias_t, sH0, t, 32, 0);
+                // ---- torso L2 (K = 32) -> 32
+        mma_stage(tmem_acc, aH0, 32, 0, aW + T_WT2, 32, 0, 0, 0, 32, mbar, phase, bar_id, t);
+        epilogue_to_operand<1>(tmem_row, 0, true, nullptr, sH1, t, 32, 0);
+                // ---- torso L3 (N padded to 16) -> sigmoid -> (alpha, rgb)
+        mma_stage(tmem_acc, aH1, 32, 0, aW + T_WT3, 32, 0, 0, 0, 16, mbar, phase, bar_id, t);
         {
             uint32_t v[16];
             umma::tmem_ld16(tmem_row, v);

@@ -55,12 +55,13 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uin
 }
 
 // D[128 x N] (+)= A[128 x K] * B[N x K]^T for K a multiple of 16; issued by ONE thread
+// A columns [k_begin, k_begin + k_count) of an operand stored with row length K_a_total; B columns [0, k_count) of K_b_total
 __device__ __forceinline__ void gemm_issue(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t K_a_total,
                                            uint32_t K_b_total, uint32_t k_begin, uint32_t k_count, uint32_t N, bool accumulate) {
     const uint32_t idesc = make_idesc_f16(128, N);
     for (uint32_t s = 0; s < k_count; s += 16) {
         const uint64_t da = make_desc(a_smem + ((k_begin + s) >> 3) * LBO_BYTES, K_a_total);
-        const uint64_t db = make_desc(b_smem + ((k_begin + s) >> 3) * LBO_BYTES, K_b_total);
+        const uint64_t db = make_desc(b_smem + (s >> 3) * LBO_BYTES, K_b_total);
         mma_f16_ss(tmem_d, da, db, idesc, (accumulate || s > 0) ? 1u : 0u);
     }
 }
@@ -89,6 +90,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
 }

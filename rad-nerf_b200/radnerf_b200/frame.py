@@ -23,7 +23,7 @@ class GridTable(C.Structure):
 
 
 class ConditioningDesc(C.Structure):
-    _fields_ = [("auds", _vp), ("F", _u32), ("Cin", _u32), ("att", _u32), ("smooth", _u32), ("has_state", _u32),
+    _fields_ = [("auds", _vp), ("F", _u32), ("Cin", _u32), ("att", _u32), ("smooth", _u32), ("reserved", _u32),
                 ("conv_w", _vp * 4), ("conv_b", _vp * 4), ("fc_w", _vp * 2), ("fc_b", _vp * 2),
                 ("att_w", _vp * 5), ("att_b", _vp * 5), ("att_fc_w", _vp), ("att_fc_b", _vp),
                 ("enc_a_state", _vp), ("lambda_", _f32),
@@ -94,8 +94,10 @@ class FusedState:
         self.workspace = None
         self.head_consts = torch.zeros(3 * 64, device=dev)
         self.torso_consts = torch.zeros(96, device=dev)
-        self.enc_a_state = torch.zeros(64, device=dev)
+        self.enc_a_state = torch.zeros(65, device=dev)  # [0..63] smoothed audio code, [64] validity flag (device side)
         self.frames = 0
+        self.graphs = {}      # config key -> (CUDAGraph, static inputs, outputs)
+        self.use_graph = True
 
     def refresh_weights(self, model):
         params = [model.encoder.embeddings, model.encoder_ambient.embeddings] + list(model.ambient_net.parameters()) + \
@@ -106,6 +108,7 @@ class FusedState:
         if versions == self.versions:
             return
         self.versions = versions
+        self.graphs.clear()  # captured graphs hold pointers to the old blobs
         self.table3 = model.encoder.embeddings.detach().to(torch.float16).contiguous()
         self.table2 = model.encoder_ambient.embeddings.detach().to(torch.float16).contiguous()
         a, s, c = model.ambient_net.net, model.sigma_net.net, model.color_net.net
@@ -132,6 +135,7 @@ class FusedState:
             self.N = N
             self.torso_alpha = torch.empty(N, 1, device=self.dev)
             self.torso_color = torch.empty(N, 3, device=self.dev)
+            self.graphs.clear()
 
     def ctl(self):
         """device loop state of the last frame as a [65, 8] int32 tensor (n_alive, n_step, step, done, n_samples, ...)"""
@@ -142,39 +146,20 @@ def _grid_table(enc, table):
     return GridTable(table.data_ptr(), enc.offsets.data_ptr(), float(np.log2(enc.per_level_scale)), int(enc.base_resolution))
 
 
-def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=0, dt_gamma=0, bg_color=None, perturb=False,
-                 force_all_rays=False, max_steps=1024, T_thresh=1e-4, **kwargs):
-    if model.training:
-        raise RuntimeError("render_frame is the inference path; training goes through run_cuda")
-    if not supported(model):
-        raise NotImplementedError("model configuration outside the fused kernels' specialisation")
+def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_scalar, noises, dt_gamma, max_steps, T_thresh):
+    """the frame's launch sequence (capturable: no host sync, outputs allocated with torch.empty)"""
     L = abi.lib()
-    st = getattr(model, "_fused", None)
-    if st is None:
-        st = model._fused = FusedState(model)
-    st.refresh_weights(model)
-
-    prefix = rays_o.shape[:-1]
-    rays_o = rays_o.contiguous().view(-1, 3).float()
-    rays_d = rays_d.contiguous().view(-1, 3).float()
-    bg_coords = bg_coords.contiguous().view(-1, 2).float()
     N = rays_o.shape[0]
     dev = rays_o.device
-    st.ensure_workspace(N)
     stream = abi.cur_stream()
 
     # ---- per-frame conditioning
     an, at = model.audio_net, getattr(model, "audio_att_net", None)
     cd = ConditioningDesc()
     if auds is not None:
-        auds = auds.contiguous().float()
         cd.auds, cd.F, cd.Cin = auds.data_ptr(), auds.shape[0], auds.shape[1]
     cd.att = int(model.att)
     cd.smooth = int(bool(model.smooth_lips))
-    has_state = bool(model.smooth_lips) and getattr(model, "enc_a", None) is not None
-    if has_state and model.enc_a.data_ptr() != st.enc_a_state.data_ptr():
-        st.enc_a_state.copy_(model.enc_a.reshape(-1))
-    cd.has_state = int(has_state)
     for i, k in enumerate((0, 2, 4, 6)):
         cd.conv_w[i], cd.conv_b[i] = an.encoder_conv[k].weight.data_ptr(), an.encoder_conv[k].bias.data_ptr()
     for i, k in enumerate((0, 2)):
@@ -187,20 +172,14 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
     cd.w_amb1 = model.ambient_net.net[0].weight.data_ptr()
     cd.w_sig1 = model.sigma_net.net[0].weight.data_ptr()
     cd.w_col1 = model.color_net.net[0].weight.data_ptr()
-    eye_t = None if eye is None else eye.reshape(-1).float().contiguous()
     cd.eye = _p(eye_t)
-    ind_code = model.individual_codes[0].detach().contiguous()
-    cd.ind_code = ind_code.data_ptr()
+    cd.ind_code = model.individual_codes.data_ptr()  # row 0 (inference uses a fixed code, renderer.py:201-202)
     cd.head_consts = st.head_consts.data_ptr()
     if model.torso:
-        pose6 = poses.reshape(-1).float().contiguous()
-        ind_torso = model.individual_codes_torso[0].detach().contiguous()
         cd.w_def1 = model.torso_deform_net.net[0].weight.data_ptr()
         cd.w_tor1 = model.torso_net.net[0].weight.data_ptr()
-        cd.pose6, cd.ind_torso, cd.torso_consts = pose6.data_ptr(), ind_torso.data_ptr(), st.torso_consts.data_ptr()
+        cd.pose6, cd.ind_torso, cd.torso_consts = pose6.data_ptr(), model.individual_codes_torso.data_ptr(), st.torso_consts.data_ptr()
     abi.check(L.rn_frame_conditioning(C.byref(cd), stream))
-    if model.smooth_lips and auds is not None:
-        model.enc_a = st.enc_a_state.view(1, 64)
 
     # ---- head
     weights_sum = torch.empty(N, device=dev)
@@ -208,7 +187,6 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
     image = torch.empty(N, 3, device=dev)
     nears = torch.empty(N, device=dev)
     fars = torch.empty(N, device=dev)
-    noises = torch.rand(N, device=dev) if perturb else None
     hd = FrameHeadDesc()
     hd.N, hd.max_steps, hd.cascade, hd.grid_size = N, int(max_steps), int(model.cascade), int(model.grid_size)
     hd.bound, hd.min_near, hd.dt_gamma, hd.T_thresh = float(model.bound), float(model.min_near), float(dt_gamma), float(T_thresh)
@@ -222,16 +200,6 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
     abi.check(L.rn_frame_head(C.byref(hd), stream))
 
     results = {}
-    # ---- torso
-    bg_t = None
-    bg_scalar = 1.0
-    if bg_color is not None:
-        if torch.is_tensor(bg_color):
-            bg_t = bg_color.reshape(-1, 3).float().contiguous()
-            if bg_t.shape[0] != N:
-                bg_t = bg_t.expand(N, 3).contiguous()
-        else:
-            bg_scalar = float(bg_color)
     torso_bg = None
     if model.torso:
         td = FrameTorsoDesc()
@@ -249,10 +217,97 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
     abi.check(L.rn_frame_finalize(N, weights_sum.data_ptr(), depth.data_ptr(), image.data_ptr(), nears.data_ptr(), fars.data_ptr(),
                                   _p(bg_t), bg_scalar, _p(st.torso_alpha) if model.torso else None,
                                   _p(st.torso_color) if model.torso else None, _p(torso_bg), stream))
-    st.frames += 1
-    results['depth'] = depth.view(*prefix)
-    results['image'] = image.view(*prefix, 3)
+    results['depth'] = depth
+    results['image'] = image
     results['weights_sum'] = weights_sum
+    return results
+
+
+def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=0, dt_gamma=0, bg_color=None, perturb=False,
+                 force_all_rays=False, max_steps=1024, T_thresh=1e-4, **kwargs):
+    """Fused inference frame.  With `model._fused.use_graph` (default) the launch sequence is captured once per
+    configuration into a CUDA graph and replayed: inputs are copied into the graph's static buffers and the returned
+    tensors are the graph's static OUTPUT buffers -- they are overwritten by the next call (consume or clone them first)."""
+    if model.training:
+        raise RuntimeError("render_frame is the inference path; training goes through run_cuda")
+    if not supported(model):
+        raise NotImplementedError("model configuration outside the fused kernels' specialisation")
+    abi.lib()
+    st = getattr(model, "_fused", None)
+    if st is None:
+        st = model._fused = FusedState(model)
+    st.refresh_weights(model)
+
+    prefix = rays_o.shape[:-1]
+    rays_o = rays_o.contiguous().view(-1, 3).float()
+    rays_d = rays_d.contiguous().view(-1, 3).float()
+    bg_coords = bg_coords.contiguous().view(-1, 2).float()
+    N = rays_o.shape[0]
+    dev = rays_o.device
+    st.ensure_workspace(N)
+
+    # lip-smoothing state: `model.enc_a` (the reference's attribute) mirrors the device-side state
+    if model.smooth_lips:
+        prev = getattr(model, "enc_a", None)
+        if prev is None:
+            st.enc_a_state.zero_()
+        elif prev.data_ptr() != st.enc_a_state.data_ptr():
+            st.enc_a_state[:64].copy_(prev.reshape(-1))
+            st.enc_a_state[64] = 1.0
+    auds_t = None if auds is None else auds.contiguous().float()
+    eye_t = None if eye is None else eye.reshape(-1).float().contiguous()
+    pose6 = poses.reshape(-1).float().contiguous() if model.torso else None
+    bg_t, bg_scalar = None, 1.0
+    if bg_color is not None:
+        if torch.is_tensor(bg_color):
+            bg_t = bg_color.reshape(-1, 3).float()
+            bg_t = (bg_t.expand(N, 3) if bg_t.shape[0] != N else bg_t).contiguous()
+        else:
+            bg_scalar = float(bg_color)
+
+    if st.use_graph and not perturb:
+        key = (N, None if auds_t is None else tuple(auds_t.shape), eye_t is not None, bg_t is not None, bg_scalar, float(dt_gamma),
+               int(max_steps), float(T_thresh), float(model.mean_density_torso), model.density_bitfield.data_ptr())
+        entry = st.graphs.get(key)
+        if entry is None:
+            static = dict(rays_o=torch.empty_like(rays_o), rays_d=torch.empty_like(rays_d), bg_coords=torch.empty_like(bg_coords),
+                          auds=None if auds_t is None else torch.empty_like(auds_t), eye=None if eye_t is None else torch.empty_like(eye_t),
+                          pose6=None if pose6 is None else torch.empty_like(pose6), bg=None if bg_t is None else torch.empty_like(bg_t))
+            for k, v in (("rays_o", rays_o), ("rays_d", rays_d), ("bg_coords", bg_coords), ("auds", auds_t), ("eye", eye_t),
+                         ("pose6", pose6), ("bg", bg_t)):
+                if v is not None:
+                    static[k].copy_(v)
+            # warm-up outside capture (lazy kernel attributes, module loading) on a scratch copy of the smoothing state
+            saved = st.enc_a_state.clone()
+            _launch(model, st, static["rays_o"], static["rays_d"], static["auds"], static["bg_coords"], static["pose6"], static["eye"],
+                    static["bg"], bg_scalar, None, dt_gamma, max_steps, T_thresh)
+            st.enc_a_state.copy_(saved)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = _launch(model, st, static["rays_o"], static["rays_d"], static["auds"], static["bg_coords"], static["pose6"],
+                               static["eye"], static["bg"], bg_scalar, None, dt_gamma, max_steps, T_thresh)
+            st.enc_a_state.copy_(saved)  # capture does not execute, but keep the invariant explicit
+            entry = st.graphs[key] = (graph, static, outs)
+        graph, static, outs = entry
+        static["rays_o"].copy_(rays_o)
+        static["rays_d"].copy_(rays_d)
+        if static["bg_coords"].data_ptr() != bg_coords.data_ptr():
+            static["bg_coords"].copy_(bg_coords)
+        for k, v in (("auds", auds_t), ("eye", eye_t), ("pose6", pose6), ("bg", bg_t)):
+            if v is not None:
+                static[k].copy_(v)
+        graph.replay()
+        results = dict(outs)
+    else:
+        noises = torch.rand(N, device=dev) if perturb else None
+        results = _launch(model, st, rays_o, rays_d, auds_t, bg_coords, pose6, eye_t, bg_t, bg_scalar, noises, dt_gamma, max_steps,
+                          T_thresh)
+    if model.smooth_lips and auds is not None:
+        model.enc_a = st.enc_a_state[:64].view(1, 64)
+    st.frames += 1
+    results['depth'] = results['depth'].view(*prefix)
+    results['image'] = results['image'].view(*prefix, 3)
     return results
 
 
