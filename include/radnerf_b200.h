@@ -42,6 +42,8 @@ const char* rn_last_error_string(void);
 int rn_abi_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t rn_launch_count(void);
+/* account for the kernels of a captured CUDA graph that a replay launches again (host bookkeeping only) */
+void rn_note_graph_replay(uint64_t kernels_in_graph);
 
 /* ------------------------------------------------------------------ gridencoder ------------------- */
 
@@ -202,6 +204,9 @@ typedef struct rn_frame_head_desc {
     rn_grid_table grid3d, grid2d;
     const void* head_blob;       /* rn_head_blob_bytes() of interleaved fp16 weights (see radnerf_b200/frame.py) */
     const float* head_consts;    /* [3*64] from rn_frame_conditioning */
+    void* consts_ready_event;    /* optional cudaEvent_t: rn_frame_conditioning ran on ANOTHER stream and recorded this event; the
+                                    head waits for it only before its first network evaluation, so the audio nets overlap the
+                                    ray setup and the first march.  NULL = same stream, no wait. */
 } rn_frame_head_desc;
 
 typedef struct rn_frame_torso_desc {
@@ -221,6 +226,11 @@ uint32_t rn_torso_blob_bytes(void);
 int rn_frame_conditioning(const rn_conditioning_desc* d, void* stream);
 int rn_frame_head(const rn_frame_head_desc* d, void* stream);
 int rn_frame_torso(const rn_frame_torso_desc* d, void* stream);
+/* rn_frame_head bracketed by CUDA events on the launching stream (bench / diagnostics; synchronises the stream):
+ * ms [3*max_steps] = (march, eval, composite) per iteration, n_samples [max_steps] = samples evaluated per iteration */
+int rn_frame_head_timed(const rn_frame_head_desc* d, void* stream, float* ms, uint32_t* n_samples);
+/* diagnostics: device buffer of 8 uint64 cycle counters filled by the head kernel; NULL disables */
+void rn_debug_set_head_prof(void* counters);
 /* final blend + depth normalisation (nerf/renderer.py:299-310); bg_color [N,3] or NULL (then bg_scalar);
  * torso_alpha/torso_color NULL when there is no torso; torso_bg_out (nullable) receives results['torso_color'] */
 int rn_frame_finalize(uint32_t N, const float* weights_sum, float* depth, float* image, const float* nears,

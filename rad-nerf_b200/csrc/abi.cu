@@ -18,3 +18,5 @@ void set_error(const char* fmt, ...) {
 extern "C" const char* rn_last_error_string(void) { return rn::g_err; }
 extern "C" int rn_abi_version(void) { return 1; }
 extern "C" uint64_t rn_launch_count(void) { return rn::g_launch_count.load(); }
+// a replayed CUDA graph re-launches the kernels that were counted once at capture time
+extern "C" void rn_note_graph_replay(uint64_t kernels_in_graph) { rn::g_launch_count.fetch_add(kernels_in_graph); }

@@ -17,50 +17,60 @@ namespace {
 __device__ __forceinline__ float h16(float x) { return __half2float(__float2half_rn(x)); }
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.02f * x; }
 
-// Conv1d(k=3, pad=1) + bias + LeakyReLU(0.02) for F frames; in [F][Cin][Lin] -> out [F][Cout][Lout]
+// Conv1d(k=3, pad=1) + bias + LeakyReLU(0.02) for F frames; in [F][Cin][Lin] -> out [F][Cout][Lout].
+// Work item o = (co, f, lo) with (f, lo) fastest: the lanes of a warp share the output channel, so every weight load is a
+// warp-uniform broadcast (one L1 transaction) instead of 32 scattered rows, and the loads of consecutive taps pipeline.
 __device__ void conv_layer(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w, const float* __restrict__ b,
                            uint32_t F, uint32_t Cin, uint32_t Cout, uint32_t Lin, uint32_t stride) {
     const uint32_t Lout = (Lin + 2 - 3) / stride + 1;
     const uint32_t total = F * Cout * Lout;
     for (uint32_t o = threadIdx.x; o < total; o += blockDim.x) {
-        const uint32_t lo = o % Lout, co = (o / Lout) % Cout, f = o / (Lout * Cout);
+        const uint32_t lo = o % Lout, f = (o / Lout) % F, co = o / (Lout * F);
         const float* wi = w + (size_t)co * Cin * 3;
         const float* xi = in + (size_t)f * Cin * Lin;
+        const int l0 = (int)(lo * stride) - 1;
+        const bool in0 = l0 >= 0, in2 = l0 + 2 < (int)Lin;
         float acc = 0.f;
+#pragma unroll 4
         for (uint32_t ci = 0; ci < Cin; ++ci) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int li = (int)(lo * stride) - 1 + k;
-                if (li >= 0 && li < (int)Lin) acc = __fmaf_rn(h16(__ldg(wi + ci * 3 + k)), xi[ci * Lin + li], acc);
-            }
+            const float w0 = h16(__ldg(wi + ci * 3)), w1 = h16(__ldg(wi + ci * 3 + 1)), w2 = h16(__ldg(wi + ci * 3 + 2));
+            const float* x = xi + ci * Lin + l0;
+            if (in0) acc = __fmaf_rn(w0, x[0], acc);
+            acc = __fmaf_rn(w1, x[1], acc);
+            if (in2) acc = __fmaf_rn(w2, x[2], acc);
         }
         const float y = h16(h16(acc) + h16(__ldg(b + co)));
-        out[o] = h16(leaky(y));
+        out[((size_t)f * Cout + co) * Lout + lo] = h16(leaky(y));
     }
     __syncthreads();
 }
 
-// Linear(+bias) on R rows: in [R][K] -> out [R][N]
+// Linear(+bias) on R rows: in [R][K] -> out [R][N]; lanes run over the rows of one output feature (uniform weight loads)
 __device__ void linear_layer(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w, const float* __restrict__ b,
                              uint32_t R, uint32_t K, uint32_t N, bool act) {
     for (uint32_t o = threadIdx.x; o < R * N; o += blockDim.x) {
-        const uint32_t n = o % N, r = o / N;
+        const uint32_t r = o % R, n = o / R;
+        const float* wr = w + (size_t)n * K;
         float acc = 0.f;
-        for (uint32_t k = 0; k < K; ++k) acc = __fmaf_rn(h16(__ldg(w + (size_t)n * K + k)), in[r * K + k], acc);
+#pragma unroll 8
+        for (uint32_t k = 0; k < K; ++k) acc = __fmaf_rn(h16(__ldg(wr + k)), in[r * K + k], acc);
         float y = h16(acc + h16(__ldg(b + n)));
         if (act) y = h16(leaky(y));
-        out[o] = y;
+        out[r * N + n] = y;
     }
     __syncthreads();
 }
 
-// bias[n] = sum_k fp16(W[n, col0 + k]) * fp16(v[k])     (fp32 accumulate)
-__device__ void hoist(const float* __restrict__ W, uint32_t ld, uint32_t col0, const float* v, uint32_t K, uint32_t N, float* __restrict__ out,
-                      bool accumulate) {
-    for (uint32_t n = threadIdx.x; n < N; n += blockDim.x) {
-        float acc = accumulate ? out[n] : 0.f;
-        for (uint32_t k = 0; k < K; ++k) acc = __fmaf_rn(h16(__ldg(W + (size_t)n * ld + col0 + k)), h16(v[k]), acc);
-        out[n] = acc;
+// bias[n] = sum_k fp16(W[n, col0 + k]) * fp16(v[k])   (fp32 accumulate).  One warp per output row: lanes stride over k
+// (coalesced row reads), then a shuffle reduction.
+__device__ void hoist(const float* __restrict__ W, uint32_t ld, uint32_t col0, const float* v, uint32_t K, uint32_t N, float* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t n = warp; n < N; n += nwarps) {
+        float acc = 0.f;
+        for (uint32_t k = lane; k < K; k += 32) acc = __fmaf_rn(h16(__ldg(W + (size_t)n * ld + col0 + k)), h16(v[k]), acc);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) out[n] = acc;
     }
 }
 
@@ -124,7 +134,7 @@ audio_frame_kernel(AudioParams p) {
     }
 
     // ---- hoisted terms of the head
-    if (p.auds) hoist(p.w_amb1, 96, 32, s_enc, 64, 64, p.head_consts, false);
+    if (p.auds) hoist(p.w_amb1, 96, 32, s_enc, 64, 64, p.head_consts);
     else if (threadIdx.x < 64) p.head_consts[threadIdx.x] = 0.f;
     if (threadIdx.x < 64) {
         const float e = p.eye ? h16(__ldg(p.eye)) : 0.f;
@@ -133,7 +143,7 @@ audio_frame_kernel(AudioParams p) {
     if (p.ind_code) {
         if (threadIdx.x < 4) s_vec[threadIdx.x] = __ldg(p.ind_code + threadIdx.x);
         __syncthreads();
-        hoist(p.w_col1, 84, 80, s_vec, 4, 64, p.head_consts + 128, false);
+        hoist(p.w_col1, 84, 80, s_vec, 4, 64, p.head_consts + 128);
     } else if (threadIdx.x < 64) {
         p.head_consts[128 + threadIdx.x] = 0.f;
     }
@@ -155,8 +165,8 @@ audio_frame_kernel(AudioParams p) {
         }
         __syncthreads();
         const uint32_t K = p.ind_torso ? 62u : 54u;
-        hoist(p.w_def1, 42 + K, 42, s_vec, K, 64, p.torso_consts, false);
-        hoist(p.w_tor1, 32 + 42 + K, 74, s_vec, K, 32, p.torso_consts + 64, false);
+        hoist(p.w_def1, 42 + K, 42, s_vec, K, 64, p.torso_consts);
+        hoist(p.w_tor1, 32 + 42 + K, 74, s_vec, K, 32, p.torso_consts + 64);
     }
 }
 

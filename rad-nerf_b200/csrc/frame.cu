@@ -2,6 +2,7 @@
 #include "frame.cuh"
 #include "march.cuh"
 #include <cstring>
+#include <vector>
 
 using namespace rn;
 
@@ -29,7 +30,7 @@ extern "C" int rn_frame_conditioning(const rn_conditioning_desc* d, void* stream
     return launch_audio_frame(p, (cudaStream_t)stream);
 }
 
-extern "C" int rn_frame_head(const rn_frame_head_desc* d, void* stream) {
+static int frame_head_impl(const rn_frame_head_desc* d, cudaStream_t st, cudaEvent_t* ev /* nullable: 3*max_steps+1 events */) {
     RN_REQUIRE(d, "null descriptor");
     if (d->N == 0) return RN_OK;
     RN_REQUIRE(d->rays_o && d->rays_d && d->aabb && d->bitfield && d->weights_sum && d->depth && d->image && d->nears && d->fars,
@@ -40,7 +41,6 @@ extern "C" int rn_frame_head(const rn_frame_head_desc* d, void* stream) {
     RN_REQUIRE(d->max_steps >= 1 && d->max_steps <= (uint32_t)FRAME_MAX_ITERS, "max_steps must be in [1, 64] for the fused frame");
     RN_REQUIRE(d->cascade >= 1 && d->cascade <= 16 && d->grid_size >= 1, "bad cascade/grid_size");
     RN_REQUIRE(((uintptr_t)d->head_blob & 15) == 0, "head_blob must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
     FrameWorkspace w;
     carve(w, (uint8_t*)d->workspace, d->N);
     int rc = launch_frame_init(d->rays_o, d->rays_d, d->aabb, d->N, d->min_near, d->max_steps, d->nears, d->fars, w, d->weights_sum,
@@ -55,12 +55,41 @@ extern "C" int rn_frame_head(const rn_frame_head_desc* d, void* stream) {
     hp.prof = (unsigned long long*)g_head_prof;
     const uint32_t max_tiles = (d->N + EVAL_TILE - 1) / EVAL_TILE;  // n_alive * n_step <= N in every iteration
     // n_step >= 1, so the reference's loop runs at most max_steps iterations
+    if (ev) cudaEventRecord(ev[0], st);
     for (uint32_t it = 0; it < d->max_steps; ++it) {
         if ((rc = launch_march_compact(it, d->N, w, d->rays_o, d->rays_d, d->fars, mp, d->noises, st))) return rc;
+        if (ev) cudaEventRecord(ev[3 * it + 1], st);
+        if (it == 0 && d->consts_ready_event) cudaStreamWaitEvent(st, (cudaEvent_t)d->consts_ready_event, 0);
         if ((rc = launch_head_eval(hp, w.ctl + it, max_tiles, st))) return rc;
+        if (ev) cudaEventRecord(ev[3 * it + 2], st);
         if ((rc = launch_composite_compact(it, d->N, d->max_steps, d->T_thresh, w, d->weights_sum, d->depth, d->image, st))) return rc;
+        if (ev) cudaEventRecord(ev[3 * it + 3], st);
     }
     return RN_OK;
+}
+
+extern "C" int rn_frame_head(const rn_frame_head_desc* d, void* stream) { return frame_head_impl(d, (cudaStream_t)stream, nullptr); }
+
+// diagnostics / bench: the same launch sequence bracketed by CUDA events on the launching stream.  SYNCHRONISES the stream.
+// ms [3 * max_steps] = (march, eval, composite) per iteration; n_samples [max_steps] = samples evaluated per iteration.
+extern "C" int rn_frame_head_timed(const rn_frame_head_desc* d, void* stream, float* ms, uint32_t* n_samples) {
+    RN_REQUIRE(d && ms && n_samples, "null pointer");
+    const uint32_t n_ev = 3 * d->max_steps + 1;
+    std::vector<cudaEvent_t> ev(n_ev);
+    for (auto& e : ev) cudaEventCreate(&e);
+    int rc = frame_head_impl(d, (cudaStream_t)stream, ev.data());
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (rc == RN_OK && e != cudaSuccess) { set_error("rn_frame_head_timed: %s", cudaGetErrorString(e)); rc = (int)e; }
+    if (rc == RN_OK) {
+        for (uint32_t i = 0; i + 1 < n_ev; ++i) cudaEventElapsedTime(ms + i, ev[i], ev[i + 1]);
+        FrameWorkspace w;
+        carve(w, (uint8_t*)d->workspace, d->N);
+        std::vector<FrameCtl> ctl(d->max_steps);
+        cudaMemcpy(ctl.data(), w.ctl, sizeof(FrameCtl) * d->max_steps, cudaMemcpyDeviceToHost);
+        for (uint32_t it = 0; it < d->max_steps; ++it) n_samples[it] = ctl[it].done ? 0u : ctl[it].n_samples;
+    }
+    for (auto& e2 : ev) cudaEventDestroy(e2);
+    return rc;
 }
 
 extern "C" int rn_frame_torso(const rn_frame_torso_desc* d, void* stream) {

@@ -37,7 +37,7 @@ class FrameHeadDesc(C.Structure):
                 ("rays_o", _vp), ("rays_d", _vp), ("aabb", _vp), ("bitfield", _vp), ("noises", _vp),
                 ("weights_sum", _vp), ("depth", _vp), ("image", _vp), ("nears", _vp), ("fars", _vp),
                 ("workspace", _vp), ("workspace_bytes", _u64),
-                ("grid3d", GridTable), ("grid2d", GridTable), ("head_blob", _vp), ("head_consts", _vp)]
+                ("grid3d", GridTable), ("grid2d", GridTable), ("head_blob", _vp), ("head_consts", _vp), ("consts_ready_event", _vp)]
 
 
 class FrameTorsoDesc(C.Structure):
@@ -47,6 +47,7 @@ class FrameTorsoDesc(C.Structure):
 
 
 abi.register("rn_frame_workspace_bytes", [_u32], _u64)
+abi.register("rn_note_graph_replay", [_u64], None)
 abi.register("rn_head_blob_bytes", [], _u32)
 abi.register("rn_torso_blob_bytes", [], _u32)
 abi.register("rn_frame_conditioning", [C.POINTER(ConditioningDesc), _vp])
@@ -97,6 +98,8 @@ class FusedState:
         self.enc_a_state = torch.zeros(65, device=dev)  # [0..63] smoothed audio code, [64] validity flag (device side)
         self.frames = 0
         self.graphs = {}      # config key -> (CUDAGraph, static inputs, outputs)
+        self.side = torch.cuda.Stream(device=dev)
+        self.cond_event = torch.cuda.Event()
         self.use_graph = True
 
     def refresh_weights(self, model):
@@ -146,14 +149,7 @@ def _grid_table(enc, table):
     return GridTable(table.data_ptr(), enc.offsets.data_ptr(), float(np.log2(enc.per_level_scale)), int(enc.base_resolution))
 
 
-def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_scalar, noises, dt_gamma, max_steps, T_thresh):
-    """the frame's launch sequence (capturable: no host sync, outputs allocated with torch.empty)"""
-    L = abi.lib()
-    N = rays_o.shape[0]
-    dev = rays_o.device
-    stream = abi.cur_stream()
-
-    # ---- per-frame conditioning
+def conditioning_desc(model, st, auds, eye_t, pose6):
     an, at = model.audio_net, getattr(model, "audio_att_net", None)
     cd = ConditioningDesc()
     if auds is not None:
@@ -179,9 +175,11 @@ def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_s
         cd.w_def1 = model.torso_deform_net.net[0].weight.data_ptr()
         cd.w_tor1 = model.torso_net.net[0].weight.data_ptr()
         cd.pose6, cd.ind_torso, cd.torso_consts = pose6.data_ptr(), model.individual_codes_torso.data_ptr(), st.torso_consts.data_ptr()
-    abi.check(L.rn_frame_conditioning(C.byref(cd), stream))
+    return cd
 
-    # ---- head
+
+def head_desc(model, st, rays_o, rays_d, noises, dt_gamma, max_steps, T_thresh):
+    N, dev = rays_o.shape[0], rays_o.device
     weights_sum = torch.empty(N, device=dev)
     depth = torch.empty(N, device=dev)
     image = torch.empty(N, 3, device=dev)
@@ -197,6 +195,28 @@ def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_s
     hd.workspace, hd.workspace_bytes = st.workspace.data_ptr(), st.ws_bytes
     hd.grid3d, hd.grid2d = _grid_table(model.encoder, st.table3), _grid_table(model.encoder_ambient, st.table2)
     hd.head_blob, hd.head_consts = st.head_blob.data_ptr(), st.head_consts.data_ptr()
+    return hd, (weights_sum, depth, image, nears, fars)
+
+
+def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_scalar, noises, dt_gamma, max_steps, T_thresh):
+    """the frame's launch sequence (capturable: no host sync, outputs allocated with torch.empty)"""
+    L = abi.lib()
+    N = rays_o.shape[0]
+    dev = rays_o.device
+    stream = abi.cur_stream()
+
+    # ---- per-frame conditioning on a forked stream: the audio nets overlap ray setup + the first march; the head waits for
+    #      the event only before its first network evaluation (works the same under CUDA-graph capture: fork/join edges)
+    cd = conditioning_desc(model, st, auds, eye_t, pose6)
+    cur = torch.cuda.current_stream()
+    st.side.wait_stream(cur)
+    with torch.cuda.stream(st.side):
+        abi.check(L.rn_frame_conditioning(C.byref(cd), abi.cur_stream()))
+        st.cond_event.record(st.side)
+
+    # ---- head
+    hd, (weights_sum, depth, image, nears, fars) = head_desc(model, st, rays_o, rays_d, noises, dt_gamma, max_steps, T_thresh)
+    hd.consts_ready_event = st.cond_event.cuda_event
     abi.check(L.rn_frame_head(C.byref(hd), stream))
 
     results = {}
@@ -217,6 +237,7 @@ def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_s
     abi.check(L.rn_frame_finalize(N, weights_sum.data_ptr(), depth.data_ptr(), image.data_ptr(), nears.data_ptr(), fars.data_ptr(),
                                   _p(bg_t), bg_scalar, _p(st.torso_alpha) if model.torso else None,
                                   _p(st.torso_color) if model.torso else None, _p(torso_bg), stream))
+    cur.wait_stream(st.side)  # join (the torso consts were produced on the side stream too; already ordered by the event)
     results['depth'] = depth
     results['image'] = image
     results['weights_sum'] = weights_sum
@@ -284,12 +305,13 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
             st.enc_a_state.copy_(saved)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            k0 = abi.launch_count()
             with torch.cuda.graph(graph):
                 outs = _launch(model, st, static["rays_o"], static["rays_d"], static["auds"], static["bg_coords"], static["pose6"],
                                static["eye"], static["bg"], bg_scalar, None, dt_gamma, max_steps, T_thresh)
             st.enc_a_state.copy_(saved)  # capture does not execute, but keep the invariant explicit
-            entry = st.graphs[key] = (graph, static, outs)
-        graph, static, outs = entry
+            entry = st.graphs[key] = (graph, static, outs, abi.launch_count() - k0)
+        graph, static, outs, n_kernels = entry
         static["rays_o"].copy_(rays_o)
         static["rays_d"].copy_(rays_d)
         if static["bg_coords"].data_ptr() != bg_coords.data_ptr():
@@ -298,6 +320,7 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
             if v is not None:
                 static[k].copy_(v)
         graph.replay()
+        abi.lib().rn_note_graph_replay(n_kernels)
         results = dict(outs)
     else:
         noises = torch.rand(N, device=dev) if perturb else None
@@ -323,5 +346,54 @@ def frame_stats(model):
     return out
 
 
-def roofline_entries(model, f, bg_local, kw, hbm, tflops):
-    return []
+abi.register("rn_frame_head_timed", [C.POINTER(FrameHeadDesc), _vp, _vp, _vp])
+
+# algorithmic bytes per sample of the fused head kernel: 3-D fp16 gathers + 2-D fp16 gathers (the feature
+# writes/re-reads of the unfused formulation, 64 B each, never happen) + the sample record in and the evaluation out
+HEAD_BYTES_PER_SAMPLE = (4 * 3 + 16 * 8 * 2 * 2) + (16 * 4 * 2 * 2) + 16 + 16
+HEAD_FLOP_PER_SAMPLE = 47872  # hoisted MLP chain
+
+
+def roofline_entries(model, f, bg_local, kw, hbm, tflops, reps=10):
+    """per-kernel device times of the head loop measured with CUDA events on the launching stream (rn_frame_head_timed)"""
+    L = abi.lib()
+    # make sure the fused state / conditioning vectors exist
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        model.render(f["ro"], f["rd"], f["auds"], bg_local, f["pose6"], eye=f["eye"], index=0, path="fused", **kw)
+    st = model._fused
+    rays_o, rays_d = f["ro"][0].contiguous(), f["rd"][0].contiguous()
+    hd, keep = head_desc(model, st, rays_o, rays_d, None, kw["dt_gamma"], kw["max_steps"], 1e-4)
+    ms = (C.c_float * (3 * kw["max_steps"]))()
+    ns = (C.c_uint32 * kw["max_steps"])()
+    tot = np.zeros(3)
+    samples = 0
+    evals = []
+    for r in range(reps + 2):
+        abi.check(L.rn_frame_head_timed(C.byref(hd), abi.cur_stream(), ms, ns))
+        if r < 2:
+            continue
+        for it in range(kw["max_steps"]):
+            if ns[it] == 0 and it > 0:
+                break
+            tot += np.array([ms[3 * it], ms[3 * it + 1], ms[3 * it + 2]])
+            samples += ns[it]
+            evals.append((ns[it], ms[3 * it + 1]))
+    n_launch = len(evals)
+    ev_ms, ev_samples = sum(e[1] for e in evals), sum(e[0] for e in evals)
+    N = rays_o.shape[0]
+    head = {"kernel": "head_eval_kernel (fused 3-D encode + ambient MLP + 2-D encode + sigma MLP + SH + colour MLP, tcgen05)",
+            "bound": "hbm", "units": ev_samples / n_launch, "unit_name": "samples", "bytes_per_unit": HEAD_BYTES_PER_SAMPLE,
+            "ms": ev_ms / n_launch, "achieved": ev_samples * HEAD_BYTES_PER_SAMPLE / ev_ms / 1e6, "peak": hbm, "unit": "GB/s",
+            "frac": ev_samples * HEAD_BYTES_PER_SAMPLE / ev_ms / 1e6 / hbm, "gunits_per_s": ev_samples / ev_ms / 1e6,
+            "launches_per_frame": n_launch / reps, "ms_per_frame": ev_ms / reps,
+            "tensor_tflops": ev_samples * HEAD_FLOP_PER_SAMPLE / ev_ms / 1e9,
+            "tensor_frac_of_peak": ev_samples * HEAD_FLOP_PER_SAMPLE / ev_ms / 1e9 / tflops}
+    march = {"kernel": "march_compact_kernel (occupancy DDA + sample compaction)", "bound": "hbm", "ms_per_frame": tot[0] / reps,
+             "bytes_per_frame": 44.0 * N + 32.0 * samples / reps, "ms": tot[0] / n_launch}
+    march.update(achieved=march["bytes_per_frame"] / march["ms_per_frame"] / 1e6, peak=hbm, unit="GB/s")
+    march["frac"] = march["achieved"] / hbm
+    comp = {"kernel": "composite_compact_kernel (compositing + survivor compaction + loop control)", "bound": "hbm",
+            "ms_per_frame": tot[2] / reps, "bytes_per_frame": 24.0 * samples / reps + 56.0 * N, "ms": tot[2] / n_launch}
+    comp.update(achieved=comp["bytes_per_frame"] / comp["ms_per_frame"] / 1e6, peak=hbm, unit="GB/s")
+    comp["frac"] = comp["achieved"] / hbm
+    return [head, march, comp]

@@ -75,3 +75,21 @@ p = prof.cpu().numpy()
 tot = p[4]
 print("head_eval phase cycles (sum over %d group-runs): enc3 %.1f%% enc2 %.1f%% mma-wait %.1f%% epilogue(4-chunk) %.1f%% other %.1f%%; cycles/tile/group = %.0f" % (
     p[5], 100*p[0]/tot, 100*p[1]/tot, 100*p[2]/tot, 100*p[3]/tot, 100*(tot-p[0]-p[1]-p[2]-p[3])/tot, tot / (815354/128)))
+
+# ---- conditioning kernel alone: 20 launches inside one CUDA graph -> pure device time
+st = model._fused
+f0 = devf[0]
+cd = frame.conditioning_desc(model, st, f0["auds"].contiguous(), f0["eye"].reshape(-1).contiguous(), f0["pose6"].reshape(-1).contiguous())
+saved = st.enc_a_state.clone()
+Lr.rn_frame_conditioning(C.byref(cd), abi.cur_stream()); torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    for _ in range(20): Lr.rn_frame_conditioning(C.byref(cd), abi.cur_stream())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+st.enc_a_state.copy_(saved)
+print("audio_frame_kernel alone: %.1f us" % (e0.elapsed_time(e1) / 20 * 1e3))
+from radnerf_b200 import roofline
+hbm, tf, _ = roofline.peaks()
+for e in frame.roofline_entries(model, devf[0], bg_t, kw, hbm, tf):
+    print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in e.items()})
