@@ -48,7 +48,8 @@ struct FrameWorkspace {
     uint32_t* misc;       // [8]: 0 = n_torso
     int32_t* alive[2];    // [N] each
     float* rays_t;        // [N]
-    uint2* ray_off;       // [N]  (offset, count) of the alive slot's samples this iteration
+    uint32_t* ray_cnt;    // [N]    samples the alive slot's ray got this iteration
+    uint32_t* sample_idx; // [8][N] position of its k-th sample in the compacted (k-major per CTA) sample list
     float4* samples;      // [N]  xyz + ray id bits
     float2* deltas;       // [N]  (dt, t after)
     float4* evals;        // [N]  (sigma, r, g, b)
