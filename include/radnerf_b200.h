@@ -176,21 +176,24 @@ typedef struct rn_grid_table {
 } rn_grid_table;
 
 /* per-frame conditioning: AudioNet + AudioAttNet + lip smoothing + hoisted first-layer bias vectors
- * (nerf/network.py:10-67,170-185; nerf/renderer.py:187-204).  All weight pointers are the fp32 parameters. */
+ * (nerf/network.py:10-67,170-185; nerf/renderer.py:187-204).  Weight/bias pointers are fp16 COPIES of the fp32
+ * parameters (what the reference's autocast produces per call; f32->f16 conversion inside the kernel would run on the
+ * quarter-rate conversion pipe); auds, eye, codes and pose stay fp32. */
 typedef struct rn_conditioning_desc {
     const float* auds;           /* [F, Cin, 16] or NULL (no audio) */
     uint32_t F, Cin, att, smooth, reserved;
-    const float* conv_w[4]; const float* conv_b[4];
-    const float* fc_w[2]; const float* fc_b[2];
-    const float* att_w[5]; const float* att_b[5];
-    const float* att_fc_w; const float* att_fc_b;
+    const void* conv_w[4]; const void* conv_b[4];      /* fp16 */
+    const void* fc_w[2]; const void* fc_b[2];
+    const void* att_w[5]; const void* att_b[5];
+    const void* att_fc_w; const void* att_fc_b;
     float* enc_a_state;          /* [65] in/out: smoothed code [0..63], [64] != 0 once it holds a previous frame (device-side flag,
                                     so a captured CUDA graph serves first and later frames alike) */
     float lambda;
-    const float* w_amb1; const float* w_sig1; const float* w_col1;
+    const void* w_amb1; const void* w_sig1; const void* w_col1;   /* fp16 [64,96] [64,65] [64,84] */
     const float* eye; const float* ind_code;
     float* head_consts;          /* out [3*64] */
-    const float* w_def1; const float* w_tor1; const float* pose6; const float* ind_torso;
+    const void* w_def1; const void* w_tor1;                        /* fp16 [64,104] [32,136] or NULL */
+    const float* pose6; const float* ind_torso;
     float* torso_consts;         /* out [64+32] */
 } rn_conditioning_desc;
 

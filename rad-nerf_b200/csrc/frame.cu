@@ -10,6 +10,9 @@ static void* g_head_prof = nullptr;
 // diagnostics: device buffer of 8 uint64 cycle counters filled by head_eval (enc3, enc2, mma, epilogue, tile, groups); NULL disables
 extern "C" void rn_debug_set_head_prof(void* p) { g_head_prof = p; }
 
+namespace rn { void set_audio_prof(void* p); }
+extern "C" void rn_debug_set_audio_prof(void* p) { rn::set_audio_prof(p); }
+
 extern "C" uint64_t rn_frame_workspace_bytes(uint32_t N) {
     FrameWorkspace w;
     return (uint64_t)carve(w, nullptr, N);

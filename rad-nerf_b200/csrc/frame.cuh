@@ -85,17 +85,18 @@ struct TorsoEvalParams {
 struct AudioParams {
     const float* auds;   // [F, Cin, 16]
     uint32_t F, Cin, att, smooth, reserved;
-    const float* conv_w[4]; const float* conv_b[4];          // AudioNet.encoder_conv.{0,2,4,6}
-    const float* fc_w[2]; const float* fc_b[2];              // AudioNet.encoder_fc1.{0,2}
-    const float* att_w[5]; const float* att_b[5];            // AudioAttNet.attentionConvNet.{0,2,4,6,8}
-    const float* att_fc_w; const float* att_fc_b;            // AudioAttNet.attentionNet.0
+    // all weights/biases below are fp16 COPIES of the fp32 parameters (the reference's autocast casts them per call)
+    const __half* conv_w[4]; const __half* conv_b[4];        // AudioNet.encoder_conv.{0,2,4,6}
+    const __half* fc_w[2]; const __half* fc_b[2];            // AudioNet.encoder_fc1.{0,2}
+    const __half* att_w[5]; const __half* att_b[5];          // AudioAttNet.attentionConvNet.{0,2,4,6,8}
+    const __half* att_fc_w; const __half* att_fc_b;          // AudioAttNet.attentionNet.0
     float* enc_a_state;  // [65]: smoothed code of the previous frame + validity flag at [64]
     float lambda;
-    const float* w_amb1; const float* w_sig1; const float* w_col1;   // [64,96] [64,65] [64,84] fp32 parameters
+    const __half* w_amb1; const __half* w_sig1; const __half* w_col1;   // [64,96] [64,65] [64,84] fp16 copies
     const float* eye;        // device [1] or null
     const float* ind_code;   // device [4] or null
     float* head_consts;      // [3][64]
-    const float* w_def1; const float* w_tor1;  // [64,104] [32,136] or null (no torso)
+    const __half* w_def1; const __half* w_tor1;  // [64,104] [32,136] fp16 copies, or null (no torso)
     const float* pose6;      // device [6]
     const float* ind_torso;  // device [8] or null
     float* torso_consts;     // [64 + 32]

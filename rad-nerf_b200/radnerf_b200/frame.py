@@ -104,7 +104,9 @@ class FusedState:
 
     def refresh_weights(self, model):
         params = [model.encoder.embeddings, model.encoder_ambient.embeddings] + list(model.ambient_net.parameters()) + \
-            list(model.sigma_net.parameters()) + list(model.color_net.parameters())
+            list(model.sigma_net.parameters()) + list(model.color_net.parameters()) + list(model.audio_net.parameters())
+        if getattr(model, 'audio_att_net', None) is not None:
+            params += list(model.audio_att_net.parameters())
         if model.torso:
             params += [model.torso_encoder.embeddings] + list(model.torso_deform_net.parameters()) + list(model.torso_net.parameters())
         versions = tuple((p.data_ptr(), p._version) for p in params)
@@ -112,6 +114,7 @@ class FusedState:
             return
         self.versions = versions
         self.graphs.clear()  # captured graphs hold pointers to the old blobs
+        self.h16 = {}  # fp16 copies of the small-net parameters used by the conditioning kernel
         self.table3 = model.encoder.embeddings.detach().to(torch.float16).contiguous()
         self.table2 = model.encoder_ambient.embeddings.detach().to(torch.float16).contiguous()
         a, s, c = model.ambient_net.net, model.sigma_net.net, model.color_net.net
@@ -151,29 +154,36 @@ def _grid_table(enc, table):
 
 def conditioning_desc(model, st, auds, eye_t, pose6):
     an, at = model.audio_net, getattr(model, "audio_att_net", None)
+
+    def H(param):  # cached fp16 copy (cleared by refresh_weights when any parameter changes)
+        t = st.h16.get(id(param))
+        if t is None:
+            t = st.h16[id(param)] = param.detach().to(torch.float16).contiguous()
+        return t.data_ptr()
+
     cd = ConditioningDesc()
     if auds is not None:
         cd.auds, cd.F, cd.Cin = auds.data_ptr(), auds.shape[0], auds.shape[1]
     cd.att = int(model.att)
     cd.smooth = int(bool(model.smooth_lips))
     for i, k in enumerate((0, 2, 4, 6)):
-        cd.conv_w[i], cd.conv_b[i] = an.encoder_conv[k].weight.data_ptr(), an.encoder_conv[k].bias.data_ptr()
+        cd.conv_w[i], cd.conv_b[i] = H(an.encoder_conv[k].weight), H(an.encoder_conv[k].bias)
     for i, k in enumerate((0, 2)):
-        cd.fc_w[i], cd.fc_b[i] = an.encoder_fc1[k].weight.data_ptr(), an.encoder_fc1[k].bias.data_ptr()
+        cd.fc_w[i], cd.fc_b[i] = H(an.encoder_fc1[k].weight), H(an.encoder_fc1[k].bias)
     if at is not None:
         for i, k in enumerate((0, 2, 4, 6, 8)):
-            cd.att_w[i], cd.att_b[i] = at.attentionConvNet[k].weight.data_ptr(), at.attentionConvNet[k].bias.data_ptr()
-        cd.att_fc_w, cd.att_fc_b = at.attentionNet[0].weight.data_ptr(), at.attentionNet[0].bias.data_ptr()
+            cd.att_w[i], cd.att_b[i] = H(at.attentionConvNet[k].weight), H(at.attentionConvNet[k].bias)
+        cd.att_fc_w, cd.att_fc_b = H(at.attentionNet[0].weight), H(at.attentionNet[0].bias)
     cd.enc_a_state, cd.lambda_ = st.enc_a_state.data_ptr(), 0.35
-    cd.w_amb1 = model.ambient_net.net[0].weight.data_ptr()
-    cd.w_sig1 = model.sigma_net.net[0].weight.data_ptr()
-    cd.w_col1 = model.color_net.net[0].weight.data_ptr()
+    cd.w_amb1 = H(model.ambient_net.net[0].weight)
+    cd.w_sig1 = H(model.sigma_net.net[0].weight)
+    cd.w_col1 = H(model.color_net.net[0].weight)
     cd.eye = _p(eye_t)
     cd.ind_code = model.individual_codes.data_ptr()  # row 0 (inference uses a fixed code, renderer.py:201-202)
     cd.head_consts = st.head_consts.data_ptr()
     if model.torso:
-        cd.w_def1 = model.torso_deform_net.net[0].weight.data_ptr()
-        cd.w_tor1 = model.torso_net.net[0].weight.data_ptr()
+        cd.w_def1 = H(model.torso_deform_net.net[0].weight)
+        cd.w_tor1 = H(model.torso_net.net[0].weight)
         cd.pose6, cd.ind_torso, cd.torso_consts = pose6.data_ptr(), model.individual_codes_torso.data_ptr(), st.torso_consts.data_ptr()
     return cd
 

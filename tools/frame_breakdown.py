@@ -89,6 +89,14 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
 st.enc_a_state.copy_(saved)
 print("audio_frame_kernel alone: %.1f us" % (e0.elapsed_time(e1) / 20 * 1e3))
+aprof = torch.zeros(16, dtype=torch.int64, device=dev)
+Lr.rn_debug_set_audio_prof.argtypes = [C.c_void_p]
+Lr.rn_debug_set_audio_prof(aprof.data_ptr())
+Lr.rn_frame_conditioning(C.byref(cd), abi.cur_stream()); torch.cuda.synchronize()
+Lr.rn_debug_set_audio_prof(None)
+st.enc_a_state.copy_(saved)
+ap = aprof.cpu().numpy()
+print("audio kernel stage cycles [load, conv1, conv2-4, fc, att-convs, att-fc+softmax+sum+smooth, head hoists, torso hoists]:", [int(ap[i+1]-ap[i]) for i in range(8)])
 from radnerf_b200 import roofline
 hbm, tf, _ = roofline.peaks()
 for e in frame.roofline_entries(model, devf[0], bg_t, kw, hbm, tf):
