@@ -170,9 +170,14 @@ int rn_get_rays(const float* pose, float fx, float fy, float cx, float cy, uint3
 
 typedef struct rn_grid_table {
     const void* table_f16;   /* [rows, 2] fp16 */
-    const int32_t* offsets;  /* [17] */
+    const int32_t* offsets;  /* [17] the encoder's offsets (gridencoder/grid.py:118-131): level sizes and wrap rules */
     float S;                 /* log2(per_level_scale) */
     uint32_t H;              /* base resolution */
+    const int32_t* packed_offsets; /* [16] first row of each level inside table_f16.  The fused kernels index a wrapped
+                                      (size-capped) level as ((i & (size-1)) | first_row), one logic op instead of an
+                                      and + 64-bit add per corner, so such a level must start at a multiple of its
+                                      power-of-two size: radnerf_b200/frame.py re-packs its fp16 copy accordingly.
+                                      A table that violates this traps the kernel.  Never NULL. */
 } rn_grid_table;
 
 /* per-frame conditioning: AudioNet + AudioAttNet + lip smoothing + hoisted first-layer bias vectors

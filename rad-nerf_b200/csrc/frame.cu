@@ -1,3 +1,4 @@
+#include <algorithm>
 // frame.cu -- C-ABI entry points of the fused inference frame (see frame.cuh for the pipeline).
 #include "frame.cuh"
 #include "march.cuh"
@@ -33,12 +34,16 @@ extern "C" int rn_frame_conditioning(const rn_conditioning_desc* d, void* stream
     return launch_audio_frame(p, (cudaStream_t)stream);
 }
 
+static uint32_t g_debug_iters = 0;
+extern "C" void rn_debug_set_max_iters(uint32_t n) { g_debug_iters = n; }
+
 static int frame_head_impl(const rn_frame_head_desc* d, cudaStream_t st, cudaEvent_t* ev /* nullable: 3*max_steps+1 events */) {
     RN_REQUIRE(d, "null descriptor");
     if (d->N == 0) return RN_OK;
     RN_REQUIRE(d->rays_o && d->rays_d && d->aabb && d->bitfield && d->weights_sum && d->depth && d->image && d->nears && d->fars,
                "null pointer");
     RN_REQUIRE(d->workspace && d->workspace_bytes >= rn_frame_workspace_bytes(d->N), "workspace too small");
+    RN_REQUIRE(d->grid3d.packed_offsets && d->grid2d.packed_offsets, "grid tables need packed_offsets");
     RN_REQUIRE(d->grid3d.table_f16 && d->grid3d.offsets && d->grid2d.table_f16 && d->grid2d.offsets && d->head_blob && d->head_consts,
                "null network pointer");
     RN_REQUIRE(d->max_steps >= 1 && d->max_steps <= (uint32_t)FRAME_MAX_ITERS, "max_steps must be in [1, 64] for the fused frame");
@@ -51,15 +56,16 @@ static int frame_head_impl(const rn_frame_head_desc* d, cudaStream_t st, cudaEve
     if (rc) return rc;
     const MarchParams mp = make_march_params(d->bound, d->dt_gamma, d->max_steps, d->cascade, d->grid_size, d->bitfield);
     HeadEvalParams hp;
-    hp.table3 = (const __half*)d->grid3d.table_f16; hp.offs3 = d->grid3d.offsets; hp.S3 = d->grid3d.S; hp.H3 = d->grid3d.H;
-    hp.table2 = (const __half*)d->grid2d.table_f16; hp.offs2 = d->grid2d.offsets; hp.S2 = d->grid2d.S; hp.H2 = d->grid2d.H;
+    hp.table3 = (const __half*)d->grid3d.table_f16; hp.offs3 = d->grid3d.offsets; hp.poffs3 = d->grid3d.packed_offsets; hp.S3 = d->grid3d.S; hp.H3 = d->grid3d.H;
+    hp.table2 = (const __half*)d->grid2d.table_f16; hp.offs2 = d->grid2d.offsets; hp.poffs2 = d->grid2d.packed_offsets; hp.S2 = d->grid2d.S; hp.H2 = d->grid2d.H;
     hp.blob = (const uint8_t*)d->head_blob; hp.consts = d->head_consts; hp.rays_d = d->rays_d;
     hp.samples = w.samples; hp.evals = w.evals; hp.bound = d->bound; hp.inv2bound = 1.0f / (2.0f * d->bound);
     hp.prof = (unsigned long long*)g_head_prof;
     const uint32_t max_tiles = (d->N + EVAL_TILE - 1) / EVAL_TILE;  // n_alive * n_step <= N in every iteration
     // n_step >= 1, so the reference's loop runs at most max_steps iterations
     if (ev) cudaEventRecord(ev[0], st);
-    for (uint32_t it = 0; it < d->max_steps; ++it) {
+    const uint32_t n_iters = g_debug_iters ? std::min(g_debug_iters, d->max_steps) : d->max_steps;
+    for (uint32_t it = 0; it < n_iters; ++it) {
         if ((rc = launch_march_compact(it, d->N, w, d->rays_o, d->rays_d, d->fars, mp, d->noises, st))) return rc;
         if (ev) cudaEventRecord(ev[3 * it + 1], st);
         if (it == 0 && d->consts_ready_event) cudaStreamWaitEvent(st, (cudaEvent_t)d->consts_ready_event, 0);
@@ -100,7 +106,7 @@ extern "C" int rn_frame_torso(const rn_frame_torso_desc* d, void* stream) {
     if (d->N == 0) return RN_OK;
     RN_REQUIRE(d->bg_coords && d->density_grid_torso && d->torso_alpha && d->torso_color && d->torso_blob && d->torso_consts, "null pointer");
     RN_REQUIRE(d->workspace && d->workspace_bytes >= rn_frame_workspace_bytes(d->N), "workspace too small");
-    RN_REQUIRE(d->grid2d.table_f16 && d->grid2d.offsets, "null network pointer");
+    RN_REQUIRE(d->grid2d.table_f16 && d->grid2d.offsets && d->grid2d.packed_offsets, "null network pointer");
     RN_REQUIRE(((uintptr_t)d->torso_blob & 15) == 0, "torso_blob must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     FrameWorkspace w;
@@ -109,7 +115,7 @@ extern "C" int rn_frame_torso(const rn_frame_torso_desc* d, void* stream) {
     int rc = launch_torso_mask(d->bg_coords, d->density_grid_torso, d->grid_size, d->thresh, d->N, w, st);
     if (rc) return rc;
     TorsoEvalParams tp;
-    tp.table = (const __half*)d->grid2d.table_f16; tp.offs = d->grid2d.offsets; tp.S = d->grid2d.S; tp.H = d->grid2d.H;
+    tp.table = (const __half*)d->grid2d.table_f16; tp.offs = d->grid2d.offsets; tp.poffs = d->grid2d.packed_offsets; tp.S = d->grid2d.S; tp.H = d->grid2d.H;
     tp.blob = (const uint8_t*)d->torso_blob; tp.consts = d->torso_consts; tp.bg_coords = d->bg_coords; tp.pix = w.torso_pix;
     tp.n_pix = w.misc; tp.out = w.torso_out; tp.shrink = d->shrink;
     if ((rc = launch_torso_eval(tp, (d->N + EVAL_TILE - 1) / EVAL_TILE, st))) return rc;

@@ -59,8 +59,8 @@ struct FrameWorkspace {
 size_t carve(FrameWorkspace& w, uint8_t* base, uint32_t N);
 
 struct HeadEvalParams {
-    const __half* table3; const int32_t* offs3; float S3; uint32_t H3;
-    const __half* table2; const int32_t* offs2; float S2; uint32_t H2;
+    const __half* table3; const int32_t* offs3; const int32_t* poffs3; float S3; uint32_t H3;
+    const __half* table2; const int32_t* offs2; const int32_t* poffs2; float S2; uint32_t H2;
     const uint8_t* blob;      // HEAD_BLOB_BYTES, interleaved fp16
     const float* consts;      // [3][64] fp32: ambient-L1 bias, sigma-L1 bias, colour-L1 bias
     const float* rays_d;      // [N,3]
@@ -71,7 +71,7 @@ struct HeadEvalParams {
 };
 
 struct TorsoEvalParams {
-    const __half* table; const int32_t* offs; float S; uint32_t H;
+    const __half* table; const int32_t* offs; const int32_t* poffs; float S; uint32_t H;
     const uint8_t* blob;       // TORSO_BLOB_BYTES
     const float* consts;       // [64] deform-L1 bias, [32] torso-L1 bias
     const float* bg_coords;    // [N,2]

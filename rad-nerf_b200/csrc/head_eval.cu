@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(HEAD_GROUPS * 128, 1)
 head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ FastLevel lv3[16], lv2[16];
-    __shared__ float s_bias[3][64];
+    __shared__ __align__(128) uint8_t s_ones[128 * 16 * 2];        // constant A operand [128 x 16]: columns 0, 1 = 1.0
+    __shared__ __align__(128) uint8_t s_biasop[3][64 * 16 * 2];    // B operands [64 x 16]: columns 0, 1 = hi / lo halves of the hoisted term
     __shared__ __align__(8) uint64_t mbar_group[HEAD_GROUPS];
     __shared__ __align__(8) uint64_t mbar_w;
     __shared__ uint32_t tmem_slot;
@@ -86,14 +87,24 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
     if (tid >= 64 && tid < 80) {
         grid::LevelMeta m;
         grid::make_level_meta(m, tid - 64, p.offs3, p.S3, p.H3, 3, 1, false);
-        make_fast_level(lv3[tid - 64], m);
+        if (!make_fast_level(lv3[tid - 64], m, (uint32_t)__ldg(p.poffs3 + (tid - 64)))) __trap();
     }
     if (tid >= 96 && tid < 112) {
         grid::LevelMeta m;
         grid::make_level_meta(m, tid - 96, p.offs2, p.S2, p.H2, 2, 1, false);
-        make_fast_level(lv2[tid - 96], m);
+        if (!make_fast_level(lv2[tid - 96], m, (uint32_t)__ldg(p.poffs2 + (tid - 96)))) __trap();
     }
-    if (tid >= 128 && tid < 128 + 192) (&s_bias[0][0])[tid - 128] = __ldg(p.consts + (tid - 128));
+    if (tid < 128) {
+        *reinterpret_cast<uint4*>(s_ones + umma::il_offset(tid, 0, 16)) = make_uint4(pack2(1.0f, 1.0f), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(s_ones + umma::il_offset(tid, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
+    } else if (tid < 128 + 192) {   // hoisted per-frame terms (audio code / eye / individual code), split so that hi + lo carries 22 bits
+        const uint32_t layer = (tid - 128) >> 6, n = (tid - 128) & 63;
+        const float b = __ldg(p.consts + (tid - 128));
+        const float hi = __half2float(__float2half_rn(b));
+        *reinterpret_cast<uint4*>(s_biasop[layer] + umma::il_offset(n, 0, 16)) = make_uint4(pack2(hi, b - hi), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(s_biasop[layer] + umma::il_offset(n, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -112,6 +123,7 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
     const uint32_t aA0 = umma::smem_u32(sA0), aEW = umma::smem_u32(sEW), aH0 = umma::smem_u32(sH0), aH1 = umma::smem_u32(sH1),
                    aCIN = umma::smem_u32(sCIN);
     const uint32_t aW = umma::smem_u32(s_blob);
+    const uint32_t aOnes = umma::smem_u32(s_ones), aB0 = umma::smem_u32(s_biasop[0]), aB1 = umma::smem_u32(s_biasop[1]), aB2 = umma::smem_u32(s_biasop[2]);
     const uint32_t* table3 = reinterpret_cast<const uint32_t*>(p.table3);
     const uint32_t* table2 = reinterpret_cast<const uint32_t*>(p.table2);
 
@@ -134,17 +146,17 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
         }
         RN_TICK(c_enc3)
         // ---- ambient L1: A0 [128x32] x WA1 -> 64, + hoisted audio term, ReLU -> H0
-        mma_stage(tmem_acc, aA0, 32, 0, aW + B_WA1, 32, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        mma_stage(tmem_acc, aA0, 32, 0, aW + B_WA1, 32, 0, 0, 0, aOnes, aB0, 64, mbar, phase, bar_id, t);
         RN_TICK(c_mma)
-        epilogue_to_operand<2>(tmem_row, 0, true, s_bias[0], sH0, t, 64, 0);
+        epilogue_to_operand<2>(tmem_row, 0, true, sH0, t, 64, 0);
         RN_TICK(c_epi)
         // ---- ambient L2: H0 -> H1
-        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WA2, 64, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WA2, 64, 0, 0, 0, 0, 0, 64, mbar, phase, bar_id, t);
         RN_TICK(c_mma)
-        epilogue_to_operand<2>(tmem_row, 0, true, nullptr, sH1, t, 64, 0);
+        epilogue_to_operand<2>(tmem_row, 0, true, sH1, t, 64, 0);
         RN_TICK(c_epi)
         // ---- ambient L3 (N padded to 16) -> tanh -> 2-D encode -> EW (first half of H0)
-        mma_stage(tmem_acc, aH1, 64, 0, aW + B_WA3, 64, 0, 0, 0, 16, mbar, phase, bar_id, t);
+        mma_stage(tmem_acc, aH1, 64, 0, aW + B_WA3, 64, 0, 0, 0, 0, 0, 16, mbar, phase, bar_id, t);
         RN_TICK(c_mma)
         {
             uint32_t v[16];
@@ -157,21 +169,21 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
         }
         RN_TICK(c_enc2)
         // ---- sigma L1: [enc_x | enc_w] as two K = 32 slabs, + hoisted eye term, ReLU -> H1
-        mma_stage(tmem_acc, aA0, 32, 0, aW + B_WS1A, 32, aEW, aW + B_WS1B, 32, 64, mbar, phase, bar_id, t);
+        mma_stage(tmem_acc, aA0, 32, 0, aW + B_WS1A, 32, aEW, aW + B_WS1B, 32, aOnes, aB1, 64, mbar, phase, bar_id, t);
         RN_TICK(c_mma)
-        epilogue_to_operand<2>(tmem_row, 0, true, s_bias[1], sH1, t, 64, 0);
+        epilogue_to_operand<2>(tmem_row, 0, true, sH1, t, 64, 0);
         RN_TICK(c_epi)
         // ---- sigma L2: H1 -> H0
-        mma_stage(tmem_acc, aH1, 64, 0, aW + B_WS2, 64, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        mma_stage(tmem_acc, aH1, 64, 0, aW + B_WS2, 64, 0, 0, 0, 0, 0, 64, mbar, phase, bar_id, t);
         RN_TICK(c_mma)
-        epilogue_to_operand<2>(tmem_row, 0, true, nullptr, sH0, t, 64, 0);
+        epilogue_to_operand<2>(tmem_row, 0, true, sH0, t, 64, 0);
         RN_TICK(c_epi)
         // ---- sigma L3: rows permuted on the host so columns 0..63 = geo_feat, column 64 = log-density
-        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WS3, 64, 0, 0, 0, 80, mbar, phase, bar_id, t);
+        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WS3, 64, 0, 0, 0, 0, 0, 80, mbar, phase, bar_id, t);
         RN_TICK(c_mma)
         float sigma;
         {
-            epilogue_to_operand<2>(tmem_row, 0, false, nullptr, sCIN, t, 80, 16);  // geo_feat -> CIN columns 16..79
+            epilogue_to_operand<2>(tmem_row, 0, false, sCIN, t, 80, 16);  // geo_feat -> CIN columns 16..79
             uint32_t v[16];
             umma::tmem_ld16(tmem_row + 64, v);
             umma::tmem_ld_wait();
@@ -187,12 +199,12 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl) {
         }
         RN_TICK(c_epi)
         // ---- colour L1: CIN [sh | geo] K = 80 -> 64, + hoisted individual-code term, ReLU -> H0
-        mma_stage(tmem_acc, aCIN, 80, 0, aW + B_WC1, 80, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        mma_stage(tmem_acc, aCIN, 80, 0, aW + B_WC1, 80, 0, 0, 0, aOnes, aB2, 64, mbar, phase, bar_id, t);
         RN_TICK(c_mma)
-        epilogue_to_operand<2>(tmem_row, 0, true, s_bias[2], sH0, t, 64, 0);
+        epilogue_to_operand<2>(tmem_row, 0, true, sH0, t, 64, 0);
         RN_TICK(c_epi)
         // ---- colour L2 (N padded to 16) -> sigmoid
-        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WC2, 64, 0, 0, 0, 16, mbar, phase, bar_id, t);
+        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WC2, 64, 0, 0, 0, 0, 0, 16, mbar, phase, bar_id, t);
         RN_TICK(c_mma)
         {
             uint32_t v[16];

@@ -9,7 +9,8 @@ namespace rn {
 
 struct MarchParams {
     float bound, dt_gamma, dt_min, dt_max;
-    float Hf, halfH, Hm1f, rH, H3f, Cm1f;
+    float Hf, halfH, Hm1f, rH, H3f, rbound;
+    int Cm1;
     const uint8_t* __restrict__ grid;
 };
 
@@ -27,7 +28,8 @@ __host__ __device__ inline MarchParams make_march_params(float bound, float dt_g
     p.Hm1f = (float)(H - 1);
     p.rH = 1.0f / (float)H;
     p.H3f = (float)(H * H * H);
-    p.Cm1f = (float)C - 1.0f;
+    p.rbound = 1.0f / bound;  // IEEE division, same value the device computes for 1 / mip_bound when mip_bound == bound
+    p.Cm1 = (int)C - 1;
     p.grid = grid;
     return p;
 }
@@ -48,10 +50,12 @@ __device__ __forceinline__ float step_size(const MarchParams& p, float t) {
     return clampf(__fmul_rn(t, p.dt_gamma), p.dt_min, p.dt_max);
 }
 
-__device__ __forceinline__ int cascade_of(float mx, float Cm1f) {
-    int e;
-    frexpf(mx, &e);  // [0,0.5) -> <=-1, [0.5,1) -> 0, [1,2) -> 1 ...        (raymarching.cu:42-54)
-    return (int)fminf(Cm1f, fmaxf(0.0f, (float)e));
+// clamp(frexp exponent of mx, 0, C-1): [0,0.5) -> <=-1 -> 0, [0.5,1) -> 0, [1,2) -> 1 ...        (raymarching.cu:42-54)
+// mx is finite and >= 0 here, so the exponent comes straight from the bit pattern (zero / denormals have a biased exponent
+// of 0 and land on level 0 exactly as frexpf's e <= 0 does); libdevice's frexpf costs ~30 instructions, twice per step.
+__device__ __forceinline__ int cascade_of(float mx, int Cm1) {
+    const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 126;
+    return min(Cm1, max(0, e));
 }
 
 // Probe the occupancy grid at parameter t.  Returns true when the cell is occupied (x,y,z,dt are then the sample);
@@ -63,12 +67,14 @@ __device__ __forceinline__ bool march_probe(const MarchParams& p, const Ray& r, 
     z = clampf(__fmaf_rn(r.dz, t, r.oz), -p.bound, p.bound);
     dt = step_size(p, t);
 
-    const int lvl_pos = cascade_of(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), p.Cm1f);
-    const int lvl_dt = cascade_of(__fmul_rn(__fmul_rn(dt, p.Hf), 0.5f), p.Cm1f);
+    const int lvl_pos = cascade_of(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), p.Cm1);
+    const int lvl_dt = cascade_of(__fmul_rn(__fmul_rn(dt, p.Hf), 0.5f), p.Cm1);
     const int level = max(lvl_pos, lvl_dt);
 
-    const float mip_bound = fminf(__int_as_float((127 + level) << 23), p.bound);
-    const float mip_rbound = 1 / mip_bound;
+    const float pow2 = __int_as_float((127 + level) << 23);
+    const float mip_bound = fminf(pow2, p.bound);
+    // 1 / mip_bound without the division sequence: exact for the power of two, precomputed (IEEE) for the scene bound
+    const float mip_rbound = pow2 <= p.bound ? __int_as_float((127 - level) << 23) : p.rbound;
 
     const int nx = (int)clampf(__fmul_rn(__fmaf_rn(x, mip_rbound, 1.0f), p.halfH), 0.0f, p.Hm1f);
     const int ny = (int)clampf(__fmul_rn(__fmaf_rn(y, mip_rbound, 1.0f), p.halfH), 0.0f, p.Hm1f);

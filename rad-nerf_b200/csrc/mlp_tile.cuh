@@ -1,6 +1,9 @@
 // mlp_tile.cuh -- building blocks shared by the fused-MLP kernels (head_eval.cu, torso_eval.cu):
 //   mma_stage            publish the group's operand rows, one thread issues the tcgen05 MMAs, everybody waits on the mbarrier
-//   epilogue_to_operand  TMEM row -> (+bias, ReLU) -> fp16 -> next layer's A operand row in shared memory
+//   epilogue_to_operand  TMEM row -> (ReLU) -> fp16 -> next layer's A operand row in shared memory.  There is no bias add:
+//                        the per-frame constant terms enter the accumulator through the MMA itself (a K = 16 slab of a
+//                        constant "ones" operand against [hi(b) | lo(b)] rows), which took ~15% of the kernel's
+//                        instructions out of the epilogues
 //   fast_encode<D>       one point through the 16 levels of a tiled, linearly interpolated 2-feature fp16 grid
 // mma_stage / epilogue are deliberately __noinline__: the kernel body has to stay inside the instruction cache (the first,
 // fully inlined version was 179 KB of SASS and spent 47% of its issue slots waiting for instructions).
@@ -23,8 +26,8 @@ __device__ __forceinline__ uint32_t relu2(uint32_t v) {
 // 32 accumulator columns [col0 + 32c, +32) per step, c < nch32: all TMEM loads are issued before the single wait.
 // relu(round(x)) == round(relu(x)), so ReLU runs on packed halves.
 template <int NCH32>
-static __device__ __noinline__ void epilogue_to_operand(uint32_t tmem_row, uint32_t col0, bool relu, const float* bias, uint8_t* dst,
-                                                        uint32_t row, uint32_t Kdst, uint32_t dcol0) {
+static __device__ __noinline__ void epilogue_to_operand(uint32_t tmem_row, uint32_t col0, bool relu, uint8_t* dst, uint32_t row,
+                                                        uint32_t Kdst, uint32_t dcol0) {
     uint32_t v[NCH32][32];
 #pragma unroll
     for (int c = 0; c < NCH32; ++c) umma::tmem_ld32(tmem_row + col0 + 32 * c, v[c]);
@@ -34,9 +37,7 @@ static __device__ __noinline__ void epilogue_to_operand(uint32_t tmem_row, uint3
         uint32_t h[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(v[c][2 * j]), b = __uint_as_float(v[c][2 * j + 1]);
-            if (bias) { a += bias[32 * c + 2 * j]; b += bias[32 * c + 2 * j + 1]; }
-            h[j] = pack2(a, b);
+            h[j] = pack2(__uint_as_float(v[c][2 * j]), __uint_as_float(v[c][2 * j + 1]));
             if (relu) h[j] = relu2(h[j]);
         }
 #pragma unroll
@@ -48,9 +49,10 @@ static __device__ __noinline__ void epilogue_to_operand(uint32_t tmem_row, uint3
 
 // publish this group's freshly written operand rows, let thread 0 issue D = A0*B0^T (+ A1*B1^T), wait for completion.
 // ka0 = first A column of the K0-slab inside an operand whose rows are Ka0 halves long.
+// (a2, b2): optional K = 16 constant slab (ones operand x bias rows), 0 = none.
 static __device__ __noinline__ void mma_stage(uint32_t tmem_acc, uint32_t a0, uint32_t Ka0, uint32_t ka0, uint32_t b0, uint32_t K0,
-                                              uint32_t a1, uint32_t b1, uint32_t K1, uint32_t N, uint64_t* mbar, uint32_t& phase,
-                                              uint32_t bar_id, uint32_t t) {
+                                              uint32_t a1, uint32_t b1, uint32_t K1, uint32_t a2, uint32_t b2, uint32_t N, uint64_t* mbar,
+                                              uint32_t& phase, uint32_t bar_id, uint32_t t) {
     umma::fence_async_smem();
     umma::fence_before_sync();
     umma::group_sync(bar_id, 128);
@@ -58,6 +60,7 @@ static __device__ __noinline__ void mma_stage(uint32_t tmem_acc, uint32_t a0, ui
         umma::fence_after_sync();
         umma::gemm_issue(tmem_acc, a0, b0, Ka0, K0, ka0, K0, N, false);
         if (K1) umma::gemm_issue(tmem_acc, a1, b1, K1, K1, 0, K1, N, true);
+        if (a2) umma::gemm_issue(tmem_acc, a2, b2, 16, 16, 0, 16, N, true);
         umma::commit(mbar);
     }
     umma::mbar_wait(mbar, phase);
@@ -66,33 +69,40 @@ static __device__ __noinline__ void mma_stage(uint32_t tmem_acc, uint32_t a0, ui
 }
 
 // ---- specialised grid level: tiled indexing, linear interpolation, align_corners = false, 2 fp16 features -------------
+// row(corner) = ((base + corner_delta) & mask) | or_off inside the packed fp16 copy of the table:
+//   dense level   (index < size, no wrap): base includes the level's first row, mask = ~0, or_off = 0
+//   capped level  (power-of-two size):     mask = size - 1, or_off = first row, which must be a multiple of size
+// -- one logic op per corner instead of an and plus a 64-bit add (6 -> 3-4 instructions per gathered corner).
 struct FastLevel {
-    float scale;      // exp2f(l*S)*H - 1
-    uint32_t s1, s2;  // strides of dimensions 1, 2 (0 once the running stride exceeded the level size: gridencoder.cu:72)
-    uint32_t mask;    // size - 1 for capped (power-of-two) levels, 0xffffffff for dense ones (index < size, no wrap)
-    uint32_t offset;  // first row of the level
+    float scale;        // exp2f(l*S)*H - 1
+    uint32_t s1, s2;    // strides of dimensions 1, 2 (0 once the running stride exceeded the level size: gridencoder.cu:72)
+    uint32_t mask, or_off, base_add;
 };
 
-// returns false if the level cannot be expressed (generic modulo) -- the host checks supported() first
-__device__ __forceinline__ bool make_fast_level(FastLevel& f, const grid::LevelMeta& m) {
+// false if the level cannot be expressed (generic modulo, hashed, misaligned packing) -- the host checks supported() first
+__device__ __forceinline__ bool make_fast_level(FastLevel& f, const grid::LevelMeta& m, uint32_t first_row) {
     f.scale = m.scale;
     f.s1 = m.stride[1];
     f.s2 = m.stride[2];
-    f.offset = m.offset;
     const uint32_t wrap = m.mode >> 1;
-    f.mask = wrap == 0 ? 0xffffffffu : m.size - 1;
-    return (m.mode & 1u) == 0 && wrap != 2;
+    if (wrap == 0) { f.mask = 0xffffffffu; f.or_off = 0; f.base_add = first_row; }
+    else { f.mask = m.size - 1; f.or_off = first_row; f.base_add = 0; }
+    return (m.mode & 1u) == 0 && wrap != 2 && (wrap == 0 || (first_row & (m.size - 1)) == 0);
 }
 
-// acc += round_half(w * g) with c10::Half's rounding (product in fp32, rounded to half, half add) on both features
-__device__ __forceinline__ void accum2(__half2& acc, float w, uint32_t g) {
+// acc += w * g on both features, accumulated in fp32 and rounded to fp16 once per level.  (grid_forward_kernel<half>
+// reproduces c10::Half's per-corner rounding bit for bit; here the 8 intermediate roundings are dropped -- two
+// instructions fewer per corner, and the result is closer to the exact interpolation than the reference's.)
+__device__ __forceinline__ void accum2(float2& acc, float w, uint32_t g) {
     const __half2 gv = *reinterpret_cast<const __half2*>(&g);
-    acc = __hadd2(acc, __floats2half2_rn(__fmul_rn(w, __low2float(gv)), __fmul_rn(w, __high2float(gv))));
+    acc.x = __fmaf_rn(w, __low2float(gv), acc.x);
+    acc.y = __fmaf_rn(w, __high2float(gv), acc.y);
 }
 
 // One point through all 16 levels; writes its 32 halfs as 4 x 16 B into row `row` of an interleaved [128 x Kdst] operand at
-// column dcol0.  Bit-identical to grid_forward_kernel<half, D, 2> (same operations in the same order); the index math is
-// specialised: base = p0 + p1*s1 + p2*s2, corner = (base + dx + dy*s1 + dz*s2) & mask.
+// column dcol0.  Same cell / weight arithmetic as grid_forward_kernel<half, D, 2> (identical cells and corner weights), fp32
+// accumulation (see accum2); the index math is specialised: base = p0 + p1*s1 + p2*s2,
+// corner = (base + dx + dy*s1 + dz*s2) & mask.
 template <int D>
 static __device__ __noinline__ void fast_encode(const float (&x)[D], const uint32_t* __restrict__ table32, const FastLevel* __restrict__ lv,
                                                 uint8_t* dst, uint32_t row, uint32_t Kdst, uint32_t dcol0) {
@@ -114,26 +124,26 @@ static __device__ __noinline__ void fast_encode(const float (&x)[D], const uint3
                 pg[d] = (uint32_t)fl;
                 fr[j][d] = pos - (float)pg[d];
             }
-            const uint32_t* __restrict__ tb = table32 + L.offset;
+            const uint32_t* __restrict__ tb = table32;
             if (oob) {
 #pragma unroll
                 for (int k = 0; k < (1 << D); ++k) g[j][k] = 0u;
             } else if constexpr (D == 3) {
-                const uint32_t b00 = pg[0] + pg[1] * L.s1 + pg[2] * L.s2, b10 = b00 + L.s1, b01 = b00 + L.s2, b11 = b10 + L.s2;
-                g[j][0] = __ldg(tb + (b00 & L.mask)); g[j][1] = __ldg(tb + ((b00 + 1) & L.mask));
-                g[j][2] = __ldg(tb + (b10 & L.mask)); g[j][3] = __ldg(tb + ((b10 + 1) & L.mask));
-                g[j][4] = __ldg(tb + (b01 & L.mask)); g[j][5] = __ldg(tb + ((b01 + 1) & L.mask));
-                g[j][6] = __ldg(tb + (b11 & L.mask)); g[j][7] = __ldg(tb + ((b11 + 1) & L.mask));
+                const uint32_t b00 = pg[0] + pg[1] * L.s1 + pg[2] * L.s2 + L.base_add, b10 = b00 + L.s1, b01 = b00 + L.s2, b11 = b10 + L.s2;
+                g[j][0] = __ldg(tb + ((b00 & L.mask) | L.or_off)); g[j][1] = __ldg(tb + (((b00 + 1) & L.mask) | L.or_off));
+                g[j][2] = __ldg(tb + ((b10 & L.mask) | L.or_off)); g[j][3] = __ldg(tb + (((b10 + 1) & L.mask) | L.or_off));
+                g[j][4] = __ldg(tb + ((b01 & L.mask) | L.or_off)); g[j][5] = __ldg(tb + (((b01 + 1) & L.mask) | L.or_off));
+                g[j][6] = __ldg(tb + ((b11 & L.mask) | L.or_off)); g[j][7] = __ldg(tb + (((b11 + 1) & L.mask) | L.or_off));
             } else {
-                const uint32_t b0 = pg[0] + pg[1] * L.s1, b1 = b0 + L.s1;
-                g[j][0] = __ldg(tb + (b0 & L.mask)); g[j][1] = __ldg(tb + ((b0 + 1) & L.mask));
-                g[j][2] = __ldg(tb + (b1 & L.mask)); g[j][3] = __ldg(tb + ((b1 + 1) & L.mask));
+                const uint32_t b0 = pg[0] + pg[1] * L.s1 + L.base_add, b1 = b0 + L.s1;
+                g[j][0] = __ldg(tb + ((b0 & L.mask) | L.or_off)); g[j][1] = __ldg(tb + (((b0 + 1) & L.mask) | L.or_off));
+                g[j][2] = __ldg(tb + ((b1 & L.mask) | L.or_off)); g[j][3] = __ldg(tb + (((b1 + 1) & L.mask) | L.or_off));
             }
         }
         uint32_t packed[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {  // ... then the interpolation, corner order = bit d of k selects dimension d
-            __half2 acc = __float2half2_rn(0.f);
+            float2 acc = make_float2(0.f, 0.f);
             if (!oob) {
                 const float x0 = 1.0f - fr[j][0], x1 = fr[j][0], y0 = 1.0f - fr[j][1], y1 = fr[j][1];
                 if constexpr (D == 3) {
@@ -148,7 +158,7 @@ static __device__ __noinline__ void fast_encode(const float (&x)[D], const uint3
                     accum2(acc, __fmul_rn(x0, y1), g[j][2]); accum2(acc, __fmul_rn(x1, y1), g[j][3]);
                 }
             }
-            packed[j] = *reinterpret_cast<const uint32_t*>(&acc);
+            packed[j] = pack2(acc.x, acc.y);
         }
         *reinterpret_cast<uint4*>(dst + umma::il_offset(row, dcol0 + 2 * l0, Kdst)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }

@@ -36,7 +36,6 @@ __global__ void __launch_bounds__(EVAL_GROUPS * 128, 1)
 torso_eval_kernel(TorsoEvalParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ FastLevel lv[16];
-    __shared__ float s_bias_d[64], s_bias_t[32];
     __shared__ __align__(8) uint64_t mbar_group[EVAL_GROUPS];
     __shared__ __align__(8) uint64_t mbar_w;
     __shared__ uint32_t tmem_slot;
@@ -62,14 +61,25 @@ torso_eval_kernel(TorsoEvalParams p) {
     if (tid >= 64 && tid < 80) {
         grid::LevelMeta m;
         grid::make_level_meta(m, tid - 64, p.offs, p.S, p.H, 2, 1, false);
-        make_fast_level(lv[tid - 64], m);
+        if (!make_fast_level(lv[tid - 64], m, (uint32_t)__ldg(p.poffs + (tid - 64)))) __trap();
     }
-    if (tid >= 128 && tid < 192) s_bias_d[tid - 128] = __ldg(p.consts + (tid - 128));
-    if (tid >= 192 && tid < 224) s_bias_t[tid - 192] = __ldg(p.consts + 64 + (tid - 192));
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     umma::mbar_wait(&mbar_w, 0);
+    // The hoisted per-frame terms (pose / individual code through deform-L1 and torso-L1) ride through the MMA: the frequency
+    // encoding has 6 padding columns (42..47), two of them carry 1.0 and the matching weight columns are patched here with
+    // the hi / lo halves of the term (22 bits).  No bias add in the epilogues.
+    if (tid < 96) {
+        const bool deform = tid < 64;
+        const uint32_t n = deform ? tid : tid - 64;
+        const float b = __ldg(p.consts + tid);
+        const float hi = __half2float(__float2half_rn(b));
+        uint8_t* w = s_blob + (deform ? T_WD1 + umma::il_offset(n, 42, 48) : T_WT1 + umma::il_offset(n, 74, 80));
+        *reinterpret_cast<uint32_t*>(w) = pack2(hi, b - hi);
+    }
+    umma::fence_async_smem();
+    __syncthreads();
 
     const uint32_t tmem_acc = tmem_slot + g * TMEM_COLS_PER_GROUP;
     const uint32_t tmem_row = tmem_acc + (((warp & 3u) * 32u) << 16);
@@ -103,7 +113,7 @@ torso_eval_kernel(TorsoEvalParams p) {
                 e[2 + 4 * f + 3] = __sinf(a1 + 1.5707963705062866f);
             }
 #pragma unroll
-            for (int j = 42; j < 48; ++j) e[j] = 0.f;
+            for (int j = 42; j < 48; ++j) e[j] = j < 44 ? 1.0f : 0.f;   // constant-one columns: carry the hoisted terms
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
                 const uint4 q = make_uint4(pack2(e[8 * c], e[8 * c + 1]), pack2(e[8 * c + 2], e[8 * c + 3]),
@@ -113,13 +123,13 @@ torso_eval_kernel(TorsoEvalParams p) {
             }
         }
                 // ---- deform L1 (K = 48) -> 64
-        mma_stage(tmem_acc, aF, 48, 0, aW + T_WD1, 48, 0, 0, 0, 64, mbar, phase, bar_id, t);
-        epilogue_to_operand<2>(tmem_row, 0, true, s_bias_d, sH0, t, 64, 0);
+        mma_stage(tmem_acc, aF, 48, 0, aW + T_WD1, 48, 0, 0, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        epilogue_to_operand<2>(tmem_row, 0, true, sH0, t, 64, 0);
                 // ---- deform L2
-        mma_stage(tmem_acc, aH0, 64, 0, aW + T_WD2, 64, 0, 0, 0, 64, mbar, phase, bar_id, t);
-        epilogue_to_operand<2>(tmem_row, 0, true, nullptr, sH1, t, 64, 0);
+        mma_stage(tmem_acc, aH0, 64, 0, aW + T_WD2, 64, 0, 0, 0, 0, 0, 64, mbar, phase, bar_id, t);
+        epilogue_to_operand<2>(tmem_row, 0, true, sH1, t, 64, 0);
                 // ---- deform L3 (N padded to 16) -> dx -> deformed coordinate -> 2-D grid encode -> TIN[0..31]
-        mma_stage(tmem_acc, aH1, 64, 0, aW + T_WD3, 64, 0, 0, 0, 16, mbar, phase, bar_id, t);
+        mma_stage(tmem_acc, aH1, 64, 0, aW + T_WD3, 64, 0, 0, 0, 0, 0, 16, mbar, phase, bar_id, t);
         {
             uint32_t v[16];
             umma::tmem_ld16(tmem_row, v);
@@ -131,13 +141,13 @@ torso_eval_kernel(TorsoEvalParams p) {
             fast_encode<2>(x, reinterpret_cast<const uint32_t*>(p.table), lv, sTIN, t, 80, 0);
         }
         // ---- torso L1 (K = 80) -> 32
-        mma_stage(tmem_acc, aTIN, 80, 0, aW + T_WT1, 80, 0, 0, 0, 32, mbar, phase, bar_id, t);
-        epilogue_to_operand<1>(tmem_row, 0, true, s_bias_t, sH0, t, 32, 0);
+        mma_stage(tmem_acc, aTIN, 80, 0, aW + T_WT1, 80, 0, 0, 0, 0, 0, 32, mbar, phase, bar_id, t);
+        epilogue_to_operand<1>(tmem_row, 0, true, sH0, t, 32, 0);
                 // ---- torso L2 (K = 32) -> 32
-        mma_stage(tmem_acc, aH0, 32, 0, aW + T_WT2, 32, 0, 0, 0, 32, mbar, phase, bar_id, t);
-        epilogue_to_operand<1>(tmem_row, 0, true, nullptr, sH1, t, 32, 0);
+        mma_stage(tmem_acc, aH0, 32, 0, aW + T_WT2, 32, 0, 0, 0, 0, 0, 32, mbar, phase, bar_id, t);
+        epilogue_to_operand<1>(tmem_row, 0, true, sH1, t, 32, 0);
                 // ---- torso L3 (N padded to 16) -> sigmoid -> (alpha, rgb)
-        mma_stage(tmem_acc, aH1, 32, 0, aW + T_WT3, 32, 0, 0, 0, 16, mbar, phase, bar_id, t);
+        mma_stage(tmem_acc, aH1, 32, 0, aW + T_WT3, 32, 0, 0, 0, 0, 0, 16, mbar, phase, bar_id, t);
         {
             uint32_t v[16];
             umma::tmem_ld16(tmem_row, v);

@@ -19,7 +19,7 @@ _vp, _u32, _f32, _u64 = C.c_void_p, C.c_uint32, C.c_float, C.c_uint64
 
 
 class GridTable(C.Structure):
-    _fields_ = [("table_f16", _vp), ("offsets", _vp), ("S", _f32), ("H", _u32)]
+    _fields_ = [("table_f16", _vp), ("offsets", _vp), ("S", _f32), ("H", _u32), ("packed_offsets", _vp)]
 
 
 class ConditioningDesc(C.Structure):
@@ -115,8 +115,8 @@ class FusedState:
         self.versions = versions
         self.graphs.clear()  # captured graphs hold pointers to the old blobs
         self.h16 = {}  # fp16 copies of the small-net parameters used by the conditioning kernel
-        self.table3 = model.encoder.embeddings.detach().to(torch.float16).contiguous()
-        self.table2 = model.encoder_ambient.embeddings.detach().to(torch.float16).contiguous()
+        self.table3 = pack_table(model.encoder)
+        self.table2 = pack_table(model.encoder_ambient)
         a, s, c = model.ambient_net.net, model.sigma_net.net, model.color_net.net
         w_s3 = s[2].weight
         w_s3 = torch.cat([w_s3[1:], w_s3[:1]], 0)  # geo_feat rows first, log-density row last (head_eval.cu)
@@ -126,7 +126,7 @@ class FusedState:
             il_pack(w_s3, 80, 64), il_pack(c[0].weight[:, :80], 64, 80), il_pack(c[1].weight, 16, 64)])
         assert self.head_blob.numel() * 2 == abi.lib().rn_head_blob_bytes()
         if model.torso:
-            self.table_t = model.torso_encoder.embeddings.detach().to(torch.float16).contiguous()
+            self.table_t = pack_table(model.torso_encoder)
             d, t = model.torso_deform_net.net, model.torso_net.net
             self.torso_blob = torch.cat([
                 il_pack(d[0].weight[:, :42], 64, 48), il_pack(d[1].weight, 64, 64), il_pack(d[2].weight, 16, 64),
@@ -148,8 +148,29 @@ class FusedState:
         return self.workspace[:65 * 32].view(torch.int32).view(65, 8)
 
 
-def _grid_table(enc, table):
-    return GridTable(table.data_ptr(), enc.offsets.data_ptr(), float(np.log2(enc.per_level_scale)), int(enc.base_resolution))
+def pack_table(enc):
+    """fp16 copy of a GridEncoder's table for the fused kernels: same rows, but every level whose size is a power of two
+    (the size-capped, wrapping levels) starts at a multiple of its size, so that the kernels can form a row index as
+    ((i & (size-1)) | first_row) -- see rn_grid_table.packed_offsets.  Returns (table [rows', 2] fp16, first rows [L] int32)."""
+    offs = enc.offsets.cpu().numpy().astype(np.int64)
+    emb = enc.embeddings.detach()
+    first, cur = [], 0
+    for l in range(len(offs) - 1):
+        size = int(offs[l + 1] - offs[l])
+        align = size if size & (size - 1) == 0 else 8
+        cur = (cur + align - 1) // align * align
+        first.append(cur)
+        cur += size
+    out = torch.zeros(cur, emb.shape[1], dtype=torch.float16, device=emb.device)
+    for l, f in enumerate(first):
+        out[f:f + int(offs[l + 1] - offs[l])] = emb[int(offs[l]):int(offs[l + 1])].to(torch.float16)
+    return out, torch.tensor(first, dtype=torch.int32, device=emb.device)
+
+
+def _grid_table(enc, packed):
+    table, first = packed
+    return GridTable(table.data_ptr(), enc.offsets.data_ptr(), float(np.log2(enc.per_level_scale)), int(enc.base_resolution),
+                     first.data_ptr())
 
 
 def conditioning_desc(model, st, auds, eye_t, pose6):
