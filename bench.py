@@ -267,6 +267,8 @@ def run_ours(args):
             fn(i)
         barrier()
         l0 = abi.launch_count()
+        fused = getattr(model, "_fused", None)
+        it0 = fused.loop_iterations() if fused is not None else 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as cs:
             e0.record()
@@ -276,6 +278,10 @@ def run_ours(args):
             barrier()
         ms = e0.elapsed_time(e1)
         launches = abi.launch_count() - l0
+        if fused is not None and fused.use_graph:
+            # a captured frame was counted as its `capture_unroll` plain iterations plus ONE pass of the WHILE node's body;
+            # replace that one pass by the body's real executions (lower bound when some frame needs < capture_unroll)
+            launches += 3 * (max(0, (fused.loop_iterations() - it0) - fused.capture_unroll * steps) - steps)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -215,6 +215,13 @@ typedef struct rn_frame_head_desc {
     void* consts_ready_event;    /* optional cudaEvent_t: rn_frame_conditioning ran on ANOTHER stream and recorded this event; the
                                     head waits for it only before its first network evaluation, so the audio nets overlap the
                                     ray setup and the first march.  NULL = same stream, no wait. */
+    uint32_t capture_unroll;     /* only used while `stream` is being captured into a CUDA graph: the first capture_unroll
+                                    iterations (0 = 1) of the march/evaluate/composite loop are captured as plain kernel nodes,
+                                    the rest is ONE conditional WHILE node whose condition the device-side loop controller sets.
+                                    An unrolled iteration that finds the loop finished costs ~1.3 us per kernel, a WHILE
+                                    iteration ~7 us more than an unrolled one: pass the iteration count typical of the scene.
+                                    Outside capture all max_steps iterations are launched. */
+    uint32_t reserved;
 } rn_frame_head_desc;
 
 typedef struct rn_frame_torso_desc {

@@ -34,7 +34,18 @@ extern "C" int rn_frame_conditioning(const rn_conditioning_desc* d, void* stream
     return launch_audio_frame(p, (cudaStream_t)stream);
 }
 
+#define RN_CUDA(call)                                                                    \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            rn::set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e_)); \
+            return (int)e_;                                                              \
+        }                                                                                \
+    } while (0)
+
 static uint32_t g_debug_iters = 0;
+static bool g_use_while_node = true;
+extern "C" void rn_debug_set_while_node(int on) { g_use_while_node = on != 0; }
 extern "C" void rn_debug_set_max_iters(uint32_t n) { g_debug_iters = n; }
 
 static int frame_head_impl(const rn_frame_head_desc* d, cudaStream_t st, cudaEvent_t* ev /* nullable: 3*max_steps+1 events */) {
@@ -62,18 +73,58 @@ static int frame_head_impl(const rn_frame_head_desc* d, cudaStream_t st, cudaEve
     hp.samples = w.samples; hp.evals = w.evals; hp.bound = d->bound; hp.inv2bound = 1.0f / (2.0f * d->bound);
     hp.prof = (unsigned long long*)g_head_prof;
     const uint32_t max_tiles = (d->N + EVAL_TILE - 1) / EVAL_TILE;  // n_alive * n_step <= N in every iteration
-    // n_step >= 1, so the reference's loop runs at most max_steps iterations
+    // n_step >= 1, so the reference's loop runs at most max_steps iterations.  All iterations are the same three launches:
+    // the kernels read the iteration index from the workspace and the loop controller (last CTA of composite) advances it.
+    auto iteration = [&](cudaStream_t s, uint32_t ev_it, bool first, unsigned long long cond) -> int {
+        int r;
+        if ((r = launch_march_compact(d->N, w, d->rays_o, d->rays_d, d->fars, mp, d->noises, s))) return r;
+        if (ev) cudaEventRecord(ev[3 * ev_it + 1], s);
+        if (first && d->consts_ready_event) cudaStreamWaitEvent(s, (cudaEvent_t)d->consts_ready_event, 0);
+        if ((r = launch_head_eval(hp, w.ctl, w.misc + 1, max_tiles, s))) return r;
+        if (ev) cudaEventRecord(ev[3 * ev_it + 2], s);
+        if ((r = launch_composite_compact(d->N, d->max_steps, d->T_thresh, w, d->weights_sum, d->depth, d->image, cond, s))) return r;
+        if (ev) cudaEventRecord(ev[3 * ev_it + 3], s);
+        return RN_OK;
+    };
     if (ev) cudaEventRecord(ev[0], st);
-    const uint32_t n_iters = g_debug_iters ? std::min(g_debug_iters, d->max_steps) : d->max_steps;
-    for (uint32_t it = 0; it < n_iters; ++it) {
-        if ((rc = launch_march_compact(it, d->N, w, d->rays_o, d->rays_d, d->fars, mp, d->noises, st))) return rc;
-        if (ev) cudaEventRecord(ev[3 * it + 1], st);
-        if (it == 0 && d->consts_ready_event) cudaStreamWaitEvent(st, (cudaEvent_t)d->consts_ready_event, 0);
-        if ((rc = launch_head_eval(hp, w.ctl + it, max_tiles, st))) return rc;
-        if (ev) cudaEventRecord(ev[3 * it + 2], st);
-        if ((rc = launch_composite_compact(it, d->N, d->max_steps, d->T_thresh, w, d->weights_sum, d->depth, d->image, st))) return rc;
-        if (ev) cudaEventRecord(ev[3 * it + 3], st);
+
+    // ---- stream capture: `capture_unroll` plain iterations, then ONE conditional WHILE node whose body is an iteration; the
+    //      loop controller sets the node's condition from the device.  Replaces max_steps unrolled iterations, most of which
+    //      would be launches that find `done` and exit (measured: 33 such launches, 44 us of a 530 us frame).
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaGraph_t graph = nullptr;
+    if (!ev && g_use_while_node && d->max_steps > 1 && cudaStreamGetCaptureInfo(st, &cs, nullptr, &graph, nullptr, nullptr) == cudaSuccess &&
+        cs == cudaStreamCaptureStatusActive && graph) {
+        cudaGraphConditionalHandle handle;
+        RN_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 0 /* no body run unless a controller asks for it */, cudaGraphCondAssignDefault));
+        const uint32_t unroll = std::min(std::max(d->capture_unroll, 1u), d->max_steps);
+        for (uint32_t it = 0; it < unroll; ++it)
+            if ((rc = iteration(st, it, it == 0, (unsigned long long)handle))) return rc;
+        if (unroll == d->max_steps) return RN_OK;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t n_deps = 0;
+        RN_CUDA(cudaStreamGetCaptureInfo(st, &cs, nullptr, &graph, &deps, &n_deps));
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        RN_CUDA(cudaGraphAddNode(&node, graph, deps, n_deps, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        static cudaStream_t body_stream = nullptr;   // capture-only helper stream
+        if (!body_stream) RN_CUDA(cudaStreamCreateWithFlags(&body_stream, cudaStreamNonBlocking));
+        RN_CUDA(cudaStreamBeginCaptureToGraph(body_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+        rc = iteration(body_stream, 0, false, (unsigned long long)handle);
+        cudaGraph_t out = nullptr;
+        RN_CUDA(cudaStreamEndCapture(body_stream, &out));
+        if (rc) return rc;
+        RN_CUDA(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
+        return RN_OK;
     }
+    const uint32_t n_iters = g_debug_iters ? std::min(g_debug_iters, d->max_steps) : d->max_steps;
+    for (uint32_t it = 0; it < n_iters; ++it)
+        if ((rc = iteration(st, it, it == 0, 0ull))) return rc;
     return RN_OK;
 }
 

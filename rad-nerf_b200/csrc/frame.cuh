@@ -45,7 +45,9 @@ struct MarchParams;
 // workspace layout (all offsets 256-byte aligned); see carve() in frame_ctl.cu
 struct FrameWorkspace {
     FrameCtl* ctl;        // [FRAME_MAX_ITERS + 1]
-    uint32_t* misc;       // [8]: 0 = n_torso
+    uint32_t* misc;       // [8] zeroed per frame: 0 = n_torso, 1 = index of the loop iteration in flight (kernels read it, the
+                          //     loop controller advances it: the same launches serve the unrolled sequence and the WHILE-node body)
+    uint32_t* stats;      // [8] never reset by the library: 0 = loop iterations executed since the workspace was zeroed
     int32_t* alive[2];    // [N] each
     float* rays_t;        // [N]
     uint32_t* ray_cnt;    // [N]    samples the alive slot's ray got this iteration
@@ -104,16 +106,17 @@ struct AudioParams {
 
 int launch_frame_init(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near, uint32_t max_steps,
                       float* nears, float* fars, const FrameWorkspace& w, float* weights_sum, float* depth, float* image, cudaStream_t st);
-int launch_march_compact(uint32_t it, uint32_t N, const FrameWorkspace& w, const float* rays_o, const float* rays_d, const float* fars,
+int launch_march_compact(uint32_t N, const FrameWorkspace& w, const float* rays_o, const float* rays_d, const float* fars,
                          const MarchParams& p, const float* noises, cudaStream_t st);
-int launch_composite_compact(uint32_t it, uint32_t N, uint32_t max_steps, float T_thresh, const FrameWorkspace& w, float* weights_sum,
-                             float* depth, float* image, cudaStream_t st);
+// cond_handle: cudaGraphConditionalHandle of the WHILE node that repeats the iteration (0 = none); the loop controller sets it
+int launch_composite_compact(uint32_t N, uint32_t max_steps, float T_thresh, const FrameWorkspace& w, float* weights_sum,
+                             float* depth, float* image, unsigned long long cond_handle, cudaStream_t st);
 int launch_torso_mask(const float* bg_coords, const float* grid, uint32_t G, float thresh, uint32_t N, const FrameWorkspace& w, cudaStream_t st);
 int launch_torso_scatter(uint32_t N, const FrameWorkspace& w, float* torso_alpha, float* torso_color, cudaStream_t st);
 int launch_finalize(uint32_t N, const float* weights_sum, float* depth, float* image, const float* nears, const float* fars,
                     const float* bg_color, float bg_scalar, const float* torso_alpha, const float* torso_color, float* torso_bg_out,
                     cudaStream_t st);
-int launch_head_eval(const HeadEvalParams& p, const FrameCtl* ctl, uint32_t max_tiles, cudaStream_t st);
+int launch_head_eval(const HeadEvalParams& p, const FrameCtl* ctl_base, const uint32_t* iter, uint32_t max_tiles, cudaStream_t st);
 int launch_torso_eval(const TorsoEvalParams& p, uint32_t max_tiles, cudaStream_t st);
 int launch_audio_frame(const AudioParams& p, cudaStream_t st);
 

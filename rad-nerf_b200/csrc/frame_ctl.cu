@@ -30,6 +30,7 @@ size_t carve(FrameWorkspace& w, uint8_t* base, uint32_t N) {
     w.evals = (float4*)take(16ull * (N + EVAL_TILE));
     w.torso_pix = (int32_t*)take(4ull * N);
     w.torso_out = (float4*)take(16ull * (N + EVAL_TILE));
+    w.stats = (uint32_t*)take(32);
     return off;
 }
 
@@ -113,8 +114,8 @@ frame_init_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
 // ---------------------------------------------------------------------------------------------------------------
 // march_compact: one thread per alive ray, <= 8 samples staged in shared memory, compacted write.
 __global__ void __launch_bounds__(CTL_THREADS)
-march_compact_kernel(const FrameCtl* ctl_in, FrameCtl* ctl_rw, const int32_t* __restrict__ alive,
-                     const float* __restrict__ rays_t, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+march_compact_kernel(FrameCtl* ctl_base, const uint32_t* __restrict__ iter, const int32_t* __restrict__ alive0,
+                     const int32_t* __restrict__ alive1, const float* __restrict__ rays_t, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                      const float* __restrict__ fars, MarchParams p, const float* __restrict__ noises,
                      uint32_t* __restrict__ ray_cnt, uint32_t* __restrict__ sample_idx, uint32_t N, float4* __restrict__ samples,
                      float2* __restrict__ deltas) {
@@ -123,10 +124,15 @@ march_compact_kernel(const FrameCtl* ctl_in, FrameCtl* ctl_rw, const int32_t* __
     __shared__ unsigned long long s_wsum[CTL_THREADS / 32];
     __shared__ uint32_t s_base;
 
+    const uint32_t it = *iter;
+    const FrameCtl* ctl_in = ctl_base + it;
+    FrameCtl* ctl_rw = ctl_base + it;
     if (ctl_in->done) return;
     const uint32_t n_alive = ctl_in->n_alive, n_step = ctl_in->n_step;
     if (blockIdx.x * CTL_THREADS >= n_alive) return;
     const uint32_t j = blockIdx.x * CTL_THREADS + threadIdx.x;
+    const int32_t* __restrict__ alive = (it & 1u) ? alive1 : alive0;
+    if (it != 0) noises = nullptr;   // the per-ray start offset is applied once, by the first march of the frame
 
     uint32_t cnt = 0;
     int32_t ray = 0;
@@ -197,8 +203,8 @@ march_compact_kernel(const FrameCtl* ctl_in, FrameCtl* ctl_rw, const int32_t* __
 // composite_compact: kernel_composite_rays semantics (raymarching.cu:942-1029) on the compacted sample list, then
 // survivor compaction; the last CTA plays the host loop (renderer.py:241-262) and publishes ctl[it + 1].
 __global__ void __launch_bounds__(CTL_THREADS)
-composite_compact_kernel(const FrameCtl* ctl_in, FrameCtl* ctl_rw, FrameCtl* ctl_next,
-                         const int32_t* __restrict__ alive_in, int32_t* __restrict__ alive_out, float* __restrict__ rays_t,
+composite_compact_kernel(FrameCtl* ctl_base, uint32_t* __restrict__ iter, uint32_t* __restrict__ stats, unsigned long long cond_handle,
+                         int32_t* __restrict__ alive0, int32_t* __restrict__ alive1, float* __restrict__ rays_t,
                          const uint32_t* __restrict__ ray_cnt, const uint32_t* __restrict__ sample_idx, const float2* __restrict__ deltas,
                          const float4* __restrict__ evals,
                          float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image, float T_thresh,
@@ -206,10 +212,16 @@ composite_compact_kernel(const FrameCtl* ctl_in, FrameCtl* ctl_rw, FrameCtl* ctl
     __shared__ uint32_t warp_sums[CTL_THREADS / 32];
     __shared__ uint32_t s_base;
 
+    const uint32_t it = *iter;
+    const FrameCtl* ctl_in = ctl_base + it;
+    FrameCtl* ctl_rw = ctl_base + it;
+    FrameCtl* ctl_next = ctl_base + it + 1;
     if (ctl_in->done) return;
     const uint32_t n_alive = ctl_in->n_alive, n_step = ctl_in->n_step;
     if (blockIdx.x * CTL_THREADS >= n_alive) return;
     const uint32_t j = blockIdx.x * CTL_THREADS + threadIdx.x;
+    const int32_t* __restrict__ alive_in = (it & 1u) ? alive1 : alive0;
+    int32_t* __restrict__ alive_out = (it & 1u) ? alive0 : alive1;
 
     uint32_t survive = 0;
     int32_t ray = 0;
@@ -267,6 +279,12 @@ composite_compact_kernel(const FrameCtl* ctl_in, FrameCtl* ctl_rw, FrameCtl* ctl
             c.n_samples = 0; c.next_alive = 0; c.blocks_done = 0;
             c.total_samples = ctl_in->total_samples + atomicAdd(&ctl_rw->n_samples, 0u);
             *ctl_next = c;
+            __threadfence();   // a CTA of this launch that starts late may read the advanced index: it must then see ctl_next
+                               // (n_alive never grows, so it still takes the early exit)
+            // every CTA of this launch has read *iter (the ticket is taken after that read), the next launch starts after this one
+            *iter = it + 1;
+            stats[0] += 1;
+            if (cond_handle) cudaGraphSetConditional(cond_handle, c.done ? 0u : 1u);   // WHILE node: run the body again?
         }
     }
 }
@@ -353,19 +371,19 @@ int launch_frame_init(const float* rays_o, const float* rays_d, const float* aab
     return finish_launch("frame_init");
 }
 
-int launch_march_compact(uint32_t it, uint32_t N, const FrameWorkspace& w, const float* rays_o, const float* rays_d,
-                         const float* fars, const MarchParams& p, const float* noises, cudaStream_t st) {
-    march_compact_kernel<<<div_up(N, (uint32_t)CTL_THREADS), CTL_THREADS, 0, st>>>(w.ctl + it, w.ctl + it, w.alive[it & 1], w.rays_t,
-                                                                                 rays_o, rays_d, fars, p, it == 0 ? noises : nullptr,
-                                                                                 w.ray_cnt, w.sample_idx, N, w.samples, w.deltas);
+int launch_march_compact(uint32_t N, const FrameWorkspace& w, const float* rays_o, const float* rays_d, const float* fars,
+                         const MarchParams& p, const float* noises, cudaStream_t st) {
+    march_compact_kernel<<<div_up(N, (uint32_t)CTL_THREADS), CTL_THREADS, 0, st>>>(w.ctl, w.misc + 1, w.alive[0], w.alive[1], w.rays_t,
+                                                                                 rays_o, rays_d, fars, p, noises, w.ray_cnt,
+                                                                                 w.sample_idx, N, w.samples, w.deltas);
     return finish_launch("march_compact");
 }
 
-int launch_composite_compact(uint32_t it, uint32_t N, uint32_t max_steps, float T_thresh, const FrameWorkspace& w,
-                             float* weights_sum, float* depth, float* image, cudaStream_t st) {
+int launch_composite_compact(uint32_t N, uint32_t max_steps, float T_thresh, const FrameWorkspace& w, float* weights_sum,
+                             float* depth, float* image, unsigned long long cond_handle, cudaStream_t st) {
     composite_compact_kernel<<<div_up(N, (uint32_t)CTL_THREADS), CTL_THREADS, 0, st>>>(
-        w.ctl + it, w.ctl + it, w.ctl + it + 1, w.alive[it & 1], w.alive[(it + 1) & 1], w.rays_t, w.ray_cnt, w.sample_idx, w.deltas, w.evals,
-        weights_sum, depth, image, T_thresh, N, max_steps);
+        w.ctl, w.misc + 1, w.stats, cond_handle, w.alive[0], w.alive[1], w.rays_t, w.ray_cnt, w.sample_idx, w.deltas, w.evals, weights_sum,
+        depth, image, T_thresh, N, max_steps);
     return finish_launch("composite_compact");
 }
 
