@@ -102,6 +102,7 @@ class FusedState:
         self.side = torch.cuda.Stream(device=dev)
         self.cond_event = torch.cuda.Event()
         self.use_graph = True
+        self.last_static = None   # input buffers of the graph used by the last frame
         self.capture_unroll = 1   # loop iterations captured as plain nodes; set from the warm-up frame before each capture
 
     def refresh_weights(self, model):
@@ -331,12 +332,18 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
                int(max_steps), float(T_thresh), float(model.mean_density_torso), model.density_bitfield.data_ptr())
         entry = st.graphs.get(key)
         if entry is None:
+            # small per-frame inputs live in ONE block [pose 4x4 | pose6 | eye | pad | auds] so that a streaming caller
+            # (radnerf_b200.stream.FrameStreamer) fills them with a single host->device copy; `pose` is only used by callers
+            # that generate the rays on the device
+            n_aud = 0 if auds_t is None else auds_t.numel()
+            flat = torch.zeros(24 + n_aud, device=dev)
             static = dict(rays_o=torch.empty_like(rays_o), rays_d=torch.empty_like(rays_d), bg_coords=torch.empty_like(bg_coords),
-                          auds=None if auds_t is None else torch.empty_like(auds_t), eye=None if eye_t is None else torch.empty_like(eye_t),
-                          pose6=None if pose6 is None else torch.empty_like(pose6), bg=None if bg_t is None else torch.empty_like(bg_t))
+                          flat=flat, pose=flat[:16].view(4, 4), auds=None if auds_t is None else flat[24:24 + n_aud].view(auds_t.shape),
+                          eye=None if eye_t is None else flat[22:23], pose6=None if pose6 is None else flat[16:22],
+                          bg=None if bg_t is None else torch.empty_like(bg_t))
             for k, v in (("rays_o", rays_o), ("rays_d", rays_d), ("bg_coords", bg_coords), ("auds", auds_t), ("eye", eye_t),
                          ("pose6", pose6), ("bg", bg_t)):
-                if v is not None:
+                if v is not None and static[k].data_ptr() != v.data_ptr():
                     static[k].copy_(v)
             # warm-up outside capture (lazy kernel attributes, module loading) on a scratch copy of the smoothing state
             saved = st.enc_a_state.clone()
@@ -355,12 +362,11 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
             st.enc_a_state.copy_(saved)  # capture does not execute, but keep the invariant explicit
             entry = st.graphs[key] = (graph, static, outs, abi.launch_count() - k0)
         graph, static, outs, n_kernels = entry
-        static["rays_o"].copy_(rays_o)
-        static["rays_d"].copy_(rays_d)
-        if static["bg_coords"].data_ptr() != bg_coords.data_ptr():
-            static["bg_coords"].copy_(bg_coords)
-        for k, v in (("auds", auds_t), ("eye", eye_t), ("pose6", pose6), ("bg", bg_t)):
-            if v is not None:
+        st.last_static = static
+        # a caller that already wrote into the graph's input buffers (FrameStreamer) passes those very tensors: no copies
+        for k, v in (("rays_o", rays_o), ("rays_d", rays_d), ("bg_coords", bg_coords), ("auds", auds_t), ("eye", eye_t),
+                     ("pose6", pose6), ("bg", bg_t)):
+            if v is not None and static[k].data_ptr() != v.data_ptr():
                 static[k].copy_(v)
         graph.replay()
         abi.lib().rn_note_graph_replay(n_kernels)

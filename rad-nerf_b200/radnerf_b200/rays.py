@@ -14,11 +14,15 @@ class RayGenerator:
         self.n = H * W if self.ids is None else self.ids.numel()
         self.device = device
 
-    def __call__(self, pose):
-        """pose [4,4] fp32 on the device -> rays_o [n,3], rays_d [n,3]"""
+    def __call__(self, pose, out=None):
+        """pose [4,4] fp32 on the device -> rays_o [n,3], rays_d [n,3] (written into `out = (rays_o, rays_d)` if given)"""
         pose = pose.contiguous()
-        ro = torch.empty(self.n, 3, device=self.device)
-        rd = torch.empty(self.n, 3, device=self.device)
+        if out is None:
+            ro = torch.empty(self.n, 3, device=self.device)
+            rd = torch.empty(self.n, 3, device=self.device)
+        else:
+            ro, rd = out
+            assert ro.is_contiguous() and rd.is_contiguous() and ro.numel() == 3 * self.n and rd.numel() == 3 * self.n
         abi.check(abi.lib().rn_get_rays(abi.ptr(pose), self.fx, self.fy, self.cx, self.cy, self.H, self.W, abi.ptr(self.ids),
                                         self.n, abi.ptr(ro), abi.ptr(rd), abi.cur_stream()))
         return ro, rd

@@ -1,0 +1,113 @@
+"""Host-facing frame pipeline of the fused renderer: the loop the reference runs in Trainer.test (nerf/utils.py:905-960) --
+per frame: pose / audio window / eye value arrive on the host, the frame is rendered, `preds.detach().cpu()` brings the
+image back -- restated as a depth-2 pipeline:
+
+    pinned host block --(ONE H2D copy)--> graph input block --> rays on device --> fused frame graph --> [NCCL all-gather]
+        --> device staging slot --(copy stream, D2H)--> pinned host image slot
+
+The device-to-host copy of frame i runs on a second stream while frame i+1 is rendered; staging and host slots alternate,
+and a slot is reused only after the copy that read it has completed (event-ordered, no host sync on the submit path).
+`collect()` is the only blocking call.  Per-frame latency is unchanged; throughput is no longer render + copy but
+max(render, copy, host issue)."""
+from collections import deque
+
+import numpy as np
+import torch
+
+from .rays import RayGenerator
+from .sharding import FrameSharder
+
+
+def pack_inputs(pose, auds, pose6=None, eye=None):
+    """one pinned fp32 block per frame, laid out like the frame graph's input block: [pose 4x4 | pose6 | eye | pad | auds]"""
+    auds = np.asarray(auds, dtype=np.float32)
+    buf = torch.zeros(24 + auds.size, dtype=torch.float32).pin_memory()
+    b = buf.numpy()
+    b[:16] = np.asarray(pose, dtype=np.float32).reshape(-1)
+    if pose6 is not None:
+        b[16:22] = np.asarray(pose6, dtype=np.float32).reshape(-1)
+    if eye is not None:
+        b[22] = float(np.asarray(eye, dtype=np.float32).reshape(-1)[0])
+    b[24:] = auds.reshape(-1)
+    return buf
+
+
+class FrameStreamer:
+    def __init__(self, model, H, W, intrinsics, bg_coords, auds_shape, use_eye=True, sharder=None, deliver=True, depth=2,
+                 **render_kw):
+        """bg_coords: [H*W, 2] on the device (this rank's rows if `sharder` splits the frame); auds_shape: e.g. (8, 44, 16);
+        deliver=False skips the device->host stage (ranks other than the one that consumes the frames)."""
+        self.model, self.kw, self.depth, self.deliver = model, render_kw, depth, deliver
+        self.dev = bg_coords.device
+        self.sharder = sharder if sharder is not None else FrameSharder(H, W, 1, 0, self.dev)
+        self.raygen = RayGenerator(H, W, intrinsics, self.dev, self.sharder)
+        self.bg = self.sharder.shard(bg_coords) if bg_coords.shape[0] == H * W and self.sharder.world > 1 else bg_coords
+        self.auds_shape, self.use_eye = tuple(auds_shape), use_eye
+        self.n_in = 24 + int(np.prod(auds_shape))
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.dev_stage = [torch.empty(H * W, 3, device=self.dev) for _ in range(depth)]
+        self.host_out = [torch.empty(H * W, 3).pin_memory() for _ in range(depth)]
+        self.staged = [torch.cuda.Event() for _ in range(depth)]
+        self.delivered = [torch.cuda.Event() for _ in range(depth)]
+        self.pending = deque()
+        self.static = None
+        self.n = 0
+        self.h2d_bytes = 4 * self.n_in
+        self.d2h_bytes = 12 * H * W
+
+    def _render(self, flat, ro, rd):
+        auds = flat[24:self.n_in].view(self.auds_shape)
+        eye = flat[22:23] if self.use_eye else None
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=self.model.opt.fp16):
+            return self.model.render(ro[None], rd[None], auds, self.bg[None], flat[16:22], eye=eye, index=0, bg_color=None,
+                                     perturb=False, path="fused", **self.kw)
+
+    def submit(self, packed):
+        """packed: pinned block from pack_inputs().  Enqueues copy-in, ray generation, the frame and copy-out; never blocks."""
+        assert packed.numel() == self.n_in and packed.is_pinned()
+        slot = self.n % self.depth
+        if self.static is None or self.model._fused.last_static is not self.static:
+            # first frame (or the graph was rebuilt): an ordinary call creates the graph and its input buffers
+            flat = packed.to(self.dev, non_blocking=True)
+            ro, rd = self.raygen(flat[:16].view(4, 4))
+            out = self._render(flat, ro, rd)
+            self.static = self.model._fused.last_static
+            self.bg = self.static["bg_coords"]   # same values, already in place: no per-frame copy of the coordinates
+        else:
+            st = self.static
+            st["flat"].copy_(packed, non_blocking=True)                      # ONE host->device copy per frame
+            self.raygen(st["pose"], out=(st["rays_o"], st["rays_d"]))        # rays straight into the graph's inputs
+            out = self._render(st["flat"], st["rays_o"], st["rays_d"])
+        img = self.sharder.gather(out["image"].view(-1, 3))
+        if self.deliver:
+            cur = torch.cuda.current_stream(self.dev)
+            cur.wait_event(self.delivered[slot])        # the copy that last read this staging slot has drained
+            self.dev_stage[slot].copy_(img)
+            self.staged[slot].record(cur)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.staged[slot])
+                self.host_out[slot].copy_(self.dev_stage[slot], non_blocking=True)
+                self.delivered[slot].record(self.copy_stream)
+        self.pending.append(slot)
+        self.n += 1
+
+    def in_flight(self):
+        return len(self.pending)
+
+    def collect(self):
+        """blocks until the oldest submitted frame is on the host; returns the pinned [H*W, 3] image (valid until `depth`
+        more frames have been submitted)"""
+        slot = self.pending.popleft()
+        if not self.deliver:
+            return None
+        self.delivered[slot].synchronize()
+        return self.host_out[slot]
+
+    def render_all(self, packed_frames):
+        """generator over host images, keeping `depth` frames in flight"""
+        for p in packed_frames:
+            if len(self.pending) == self.depth:
+                yield self.collect()
+            self.submit(p)
+        while self.pending:
+            yield self.collect()
