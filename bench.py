@@ -162,6 +162,10 @@ def cpu_frame_rate(hw, frames_to_time=1, threads=None):
     return 1.0 / t, threads, sum(s[2] for s in model.last_frame_stats)
 
 
+WORKLOAD = ("RAD-NeRF head+torso inference (BASELINE configs[2]), %dx%d, obama_eo shapes (wav2vec 44-d x16, att=2, exp_eye, "
+            "ind codes), random-init, synthetic head occupancy")
+
+
 def run_reference_arm(args):
     """--impl reference: the CPU port on all host threads, same metric/config; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -175,8 +179,8 @@ def run_reference_arm(args):
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "RAD-NeRF head+torso inference, %dx%d, obama_eo shapes, random-init" % (args.hw, args.hw),
-                       "frame": [args.hw, args.hw], "note": "reference extensions are CUDA-only; CPU arm = oracle port"},
+            "config": {"workload": WORKLOAD % (args.hw, args.hw), "frame": [args.hw, args.hw], "rays_per_frame": args.hw * args.hw,
+                       "note": "the reference's extensions are CUDA-only; its CPU implementation is the oracle port (oracle/), all host threads"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
@@ -321,8 +325,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic", "impl": "ours",
-            "config": {"workload": "RAD-NeRF head+torso inference (BASELINE configs[2]), %dx%d, obama_eo shapes (wav2vec 44-d x16, "
-                                   "att=2, exp_eye, ind codes), random-init, synthetic head occupancy" % (hw, hw),
+            "config": {"workload": WORKLOAD % (hw, hw),
                        "frame": [hw, hw], "rays_per_frame": hw * hw, "path": path,
                        "parallelism": "rays of each frame sharded by interleaved row tiles over %d GPU(s), all-gather of image tiles" % world,
                        "l2": "the %d frames cycled through carry %.0f MB of distinct ray inputs (> 126 MB L2); hash tables and "

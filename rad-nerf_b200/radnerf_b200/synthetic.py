@@ -130,3 +130,31 @@ def audio_window(bank, index, att=2):
     if pad_r:
         a = np.concatenate([a, np.zeros((pad_r,) + a.shape[1:], a.dtype)], 0)
     return a
+
+
+# --------------------------------------------------------------------------------------------- training batches
+def training_batch(H, W, n_rays, frame_index=0, seed=0, att=2, audio_dim=44):
+    """One synthetic training batch in the shape NeRFDataset.collate produces for training (nerf/provider.py:250-290,
+    SURVEY 8(d) "Training"): n_rays random pixels of an H x W frame seen from the orbit camera, target colours ~ U(0,1),
+    face mask = centre box, white background, audio window / eye / pose of frame `frame_index`.  numpy, host side."""
+    from .posemath import convert_poses
+    import torch
+    rng = np.random.default_rng(1000 * seed + frame_index)
+    pose = orbit_pose(yaw_deg=10.0 * np.sin(2 * np.pi * frame_index / 64), pitch_deg=2.0)
+    ro, rd = get_rays(pose, intrinsics_for(H, W), H, W)
+    pix = rng.choice(H * W, size=n_rays, replace=n_rays > H * W)
+    ys, xs = pix // W, pix % W
+    face = (np.abs(ys - H / 2) < H / 4) & (np.abs(xs - W / 2) < W / 4)
+    bank = audio_feature_bank(600, audio_dim, 16, seed=0)
+    return dict(rays_o=ro[pix][None], rays_d=rd[pix][None], bg_coords=get_bg_coords(H, W)[pix][None],
+                poses=convert_poses(torch.from_numpy(pose)[None]).numpy(), auds=audio_window(bank, 8 + frame_index, att),
+                eye=np.array([[0.25]], np.float32), index=[frame_index], rgb=rng.random((1, n_rays, 3), dtype=np.float32),
+                face_mask=face[None], bg_color=np.ones((n_rays, 3), np.float32))
+
+
+def batch_to(batch, device):
+    import torch
+    out = {}
+    for k, v in batch.items():
+        out[k] = torch.from_numpy(v).to(device) if isinstance(v, np.ndarray) else v
+    return out

@@ -1,0 +1,117 @@
+"""Training step of the ray path and its data-parallel gradient exchange ("Training step" row).
+
+`train_step` restates what Trainer.train_step + the optimiser part of Trainer.train_one_epoch do for one batch of rays
+(nerf/utils.py:718-808, 1153-1182): render in training mode through the op-by-op path (march_rays_train ->
+network -> composite_rays_train, all autograd Functions over the C ABI), per-ray MSE, the alpha-entropy term, the
+ambient regulariser outside the face mask, GradScaler backward/step.
+
+`GradSync` is the multi-GPU part: one process per GPU holds a replica and draws its own rays; gradients are summed with
+NCCL over NVLink and divided by the world size.  The three hash tables carry ~99% of the gradient bytes (12 MB of
+12.1 MB) and their gradients become final at well separated points of the backward pass, so each table is all-reduced
+from an autograd hook the moment its gradient is accumulated -- asynchronously, overlapping the remainder of backward --
+while every small parameter (MLPs, audio nets, codes) travels in ONE flat bucket once backward is done.  There is no
+collective in the forward pass."""
+import torch
+import torch.distributed as dist
+
+
+class GradSync:
+    def __init__(self, params, world=None, table_numel=1 << 18, group=None):
+        """params: iterable of parameters to keep in sync; tensors with >= table_numel elements get their own
+        asynchronous all-reduce, the rest share a flat bucket."""
+        self.group = group
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.params = [p for p in params if p.requires_grad]
+        self.big = [p for p in self.params if p.numel() >= table_numel]
+        self.small = [p for p in self.params if p.numel() < table_numel]
+        self.works = []
+        self.hooks = []
+        self.bytes_last = 0
+        if self.world > 1:
+            for p in self.big:
+                self.hooks.append(p.register_post_accumulate_grad_hook(self._on_table_grad))
+
+    def _on_table_grad(self, p):
+        # the gradient of this table is final for this step: start its all-reduce now, backward continues underneath
+        self.works.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.bytes_last += p.grad.numel() * p.grad.element_size()
+
+    def finish(self):
+        """call after backward(): exchanges the small-parameter bucket, waits for the table reductions, averages"""
+        if self.world <= 1:
+            return
+        grads = [p.grad for p in self.small if p.grad is not None]
+        if grads:
+            flat = torch.cat([g.reshape(-1).float() for g in grads])
+            self.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self.bytes_last += flat.numel() * 4
+        for w in self.works:
+            w.wait()
+        self.works = []
+        inv = 1.0 / self.world
+        if grads:
+            off = 0
+            for g in grads:
+                n = g.numel()
+                g.copy_(flat[off:off + n].view_as(g) * inv)
+                off += n
+        for p in self.big:
+            if p.grad is not None:
+                p.grad.mul_(inv)
+
+    def begin_step(self):
+        self.bytes_last = 0
+
+    def remove(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
+
+
+def head_loss(out, rgb, face_mask, lambda_amb):
+    """nerf/utils.py:749,783-806 for the head phase"""
+    loss = ((out["image"] - rgb) ** 2).mean(-1).mean()
+    a = out["weights_sum"].clamp(1e-5, 1 - 1e-5)
+    loss = loss + 1e-4 * (-a * torch.log2(a) - (1 - a) * torch.log2(1 - a)).mean()
+    if lambda_amb:
+        loss = loss + lambda_amb * (out["ambient"] * (~face_mask.reshape(-1))).mean()
+    return loss
+
+
+def torso_loss(out, rgb):
+    """nerf/utils.py:746-749,787-791 for the torso phase"""
+    loss = ((out["torso_color"].view_as(rgb) - rgb) ** 2).mean(-1).mean()
+    a = out["torso_alpha"].clamp(1e-5, 1 - 1e-5)
+    return loss + 1e-4 * (-a * torch.log2(a) - (1 - a) * torch.log2(1 - a)).mean()
+
+
+def train_step(model, batch, optimizer, scaler=None, sync=None, lambda_amb=0.1, phase=None):
+    """one optimisation step on `batch` = dict(rays_o [1,N,3], rays_d, auds, bg_coords [1,N,2], poses [1,6], eye, index,
+    rgb [1,N,3], face_mask [1,N] bool, bg_color [N,3] or scalar).  phase: "head" | "torso" (default: the model's
+    --torso flag, as the reference decides).  Returns the detached loss."""
+    model.train()
+    dev = batch["rays_o"].device
+    amp = bool(model.opt.fp16) and dev.type == "cuda"
+    if sync is not None:
+        sync.begin_step()
+    optimizer.zero_grad(set_to_none=False)
+    with torch.autocast(dev.type, dtype=torch.float16, enabled=amp):
+        out = model.render(batch["rays_o"], batch["rays_d"], batch["auds"], batch["bg_coords"], batch["poses"], eye=batch.get("eye"),
+                           index=batch.get("index", 0), bg_color=batch.get("bg_color"), perturb=True, force_all_rays=False,
+                           **model.opt.render_kwargs())
+        rgb = batch["rgb"]
+        if phase is None:
+            phase = "torso" if getattr(model, "torso", False) else "head"
+        loss = head_loss(out, rgb, batch["face_mask"], lambda_amb) if phase == "head" else torso_loss(out, rgb)
+    if scaler is not None and amp:
+        scaler.scale(loss).backward()
+        if sync is not None:
+            sync.finish()
+        scaler.step(optimizer)
+        scaler.update()
+    else:
+        loss.backward()
+        if sync is not None:
+            sync.finish()
+        optimizer.step()
+    return loss.detach()

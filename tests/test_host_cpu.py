@@ -43,6 +43,66 @@ def test_frame_sharding_two_ranks_gloo():
     assert r0 == set(range(0, 8)) | set(range(16, 24))
 
 
+def _toy_model():
+    torch.manual_seed(0)
+    m = torch.nn.Module()
+    m.table = torch.nn.Parameter(torch.randn(512, 2) * 0.1)   # >= table_numel below: own asynchronous all-reduce
+    m.lin = torch.nn.Linear(2, 3)                              # small parameters: flat bucket
+    m.unused = torch.nn.Parameter(torch.zeros(4))              # never receives a gradient
+    return m
+
+
+def _toy_loss(m, seed):
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, 512, (64,), generator=g)
+    target = torch.randn(64, 3, generator=g)
+    return ((m.lin(m.table[idx]) - target) ** 2).mean()
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.join(ROOT, "rad-nerf_b200"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from radnerf_b200.train import GradSync
+    m = _toy_model()
+    sync = GradSync(m.parameters(), table_numel=1024)
+    assert [p.numel() for p in sync.big] == [1024] and len(sync.small) == 3
+    got = []
+    for step in range(2):   # two steps: the hooks must keep firing and grads must not accumulate across steps
+        for p in m.parameters():
+            if p.grad is not None:
+                p.grad.zero_()
+        sync.begin_step()
+        _toy_loss(m, 100 * step + rank).backward()   # every rank draws its own batch
+        sync.finish()
+        got.append([None if p.grad is None else p.grad.clone() for p in m.parameters()])
+    out[rank] = (got, sync.bytes_last)
+    dist.destroy_process_group()
+
+
+def test_gradsync_two_ranks_gloo_equals_mean_of_local_grads():
+    """Data-parallel gradient exchange: after GradSync.finish() every rank must hold the MEAN over ranks of the per-rank
+    gradients (table via its own hook-driven all-reduce, small parameters via the flat bucket); unused parameters stay None."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() + 17) % 1000
+    mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
+    for step in range(2):
+        want = None
+        for r in range(world):
+            m = _toy_model()
+            _toy_loss(m, 100 * step + r).backward()
+            g = [None if p.grad is None else p.grad / world for p in m.parameters()]
+            want = g if want is None else [a if b is None else a + b for a, b in zip(want, g)]
+        for r in range(world):
+            for a, b in zip(out[r][0][step], want):
+                assert (a is None) == (b is None)
+                if a is not None:
+                    assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
+    assert out[0][1] == (1024 + 6 + 3) * 4   # bytes exchanged per step: the table + the flat bucket (lin.weight, lin.bias)
+
+
 def test_sharder_rejects_unbalanced_split():
     sys.path.insert(0, os.path.join(ROOT, "rad-nerf_b200"))
     from radnerf_b200.sharding import FrameSharder
