@@ -189,6 +189,8 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its version banner there)
     import torch
     import torch.distributed as dist
     from radnerf_b200 import abi, synthetic as syn
