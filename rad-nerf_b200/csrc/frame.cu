@@ -162,13 +162,13 @@ extern "C" int rn_frame_torso(const rn_frame_torso_desc* d, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     FrameWorkspace w;
     carve(w, (uint8_t*)d->workspace, d->N);
-    cudaMemsetAsync(w.misc, 0, 32, st);
+    cudaMemsetAsync(w.tmisc, 0, 32, st);
     int rc = launch_torso_mask(d->bg_coords, d->density_grid_torso, d->grid_size, d->thresh, d->N, w, st);
     if (rc) return rc;
     TorsoEvalParams tp;
     tp.table = (const __half*)d->grid2d.table_f16; tp.offs = d->grid2d.offsets; tp.poffs = d->grid2d.packed_offsets; tp.S = d->grid2d.S; tp.H = d->grid2d.H;
     tp.blob = (const uint8_t*)d->torso_blob; tp.consts = d->torso_consts; tp.bg_coords = d->bg_coords; tp.pix = w.torso_pix;
-    tp.n_pix = w.misc; tp.out = w.torso_out; tp.shrink = d->shrink;
+    tp.n_pix = w.tmisc; tp.out = w.torso_out; tp.shrink = d->shrink;
     if ((rc = launch_torso_eval(tp, (d->N + EVAL_TILE - 1) / EVAL_TILE, st))) return rc;
     return launch_torso_scatter(d->N, w, d->torso_alpha, d->torso_color, st);
 }

@@ -45,8 +45,9 @@ struct MarchParams;
 // workspace layout (all offsets 256-byte aligned); see carve() in frame_ctl.cu
 struct FrameWorkspace {
     FrameCtl* ctl;        // [FRAME_MAX_ITERS + 1]
-    uint32_t* misc;       // [8] zeroed per frame: 0 = n_torso, 1 = index of the loop iteration in flight (kernels read it, the
+    uint32_t* misc;       // [8] zeroed per frame: 1 = index of the loop iteration in flight (kernels read it, the
                           //     loop controller advances it: the same launches serve the unrolled sequence and the WHILE-node body)
+    uint32_t* tmisc;      // [8] zeroed by rn_frame_torso: 0 = n_torso (own block: the torso runs concurrently with the head loop)
     uint32_t* stats;      // [8] never reset by the library: 0 = loop iterations executed since the workspace was zeroed
     int32_t* alive[2];    // [N] each
     float* rays_t;        // [N]

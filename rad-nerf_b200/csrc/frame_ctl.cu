@@ -30,7 +30,8 @@ size_t carve(FrameWorkspace& w, uint8_t* base, uint32_t N) {
     w.evals = (float4*)take(16ull * (N + EVAL_TILE));
     w.torso_pix = (int32_t*)take(4ull * N);
     w.torso_out = (float4*)take(16ull * (N + EVAL_TILE));
-    w.stats = (uint32_t*)take(32);
+    w.tmisc = (uint32_t*)take(32);
+    w.stats = (uint32_t*)take(32);   // keep last: radnerf_b200/frame.py reads it at workspace_bytes - 256
     return off;
 }
 
@@ -389,14 +390,14 @@ int launch_composite_compact(uint32_t N, uint32_t max_steps, float T_thresh, con
 
 int launch_torso_mask(const float* bg_coords, const float* grid, uint32_t G, float thresh, uint32_t N, const FrameWorkspace& w,
                       cudaStream_t st) {
-    torso_mask_kernel<<<div_up(N, (uint32_t)CTL_THREADS), CTL_THREADS, 0, st>>>(bg_coords, grid, G, thresh, N, w.torso_pix, w.misc);
+    torso_mask_kernel<<<div_up(N, (uint32_t)CTL_THREADS), CTL_THREADS, 0, st>>>(bg_coords, grid, G, thresh, N, w.torso_pix, w.tmisc);
     return finish_launch("torso_mask");
 }
 
 int launch_torso_scatter(uint32_t N, const FrameWorkspace& w, float* torso_alpha, float* torso_color, cudaStream_t st) {
     cudaMemsetAsync(torso_alpha, 0, 4ull * N, st);
     cudaMemsetAsync(torso_color, 0, 12ull * N, st);
-    torso_scatter_kernel<<<wave_grid(N, 256, 4), 256, 0, st>>>(w.torso_pix, w.torso_out, w.misc, torso_alpha, torso_color);
+    torso_scatter_kernel<<<wave_grid(N, 256, 4), 256, 0, st>>>(w.torso_pix, w.torso_out, w.tmisc, torso_alpha, torso_color);
     return finish_launch("torso_scatter");
 }
 

@@ -246,39 +246,40 @@ def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_s
     dev = rays_o.device
     stream = abi.cur_stream()
 
-    # ---- per-frame conditioning on a forked stream: the audio nets overlap ray setup + the first march; the head waits for
-    #      the event only before its first network evaluation (works the same under CUDA-graph capture: fork/join edges)
+    # ---- forked stream: per-frame conditioning (audio nets), then the whole torso branch.  The audio nets overlap ray setup
+    #      + the first march (the head waits for `cond_event` only before its first network evaluation); the torso branch
+    #      only meets the head in the final blend, so it fills the SMs the march / composite phases of the head loop leave
+    #      idle.  Works the same under CUDA-graph capture (fork / join edges).
     cd = conditioning_desc(model, st, auds, eye_t, pose6)
     cur = torch.cuda.current_stream()
+    results = {}
+    torso_bg = torch.empty(N, 3, device=dev) if model.torso else None
     st.side.wait_stream(cur)
     with torch.cuda.stream(st.side):
         abi.check(L.rn_frame_conditioning(C.byref(cd), abi.cur_stream()))
         st.cond_event.record(st.side)
+        if model.torso:
+            td = FrameTorsoDesc()
+            td.N, td.grid_size = N, int(model.grid_size)
+            td.thresh, td.shrink = float(min(model.density_thresh_torso, model.mean_density_torso)), float(model.opt.torso_shrink)
+            td.bg_coords, td.density_grid_torso = bg_coords.data_ptr(), model.density_grid_torso.data_ptr()
+            td.workspace, td.workspace_bytes = st.workspace.data_ptr(), st.ws_bytes
+            td.grid2d = _grid_table(model.torso_encoder, st.table_t)
+            td.torso_blob, td.torso_consts = st.torso_blob.data_ptr(), st.torso_consts.data_ptr()
+            td.torso_alpha, td.torso_color = st.torso_alpha.data_ptr(), st.torso_color.data_ptr()
+            abi.check(L.rn_frame_torso(C.byref(td), abi.cur_stream()))
+            results['torso_alpha'] = st.torso_alpha
+            results['torso_color'] = torso_bg
 
     # ---- head
     hd, (weights_sum, depth, image, nears, fars) = head_desc(model, st, rays_o, rays_d, noises, dt_gamma, max_steps, T_thresh)
     hd.consts_ready_event = st.cond_event.cuda_event
     abi.check(L.rn_frame_head(C.byref(hd), stream))
 
-    results = {}
-    torso_bg = None
-    if model.torso:
-        td = FrameTorsoDesc()
-        td.N, td.grid_size = N, int(model.grid_size)
-        td.thresh, td.shrink = float(min(model.density_thresh_torso, model.mean_density_torso)), float(model.opt.torso_shrink)
-        td.bg_coords, td.density_grid_torso = bg_coords.data_ptr(), model.density_grid_torso.data_ptr()
-        td.workspace, td.workspace_bytes = st.workspace.data_ptr(), st.ws_bytes
-        td.grid2d = _grid_table(model.torso_encoder, st.table_t)
-        td.torso_blob, td.torso_consts = st.torso_blob.data_ptr(), st.torso_consts.data_ptr()
-        td.torso_alpha, td.torso_color = st.torso_alpha.data_ptr(), st.torso_color.data_ptr()
-        abi.check(L.rn_frame_torso(C.byref(td), stream))
-        torso_bg = torch.empty(N, 3, device=dev)
-        results['torso_alpha'] = st.torso_alpha
-        results['torso_color'] = torso_bg
+    cur.wait_stream(st.side)  # join: the final blend needs the torso
     abi.check(L.rn_frame_finalize(N, weights_sum.data_ptr(), depth.data_ptr(), image.data_ptr(), nears.data_ptr(), fars.data_ptr(),
                                   _p(bg_t), bg_scalar, _p(st.torso_alpha) if model.torso else None,
                                   _p(st.torso_color) if model.torso else None, _p(torso_bg), stream))
-    cur.wait_stream(st.side)  # join (the torso consts were produced on the side stream too; already ordered by the event)
     results['depth'] = depth
     results['image'] = image
     results['weights_sum'] = weights_sum
