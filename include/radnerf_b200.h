@@ -222,6 +222,10 @@ typedef struct rn_frame_head_desc {
                                     iteration ~7 us more than an unrolled one: pass the iteration count typical of the scene.
                                     Outside capture all max_steps iterations are launched. */
     uint32_t reserved;
+    const float* occ_aabb;       /* optional device [6] (xmin,ymin,zmin,xmax,ymax,zmax): a CONSERVATIVE bounding box of every occupied
+                                    cell of the bitfield, all cascades, inflated by at least one cell.  A ray whose [near, far]
+                                    segment provably misses it cannot emit a sample, so it is not marched (same outputs; about
+                                    70% of the rays of a talking-head frame).  NULL = march every ray. */
 } rn_frame_head_desc;
 
 typedef struct rn_frame_torso_desc {

@@ -62,7 +62,7 @@ static int frame_head_impl(const rn_frame_head_desc* d, cudaStream_t st, cudaEve
     RN_REQUIRE(((uintptr_t)d->head_blob & 15) == 0, "head_blob must be 16-byte aligned");
     FrameWorkspace w;
     carve(w, (uint8_t*)d->workspace, d->N);
-    int rc = launch_frame_init(d->rays_o, d->rays_d, d->aabb, d->N, d->min_near, d->max_steps, d->nears, d->fars, w, d->weights_sum,
+    int rc = launch_frame_init(d->rays_o, d->rays_d, d->aabb, d->occ_aabb, d->N, d->min_near, d->max_steps, d->nears, d->fars, w, d->weights_sum,
                                d->depth, d->image, st);
     if (rc) return rc;
     const MarchParams mp = make_march_params(d->bound, d->dt_gamma, d->max_steps, d->cascade, d->grid_size, d->bitfield);

@@ -62,12 +62,15 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& t
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-frame_init_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ aabb, uint32_t N,
-                  float min_near, uint32_t max_steps, float* __restrict__ nears, float* __restrict__ fars,
+frame_init_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ aabb,
+                  const float* __restrict__ occ_aabb, uint32_t N, float min_near, uint32_t max_steps, float* __restrict__ nears, float* __restrict__ fars,
                   float* __restrict__ rays_t, int32_t* __restrict__ alive0, float* __restrict__ weights_sum,
                   float* __restrict__ depth, float* __restrict__ image, FrameCtl* __restrict__ ctl, uint32_t* __restrict__ misc) {
-    __shared__ float box[6];
-    if (threadIdx.x < 6) box[threadIdx.x] = aabb[threadIdx.x];
+    __shared__ float box[6], occ[6];
+    if (threadIdx.x < 6) {
+        box[threadIdx.x] = aabb[threadIdx.x];
+        occ[threadIdx.x] = occ_aabb ? occ_aabb[threadIdx.x] : (threadIdx.x < 3 ? -FLT_MAX : FLT_MAX);
+    }
     __syncthreads();
     if (blockIdx.x == 0) {
         // ctl[] and misc[] were zeroed by the memset node that precedes this kernel
@@ -102,9 +105,22 @@ frame_init_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
             }
         }
         if (miss) near = far = FLT_MAX;
+        // Rays that cannot meet an occupied cell are not marched: start them at `far`.  Every position the marcher probes
+        // lies on the segment [near, far] of the ray, so a segment that misses the (inflated) bounding box of the occupied
+        // cells emits no sample -- exactly what marching it through empty space would find.  The test only prunes on a
+        // proven miss: any NaN (0 * inf on a slab plane) compares false and the ray is marched as usual.
+        float t0 = near, t1 = far;
+        {
+            const float ax = (occ[0] - ox) * rdx, bx = (occ[3] - ox) * rdx;
+            const float ay = (occ[1] - oy) * rdy, by = (occ[4] - oy) * rdy;
+            const float az = (occ[2] - oz) * rdz, bz = (occ[5] - oz) * rdz;
+            t0 = fmaxf(t0, fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz))));
+            t1 = fminf(t1, fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz))));
+        }
+        const bool prune = t0 > t1;
         nears[n] = near;
         fars[n] = far;
-        rays_t[n] = near;
+        rays_t[n] = prune ? far : near;
         alive0[n] = (int32_t)n;
         weights_sum[n] = 0.f;
         depth[n] = 0.f;
@@ -362,12 +378,12 @@ finalize_kernel(uint32_t N, const float* __restrict__ weights_sum, float* __rest
 }  // namespace
 
 // ---- launchers used by frame.cu --------------------------------------------------------------------------------
-int launch_frame_init(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near, uint32_t max_steps,
-                      float* nears, float* fars, const FrameWorkspace& w, float* weights_sum, float* depth, float* image,
-                      cudaStream_t st) {
+int launch_frame_init(const float* rays_o, const float* rays_d, const float* aabb, const float* occ_aabb, uint32_t N, float min_near,
+                      uint32_t max_steps, float* nears, float* fars, const FrameWorkspace& w, float* weights_sum, float* depth,
+                      float* image, cudaStream_t st) {
     cudaMemsetAsync(w.ctl, 0, sizeof(FrameCtl) * (FRAME_MAX_ITERS + 1), st);
     cudaMemsetAsync(w.misc, 0, 32, st);
-    frame_init_kernel<<<wave_grid(N, 256, 8), 256, 0, st>>>(rays_o, rays_d, aabb, N, min_near, max_steps, nears, fars, w.rays_t,
+    frame_init_kernel<<<wave_grid(N, 256, 8), 256, 0, st>>>(rays_o, rays_d, aabb, occ_aabb, N, min_near, max_steps, nears, fars, w.rays_t,
                                                             w.alive[0], weights_sum, depth, image, w.ctl, w.misc);
     return finish_launch("frame_init");
 }

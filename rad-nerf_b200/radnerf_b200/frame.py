@@ -38,7 +38,7 @@ class FrameHeadDesc(C.Structure):
                 ("weights_sum", _vp), ("depth", _vp), ("image", _vp), ("nears", _vp), ("fars", _vp),
                 ("workspace", _vp), ("workspace_bytes", _u64),
                 ("grid3d", GridTable), ("grid2d", GridTable), ("head_blob", _vp), ("head_consts", _vp), ("consts_ready_event", _vp),
-                ("capture_unroll", _u32), ("reserved", _u32)]
+                ("capture_unroll", _u32), ("reserved", _u32), ("occ_aabb", _vp)]
 
 
 class FrameTorsoDesc(C.Structure):
@@ -146,6 +146,33 @@ class FusedState:
             self.torso_color = torch.empty(N, 3, device=self.dev)
             self.graphs.clear()
 
+    def occupied_box(self, model):
+        """device [6]: bounding box of all occupied cells of the density bitfield (every cascade, world coordinates), inflated
+        by one cell per side -- rn_frame_head_desc.occ_aabb.  Recomputed into the SAME buffer when the bitfield changes."""
+        bf = model.density_bitfield
+        tag = (bf.data_ptr(), bf._version)
+        if getattr(self, "_occ_tag", None) != tag:
+            H, Cc, bound = int(model.grid_size), int(model.cascade), float(model.bound)
+            bits = ((bf.view(-1, 1) >> torch.arange(8, device=bf.device, dtype=torch.uint8)) & 1).view(Cc, H ** 3)
+            lo = torch.full((3,), float("inf"), device=bf.device)
+            hi = torch.full((3,), float("-inf"), device=bf.device)
+            for lvl in range(Cc):
+                idx = bits[lvl].nonzero().view(-1).to(torch.int32).contiguous()
+                if idx.numel() == 0:
+                    continue
+                coords = torch.empty(idx.numel(), 3, dtype=torch.int32, device=bf.device)
+                abi.check(abi.lib().rn_morton3D_invert(abi.ptr(idx), idx.numel(), abi.ptr(coords), abi.cur_stream()))
+                b = min(2.0 ** lvl, bound)
+                cell = 2.0 * b / H
+                lo = torch.minimum(lo, coords.min(0).values.float() * cell - b - cell)
+                hi = torch.maximum(hi, (coords.max(0).values.float() + 1) * cell - b + cell)
+            box = torch.cat([lo, hi])
+            if not hasattr(self, "_occ_box"):
+                self._occ_box = torch.empty(6, device=bf.device)
+            self._occ_box.copy_(box)   # an empty grid leaves (+inf, -inf): every ray is pruned, as it would find nothing
+            self._occ_tag = tag
+        return self._occ_box
+
     def loop_iterations(self):
         """march/evaluate/composite iterations executed since the workspace was created (device counter; forces a sync).
         A captured frame holds iteration 0 plus ONE conditional WHILE node, so the kernels a replay launches are
@@ -236,6 +263,7 @@ def head_desc(model, st, rays_o, rays_d, noises, dt_gamma, max_steps, T_thresh):
     hd.grid3d, hd.grid2d = _grid_table(model.encoder, st.table3), _grid_table(model.encoder_ambient, st.table2)
     hd.head_blob, hd.head_consts = st.head_blob.data_ptr(), st.head_consts.data_ptr()
     hd.capture_unroll = st.capture_unroll
+    hd.occ_aabb = st.occupied_box(model).data_ptr()
     return hd, (weights_sum, depth, image, nears, fars)
 
 
@@ -300,6 +328,7 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
     if st is None:
         st = model._fused = FusedState(model)
     st.refresh_weights(model)
+    st.occupied_box(model)   # refreshed here, outside any capture, when the bitfield changed
 
     prefix = rays_o.shape[:-1]
     rays_o = rays_o.contiguous().view(-1, 3).float()
@@ -438,6 +467,17 @@ def roofline_entries(model, f, bg_local, kw, hbm, tflops, reps=10):
             "launches_per_frame": n_launch / reps, "ms_per_frame": ev_ms / reps,
             "tensor_tflops": ev_samples * HEAD_FLOP_PER_SAMPLE / ev_ms / 1e9,
             "tensor_frac_of_peak": ev_samples * HEAD_FLOP_PER_SAMPLE / ev_ms / 1e9 / tflops}
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/, per sample x this launch size)
+    try:
+        import json, os
+        prof = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "profiles", "r01_head_eval_ncu_full.json")
+        per = json.load(open(prof))["per_sample"]
+        head["traffic"] = per["dram_bytes"] * head["units"]
+        head["traffic_note"] = ("dram__bytes_read+write per sample (%.1f B, profiles/%s) x samples per launch; far below the algorithmic "
+                                "812 B/sample because both hash tables (5.8 MB) stay L2-resident: the gathers are served by L1/L2"
+                                % (per["dram_bytes"], os.path.basename(prof)))
+    except Exception:
+        head["traffic"] = None
     march = {"kernel": "march_compact_kernel (occupancy DDA + sample compaction)", "bound": "hbm", "ms_per_frame": tot[0] / reps,
              "bytes_per_frame": 44.0 * N + 32.0 * samples / reps, "ms": tot[0] / n_launch}
     march.update(achieved=march["bytes_per_frame"] / march["ms_per_frame"] / 1e6, peak=hbm, unit="GB/s")

@@ -110,6 +110,6 @@ def measure(model, f, bg_local, kw, path):
     kernels += extra
     dom = extra[0] if (path == "fused" and extra) else g3
     roof = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
-            "traffic": dom.get("traffic"), "kernel": dom["kernel"], "peak_source": src + " (MEASURED_PEAKS.json)" if src == "measured" else src,
+            "traffic": dom.get("traffic"), "traffic_note": dom.get("traffic_note"), "kernel": dom["kernel"], "peak_source": src + " (MEASURED_PEAKS.json)" if src == "measured" else src,
             "algorithmic_per_launch": dom.get("bytes_per_unit", 0) * dom.get("units", 0), "launch_ms": dom["ms"]}
     return roof, kernels
