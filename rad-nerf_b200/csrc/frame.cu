@@ -80,7 +80,7 @@ static int frame_head_impl(const rn_frame_head_desc* d, cudaStream_t st, cudaEve
         if ((r = launch_march_compact(d->N, w, d->rays_o, d->rays_d, d->fars, mp, d->noises, s))) return r;
         if (ev) cudaEventRecord(ev[3 * ev_it + 1], s);
         if (first && d->consts_ready_event) cudaStreamWaitEvent(s, (cudaEvent_t)d->consts_ready_event, 0);
-        if ((r = launch_head_eval(hp, w.ctl, w.misc + 1, max_tiles, s))) return r;
+        if ((r = launch_head_eval(hp, w.cur, max_tiles, s))) return r;
         if (ev) cudaEventRecord(ev[3 * ev_it + 2], s);
         if ((r = launch_composite_compact(d->N, d->max_steps, d->T_thresh, w, d->weights_sum, d->depth, d->image, cond, s))) return r;
         if (ev) cudaEventRecord(ev[3 * ev_it + 3], s);

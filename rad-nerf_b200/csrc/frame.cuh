@@ -31,6 +31,16 @@ struct FrameCtl {            // one per iteration, written by the previous itera
 };
 static_assert(sizeof(FrameCtl) == 32, "FrameCtl layout");
 
+// State of the loop iteration in flight, at a FIXED address: the loop kernels read it directly (one load, no dependent
+// index -> entry chain), the loop controller (last CTA of composite_compact) files it into the per-iteration history
+// `ctl[it]` (diagnostics: frame_stats, rn_frame_head_timed) and replaces it with the next iteration's.
+struct FrameCur {
+    FrameCtl c;
+    uint32_t it;             // index of this iteration
+    uint32_t pad[7];
+};
+static_assert(sizeof(FrameCur) == 64, "FrameCur layout");
+
 constexpr int FRAME_MAX_ITERS = 64;  // >= max_steps supported by the fused path
 constexpr int EVAL_GROUPS = 3;       // 128-thread tile groups per CTA in the eval kernels
 constexpr int EVAL_TILE = 128;
@@ -45,8 +55,7 @@ struct MarchParams;
 // workspace layout (all offsets 256-byte aligned); see carve() in frame_ctl.cu
 struct FrameWorkspace {
     FrameCtl* ctl;        // [FRAME_MAX_ITERS + 1]
-    uint32_t* misc;       // [8] zeroed per frame: 1 = index of the loop iteration in flight (kernels read it, the
-                          //     loop controller advances it: the same launches serve the unrolled sequence and the WHILE-node body)
+    FrameCur* cur;        // the iteration in flight (zeroed per frame): the same launches serve the unrolled sequence and the WHILE-node body
     uint32_t* tmisc;      // [8] zeroed by rn_frame_torso: 0 = n_torso (own block: the torso runs concurrently with the head loop)
     uint32_t* stats;      // [8] never reset by the library: 0 = loop iterations executed since the workspace was zeroed
     int32_t* alive[2];    // [N] each
@@ -117,7 +126,7 @@ int launch_torso_scatter(uint32_t N, const FrameWorkspace& w, float* torso_alpha
 int launch_finalize(uint32_t N, const float* weights_sum, float* depth, float* image, const float* nears, const float* fars,
                     const float* bg_color, float bg_scalar, const float* torso_alpha, const float* torso_color, float* torso_bg_out,
                     cudaStream_t st);
-int launch_head_eval(const HeadEvalParams& p, const FrameCtl* ctl_base, const uint32_t* iter, uint32_t max_tiles, cudaStream_t st);
+int launch_head_eval(const HeadEvalParams& p, const FrameCur* cur, uint32_t max_tiles, cudaStream_t st);
 int launch_torso_eval(const TorsoEvalParams& p, uint32_t max_tiles, cudaStream_t st);
 int launch_audio_frame(const AudioParams& p, cudaStream_t st);
 

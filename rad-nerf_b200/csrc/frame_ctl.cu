@@ -19,7 +19,7 @@ size_t carve(FrameWorkspace& w, uint8_t* base, uint32_t N) {
     size_t off = 0;
     auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += align256(bytes); return p; };
     w.ctl = (FrameCtl*)take(sizeof(FrameCtl) * (FRAME_MAX_ITERS + 1));
-    w.misc = (uint32_t*)take(32);
+    w.cur = (FrameCur*)take(sizeof(FrameCur));
     w.alive[0] = (int32_t*)take(4ull * N);
     w.alive[1] = (int32_t*)take(4ull * N);
     w.rays_t = (float*)take(4ull * N);
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256)
 frame_init_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ aabb,
                   const float* __restrict__ occ_aabb, uint32_t N, float min_near, uint32_t max_steps, float* __restrict__ nears, float* __restrict__ fars,
                   float* __restrict__ rays_t, int32_t* __restrict__ alive0, float* __restrict__ weights_sum,
-                  float* __restrict__ depth, float* __restrict__ image, FrameCtl* __restrict__ ctl, uint32_t* __restrict__ misc) {
+                  float* __restrict__ depth, float* __restrict__ image, FrameCur* __restrict__ cur) {
     __shared__ float box[6], occ[6];
     if (threadIdx.x < 6) {
         box[threadIdx.x] = aabb[threadIdx.x];
@@ -73,12 +73,12 @@ frame_init_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
     }
     __syncthreads();
     if (blockIdx.x == 0) {
-        // ctl[] and misc[] were zeroed by the memset node that precedes this kernel
+        // the history ctl[] and *cur were zeroed by the memset nodes that precede this kernel
         if (threadIdx.x == 0) {
-            ctl[0].n_alive = N;
-            ctl[0].n_step = 1;   // clamp(N // N, 1, 8)
-            ctl[0].step = 0;
-            ctl[0].done = (max_steps == 0 || N == 0) ? 1u : 0u;
+            cur->c.n_alive = N;
+            cur->c.n_step = 1;   // clamp(N // N, 1, 8)
+            cur->c.step = 0;
+            cur->c.done = (max_steps == 0 || N == 0) ? 1u : 0u;
         }
     }
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
@@ -131,7 +131,7 @@ frame_init_kernel(const float* __restrict__ rays_o, const float* __restrict__ ra
 // ---------------------------------------------------------------------------------------------------------------
 // march_compact: one thread per alive ray, <= 8 samples staged in shared memory, compacted write.
 __global__ void __launch_bounds__(CTL_THREADS)
-march_compact_kernel(FrameCtl* ctl_base, const uint32_t* __restrict__ iter, const int32_t* __restrict__ alive0,
+march_compact_kernel(FrameCur* cur, const int32_t* __restrict__ alive0,
                      const int32_t* __restrict__ alive1, const float* __restrict__ rays_t, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                      const float* __restrict__ fars, MarchParams p, const float* __restrict__ noises,
                      uint32_t* __restrict__ ray_cnt, uint32_t* __restrict__ sample_idx, uint32_t N, float4* __restrict__ samples,
@@ -141,11 +141,10 @@ march_compact_kernel(FrameCtl* ctl_base, const uint32_t* __restrict__ iter, cons
     __shared__ unsigned long long s_wsum[CTL_THREADS / 32];
     __shared__ uint32_t s_base;
 
-    const uint32_t it = *iter;
-    const FrameCtl* ctl_in = ctl_base + it;
-    FrameCtl* ctl_rw = ctl_base + it;
-    if (ctl_in->done) return;
-    const uint32_t n_alive = ctl_in->n_alive, n_step = ctl_in->n_step;
+    const uint4 head = *reinterpret_cast<const uint4*>(&cur->c);   // n_alive, n_step, step, done
+    FrameCtl* ctl_rw = &cur->c;
+    if (head.w) return;
+    const uint32_t n_alive = head.x, n_step = head.y, it = cur->it;
     if (blockIdx.x * CTL_THREADS >= n_alive) return;
     const uint32_t j = blockIdx.x * CTL_THREADS + threadIdx.x;
     const int32_t* __restrict__ alive = (it & 1u) ? alive1 : alive0;
@@ -220,7 +219,7 @@ march_compact_kernel(FrameCtl* ctl_base, const uint32_t* __restrict__ iter, cons
 // composite_compact: kernel_composite_rays semantics (raymarching.cu:942-1029) on the compacted sample list, then
 // survivor compaction; the last CTA plays the host loop (renderer.py:241-262) and publishes ctl[it + 1].
 __global__ void __launch_bounds__(CTL_THREADS)
-composite_compact_kernel(FrameCtl* ctl_base, uint32_t* __restrict__ iter, uint32_t* __restrict__ stats, unsigned long long cond_handle,
+composite_compact_kernel(FrameCur* cur, FrameCtl* __restrict__ history, uint32_t* __restrict__ stats, unsigned long long cond_handle,
                          int32_t* __restrict__ alive0, int32_t* __restrict__ alive1, float* __restrict__ rays_t,
                          const uint32_t* __restrict__ ray_cnt, const uint32_t* __restrict__ sample_idx, const float2* __restrict__ deltas,
                          const float4* __restrict__ evals,
@@ -229,12 +228,10 @@ composite_compact_kernel(FrameCtl* ctl_base, uint32_t* __restrict__ iter, uint32
     __shared__ uint32_t warp_sums[CTL_THREADS / 32];
     __shared__ uint32_t s_base;
 
-    const uint32_t it = *iter;
-    const FrameCtl* ctl_in = ctl_base + it;
-    FrameCtl* ctl_rw = ctl_base + it;
-    FrameCtl* ctl_next = ctl_base + it + 1;
-    if (ctl_in->done) return;
-    const uint32_t n_alive = ctl_in->n_alive, n_step = ctl_in->n_step;
+    const uint4 head = *reinterpret_cast<const uint4*>(&cur->c);   // n_alive, n_step, step, done
+    FrameCtl* ctl_rw = &cur->c;
+    if (head.w) return;
+    const uint32_t n_alive = head.x, n_step = head.y, it = cur->it;
     if (blockIdx.x * CTL_THREADS >= n_alive) return;
     const uint32_t j = blockIdx.x * CTL_THREADS + threadIdx.x;
     const int32_t* __restrict__ alive_in = (it & 1u) ? alive1 : alive0;
@@ -287,19 +284,25 @@ composite_compact_kernel(FrameCtl* ctl_base, uint32_t* __restrict__ iter, uint32
         if (ticket == active - 1) {
             __threadfence();
             const uint32_t next = atomicAdd(&ctl_rw->next_alive, 0u);
-            const uint32_t step = ctl_in->step + n_step;  // `step += n_step`
+            const uint32_t n_samples = atomicAdd(&ctl_rw->n_samples, 0u);
+            const uint32_t step = head.z + n_step;  // `step += n_step`
+            const uint32_t total = ctl_rw->total_samples + n_samples;
+            FrameCtl h;   // history entry of the iteration that just finished
+            h.n_alive = n_alive; h.n_step = n_step; h.step = head.z; h.done = 0;
+            h.n_samples = n_samples; h.next_alive = next; h.blocks_done = active; h.total_samples = total;
+            history[it] = h;
             FrameCtl c;
             c.n_alive = next;
             c.n_step = next ? max(min(N / next, 8u), 1u) : 1u;  // `max(min(N // n_alive, 8), 1)`
             c.step = step;
             c.done = (step >= max_steps || next == 0) ? 1u : 0u;
             c.n_samples = 0; c.next_alive = 0; c.blocks_done = 0;
-            c.total_samples = ctl_in->total_samples + atomicAdd(&ctl_rw->n_samples, 0u);
-            *ctl_next = c;
-            __threadfence();   // a CTA of this launch that starts late may read the advanced index: it must then see ctl_next
-                               // (n_alive never grows, so it still takes the early exit)
-            // every CTA of this launch has read *iter (the ticket is taken after that read), the next launch starts after this one
-            *iter = it + 1;
+            c.total_samples = total;
+            // Every CTA that works on this iteration has taken its ticket, i.e. is past its reads of *cur.  A CTA of this
+            // launch that starts late may see any mix of old and new fields; n_alive never grows and `done` only rises, so
+            // it still takes its early exit.
+            cur->c = c;
+            cur->it = it + 1;
             stats[0] += 1;
             if (cond_handle) cudaGraphSetConditional(cond_handle, c.done ? 0u : 1u);   // WHILE node: run the body again?
         }
@@ -382,15 +385,15 @@ int launch_frame_init(const float* rays_o, const float* rays_d, const float* aab
                       uint32_t max_steps, float* nears, float* fars, const FrameWorkspace& w, float* weights_sum, float* depth,
                       float* image, cudaStream_t st) {
     cudaMemsetAsync(w.ctl, 0, sizeof(FrameCtl) * (FRAME_MAX_ITERS + 1), st);
-    cudaMemsetAsync(w.misc, 0, 32, st);
+    cudaMemsetAsync(w.cur, 0, sizeof(FrameCur), st);
     frame_init_kernel<<<wave_grid(N, 256, 8), 256, 0, st>>>(rays_o, rays_d, aabb, occ_aabb, N, min_near, max_steps, nears, fars, w.rays_t,
-                                                            w.alive[0], weights_sum, depth, image, w.ctl, w.misc);
+                                                            w.alive[0], weights_sum, depth, image, w.cur);
     return finish_launch("frame_init");
 }
 
 int launch_march_compact(uint32_t N, const FrameWorkspace& w, const float* rays_o, const float* rays_d, const float* fars,
                          const MarchParams& p, const float* noises, cudaStream_t st) {
-    march_compact_kernel<<<div_up(N, (uint32_t)CTL_THREADS), CTL_THREADS, 0, st>>>(w.ctl, w.misc + 1, w.alive[0], w.alive[1], w.rays_t,
+    march_compact_kernel<<<div_up(N, (uint32_t)CTL_THREADS), CTL_THREADS, 0, st>>>(w.cur, w.alive[0], w.alive[1], w.rays_t,
                                                                                  rays_o, rays_d, fars, p, noises, w.ray_cnt,
                                                                                  w.sample_idx, N, w.samples, w.deltas);
     return finish_launch("march_compact");
@@ -399,7 +402,7 @@ int launch_march_compact(uint32_t N, const FrameWorkspace& w, const float* rays_
 int launch_composite_compact(uint32_t N, uint32_t max_steps, float T_thresh, const FrameWorkspace& w, float* weights_sum,
                              float* depth, float* image, unsigned long long cond_handle, cudaStream_t st) {
     composite_compact_kernel<<<div_up(N, (uint32_t)CTL_THREADS), CTL_THREADS, 0, st>>>(
-        w.ctl, w.misc + 1, w.stats, cond_handle, w.alive[0], w.alive[1], w.rays_t, w.ray_cnt, w.sample_idx, w.deltas, w.evals, weights_sum,
+        w.cur, w.ctl, w.stats, cond_handle, w.alive[0], w.alive[1], w.rays_t, w.ray_cnt, w.sample_idx, w.deltas, w.evals, weights_sum,
         depth, image, T_thresh, N, max_steps);
     return finish_launch("composite_compact");
 }

@@ -55,7 +55,7 @@ constexpr uint32_t HEAD_SMEM = HEAD_BLOB_BYTES + HEAD_GROUPS * GROUP_BYTES;
 constexpr uint32_t TMEM_COLS_PER_GROUP = 128;
 
 __global__ void __launch_bounds__(HEAD_GROUPS * 128, 1)
-head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl_base, const uint32_t* iter) {
+head_eval_kernel(HeadEvalParams p, const FrameCur* cur) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ FastLevel lv3[16], lv2[16];
     __shared__ __align__(128) uint8_t s_ones[128 * 16 * 2];        // constant A operand [128 x 16]: columns 0, 1 = 1.0
@@ -64,7 +64,7 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl_base, const uint32_t* ite
     __shared__ __align__(8) uint64_t mbar_w;
     __shared__ uint32_t tmem_slot;
 
-    const FrameCtl* ctl = ctl_base + *iter;
+    const FrameCtl* ctl = &cur->c;
     if (ctl->done) return;
     const uint32_t n_samples = ctl->n_samples;
     const uint32_t n_tiles = (n_samples + EVAL_TILE - 1) / EVAL_TILE;
@@ -241,7 +241,7 @@ head_eval_kernel(HeadEvalParams p, const FrameCtl* ctl_base, const uint32_t* ite
 
 }  // namespace
 
-int launch_head_eval(const HeadEvalParams& p, const FrameCtl* ctl_base, const uint32_t* iter, uint32_t max_tiles, cudaStream_t st) {
+int launch_head_eval(const HeadEvalParams& p, const FrameCur* cur, uint32_t max_tiles, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(head_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM);
@@ -251,7 +251,7 @@ int launch_head_eval(const HeadEvalParams& p, const FrameCtl* ctl_base, const ui
     uint32_t grid = (max_tiles + HEAD_GROUPS - 1) / HEAD_GROUPS;
     if (grid > RN_NUM_SMS) grid = RN_NUM_SMS;
     if (grid == 0) grid = 1;
-    head_eval_kernel<<<grid, HEAD_GROUPS * 128, HEAD_SMEM, st>>>(p, ctl_base, iter);
+    head_eval_kernel<<<grid, HEAD_GROUPS * 128, HEAD_SMEM, st>>>(p, cur);
     return finish_launch("head_eval");
 }
 
