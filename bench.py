@@ -220,6 +220,10 @@ def run_ours(args):
 
     from radnerf_b200.sharding import FrameSharder
     sharder = FrameSharder(hw, hw, world, rank, dev)
+    gather_impl = "none" if world == 1 else ("peer stores over NVLink (symmetric memory) + barrier" if sharder.enable_peer_gather()
+                                              and os.environ.get("RADNERF_GATHER", "peer") == "peer" else "nccl all_gather + un-permute")
+    if gather_impl.startswith("nccl"):
+        sharder.peer = None
 
     # ---- device-resident inputs for `value`
     dev_frames = []
@@ -329,7 +333,7 @@ def run_ours(args):
             "data": "synthetic", "impl": "ours",
             "config": {"workload": WORKLOAD % (hw, hw),
                        "frame": [hw, hw], "rays_per_frame": hw * hw, "path": path,
-                       "parallelism": "rays of each frame sharded by interleaved row tiles over %d GPU(s), all-gather of image tiles" % world,
+                       "parallelism": "rays of each frame sharded by interleaved row tiles over %d GPU(s), all-gather of image tiles: %s" % (world, gather_impl),
                        "l2": "the %d frames cycled through carry %.0f MB of distinct ray inputs (> 126 MB L2); hash tables and "
                              "weights are re-used across frames by design" % (len(frames), len(frames) * hw * hw * 24 / 1e6)},
             "clocks": clocks, "gpu_launches": launches,

@@ -160,6 +160,15 @@ int rn_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, ui
 int rn_get_rays(const float* pose, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
                 const int32_t* pixel_ids, uint32_t n, float* rays_o, float* rays_d, void* stream);
 
+/* Multi-GPU frame assembly without a collective library (replaces ncclAllGather + un-permute for the ray-sharded frame,
+ * SURVEY 8(e) "Inference frame"): this rank's finished image rows are stored directly into every rank's full-frame buffer
+ * through peer mappings (NVLink / NVSwitch).  local [n_local,3] fp32; ids [n_local] pixel index of each row in the full frame,
+ * organised in runs of run_pixels consecutive pixels (run_pixels*3 % 4 == 0, run starts 16-byte aligned in the frame);
+ * peers: device array of `world` base addresses of the [H*W,3] fp32 frames (e.g. torch symmetric memory).  The caller
+ * orders the stores against the readers with a cross-rank barrier. */
+int rn_scatter_rows_to_peers(const float* local, const int32_t* ids, uint32_t n_local, uint32_t run_pixels,
+                             const uint64_t* peers, uint32_t world, void* stream);
+
 /* ------------------------------------------------------------------ fused inference frame ------------ */
 /* One call per stage of NeRFRenderer.run_cuda's inference branch (nerf/renderer.py:158-316) with no host round trip:
  * the reference's Python `while step < max_steps` loop, its per-iteration march_rays / NeRFNetwork.forward /

@@ -106,12 +106,16 @@ class FusedState:
         self.capture_unroll = 1   # loop iterations captured as plain nodes; set from the warm-up frame before each capture
 
     def refresh_weights(self, model):
-        params = [model.encoder.embeddings, model.encoder_ambient.embeddings] + list(model.ambient_net.parameters()) + \
-            list(model.sigma_net.parameters()) + list(model.color_net.parameters()) + list(model.audio_net.parameters())
-        if getattr(model, 'audio_att_net', None) is not None:
-            params += list(model.audio_att_net.parameters())
-        if model.torso:
-            params += [model.torso_encoder.embeddings] + list(model.torso_deform_net.parameters()) + list(model.torso_net.parameters())
+        params = getattr(self, "_params", None)
+        if params is None:   # the module tree is fixed: walk it once, then only compare (pointer, version) per frame
+            params = [model.encoder.embeddings, model.encoder_ambient.embeddings] + list(model.ambient_net.parameters()) + \
+                list(model.sigma_net.parameters()) + list(model.color_net.parameters()) + list(model.audio_net.parameters())
+            if getattr(model, 'audio_att_net', None) is not None:
+                params += list(model.audio_att_net.parameters())
+            if model.torso:
+                params += [model.torso_encoder.embeddings] + list(model.torso_deform_net.parameters()) + list(model.torso_net.parameters())
+            params += [p for p in (getattr(model, "individual_codes", None), getattr(model, "individual_codes_torso", None)) if p is not None]
+            self._params = params
         versions = tuple((p.data_ptr(), p._version) for p in params)
         if versions == self.versions:
             return

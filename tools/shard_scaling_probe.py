@@ -33,3 +33,8 @@ for world in (1, 2, 4, 8):
     e1.record(); torch.cuda.synchronize()
     print(json.dumps({"hw": hw, "world": world, "rays_per_rank": hw * hw // world, "ms_per_frame_rank0": e0.elapsed_time(e1) / 200,
                       "schedule": frame.frame_stats(model)}))
+    if os.environ.get("KERNELS"):
+        from radnerf_b200 import roofline
+        hbm, tfl, _ = roofline.peaks()
+        for e in frame.roofline_entries(model, devf[0], bg_l, kw, hbm, tfl):
+            print("   ", e["kernel"][:28], {k: (round(float(v), 4) if isinstance(v, (int, float)) or hasattr(v, "item") else v) for k, v in e.items() if k in ("ms", "ms_per_frame", "units", "launches_per_frame")})
