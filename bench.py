@@ -342,6 +342,27 @@ def run_ours(args):
                            else "model.render per frame, synchronous copy-out",
                     "ms_per_step": ms_e2e / args.steps}}
 
+    # ---- N > 1: the same job in FRAME-parallel mode (whole frames per GPU, no collective), reported next to the ray-sharded
+    #      headline: ray sharding cuts latency, but a 512x512 frame cannot scale past its ~0.29 ms dependency chain
+    if world > 1 and path == "fused":
+        from radnerf_b200.stream import FrameStreamer as _FS
+        full = _FS(model, hw, hw, intr, bg_t[0], frames[0]["auds"].shape, use_eye=True, deliver=True, depth=2, **kw)
+        model.enc_a = None
+
+        def render_fp(i):
+            if full.in_flight() == full.depth:
+                full.collect()
+            full.submit(packed[i % len(packed)])
+
+        def drain_fp():
+            while full.in_flight():
+                full.collect()
+        ms_fp, _, _ = timed(render_fp, args.steps, W, drain_fp)
+        line["frame_parallel"] = {"value": world * args.steps / (ms_fp / 1e3), "unit": UNIT, "ms_per_step_per_gpu": ms_fp / args.steps,
+                                  "what": "every GPU renders WHOLE frames of its own slice of the sequence end to end (host inputs in, fp32 "
+                                          "image back on the host; radnerf_b200.stream.render_sequence), no collective; weak scaling"}
+        model.enc_a = None
+
     if rank == 0:
         from radnerf_b200 import roofline
         line["roofline"], line["kernels"] = roofline.measure(model, dev_frames[0], bg_local, kw, path)

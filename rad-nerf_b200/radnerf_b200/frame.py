@@ -249,6 +249,32 @@ def conditioning_desc(model, st, auds, eye_t, pose6):
     return cd
 
 
+def advance_conditioning(model, auds, eye=None, poses=None):
+    """Run only the per-frame conditioning kernel (audio nets + lip-smoothing EMA) for a frame that is NOT rendered here:
+    a rank that renders a slice of a sequence calls this for the frames just before its slice so that its smoothing
+    state matches a run over the whole sequence (radnerf_b200.stream.render_sequence)."""
+    abi.lib()
+    st = getattr(model, "_fused", None)
+    if st is None:
+        st = model._fused = FusedState(model)
+    st.refresh_weights(model)
+    if model.smooth_lips:
+        prev = getattr(model, "enc_a", None)
+        if prev is None:
+            st.enc_a_state.zero_()
+        elif prev.data_ptr() != st.enc_a_state.data_ptr():
+            st.enc_a_state[:64].copy_(prev.reshape(-1))
+            st.enc_a_state[64] = 1.0
+    auds_t = auds.contiguous().float()
+    eye_t = None if eye is None else eye.reshape(-1).float().contiguous()
+    pose6 = poses.reshape(-1).float().contiguous() if model.torso else None
+    st._keep = (auds_t, eye_t, pose6)   # alive until the kernel has run
+    cd = conditioning_desc(model, st, auds_t, eye_t, pose6)
+    abi.check(abi.lib().rn_frame_conditioning(C.byref(cd), abi.cur_stream()))
+    if model.smooth_lips:
+        model.enc_a = st.enc_a_state[:64].view(1, 64)
+
+
 def head_desc(model, st, rays_o, rays_d, noises, dt_gamma, max_steps, T_thresh):
     N, dev = rays_o.shape[0], rays_o.device
     weights_sum = torch.empty(N, device=dev)

@@ -111,3 +111,36 @@ class FrameStreamer:
             self.submit(p)
         while self.pending:
             yield self.collect()
+
+
+# ------------------------------------------------------------------------------------------------ sequences on N GPUs
+SMOOTHING_MEMORY = 24   # frames after which the lip-smoothing EMA (lambda = 0.35) has forgotten its start: 0.35**24 ~ 1e-11
+
+
+def sequence_slice(n_frames, world, rank):
+    """contiguous slice [lo, hi) of a sequence owned by `rank` (the first n_frames % world ranks get one frame more)"""
+    base, extra = divmod(n_frames, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def render_sequence(model, packed_frames, H, W, intrinsics, bg_coords, auds_shape, world=1, rank=0, use_eye=True, **render_kw):
+    """Frame-parallel rendering of a known sequence (the offline `test.py` case): rank r renders the contiguous slice
+    sequence_slice(len(frames), world, r) of WHOLE frames with a replicated model -- no collective, no ray sharding, so the
+    throughput of N GPUs is N times one GPU's (a 512x512 frame split by rays stops scaling at ~0.29 ms of per-frame latency,
+    see DESIGN.md 6).  Frames are only coupled by the lip-smoothing EMA; a rank first runs the conditioning kernel (39 us)
+    over the SMOOTHING_MEMORY frames in front of its slice, which reproduces the state of a run over the whole sequence
+    to below fp32 resolution.  Yields (frame index, pinned host image)."""
+    from . import frame as _frame
+    lo, hi = sequence_slice(len(packed_frames), world, rank)
+    dev = bg_coords.device
+    n_in = 24 + int(np.prod(auds_shape))
+    model.enc_a = None
+    for p in packed_frames[max(0, lo - SMOOTHING_MEMORY):lo]:
+        flat = p.to(dev, non_blocking=True)
+        _frame.advance_conditioning(model, flat[24:n_in].view(tuple(auds_shape)), flat[22:23] if use_eye else None, flat[16:22])
+    streamer = FrameStreamer(model, H, W, intrinsics, bg_coords, auds_shape, use_eye=use_eye, **render_kw)
+    idx = lo
+    for img in streamer.render_all(packed_frames[lo:hi]):
+        yield idx, img
+        idx += 1

@@ -126,3 +126,31 @@ def test_frame_streamer_delivers_the_frames_model_render_produces():
     for a, b in zip(got, want):
         assert torch.equal(a, b)
     assert not torch.equal(got[0], got[1])  # the frames differ, so order and slot reuse are really exercised
+
+
+def test_frame_parallel_slices_reproduce_the_whole_sequence_run():
+    """render_sequence(world=2) must give, for each rank's slice, the frames a single run over the whole sequence gives --
+    including the lip-smoothing state that couples consecutive frames (primed over the frames in front of the slice)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from radnerf_b200.stream import pack_inputs, render_sequence, sequence_slice
+    hw, n = 64, 60
+    model = bench.make_model(DEV, seed=5)
+    assert model.smooth_lips
+    frames, intr, bg = bench.make_frames(hw, n)
+    bg_t = torch.from_numpy(bg).to(DEV)
+    kw = model.opt.render_kwargs()
+    packed = [pack_inputs(f["pose"], f["auds"], f["pose6"], f["eye"]) for f in frames]
+    whole = {i: img.clone() for i, img in render_sequence(model, packed, hw, hw, intr, bg_t, frames[0]["auds"].shape, **kw)}
+    assert sorted(whole) == list(range(n))
+    assert sequence_slice(n, 2, 0) == (0, 30) and sequence_slice(n, 2, 1) == (30, 60) and sequence_slice(7, 3, 0) == (0, 3)
+    for rank in (0, 1):
+        part = {i: img.clone() for i, img in render_sequence(model, packed, hw, hw, intr, bg_t, frames[0]["auds"].shape, world=2, rank=rank, **kw)}
+        lo, hi = sequence_slice(n, 2, rank)
+        assert sorted(part) == list(range(lo, hi))
+        for i in part:
+            assert (part[i] - whole[i]).abs().max().item() <= 1e-6, (rank, i)
+    # the smoothing state matters: without priming, the first frame of rank 1's slice would differ visibly
+    model.enc_a = None
+    assert not torch.equal(whole[29], whole[30])
