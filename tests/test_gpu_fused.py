@@ -154,3 +154,68 @@ def test_frame_parallel_slices_reproduce_the_whole_sequence_run():
     # the smoothing state matters: without priming, the first frame of rank 1's slice would differ visibly
     model.enc_a = None
     assert not torch.equal(whole[29], whole[30])
+
+
+def _custom_scene(hw, n_frames=2, seed=0, **opt_kw):
+    """like _scene but for an arbitrary reference configuration (BASELINE.json configs[1] and configs[4])"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from radnerf_b200.model import NeRFNetwork, Options
+    from radnerf_b200 import synthetic as syn
+    from radnerf_b200.posemath import convert_poses
+    torch.manual_seed(seed)
+    model = NeRFNetwork(Options(smooth_lips=True, fp16=True, exp_eye=True, **opt_kw))
+    grid = syn.head_density_grid(128, semi_axes=(0.34, 0.24, 0.37))
+    model.density_grid.copy_(torch.from_numpy(grid))
+    model.mean_density = float(np.clip(grid, 0, None).mean())
+    model.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, min(model.mean_density, model.density_thresh))))
+    if model.torso:
+        tg = syn.torso_density_grid(128)
+        model.density_grid_torso.copy_(torch.from_numpy(tg))
+        model.mean_density_torso = float(tg.mean())
+    model = model.eval().to(DEV)
+    g = torch.Generator(device="cpu").manual_seed(seed + 1)
+    encs = [model.encoder, model.encoder_ambient] + ([model.torso_encoder] if model.torso else [])
+    for enc in encs:
+        with torch.no_grad():
+            enc.embeddings.copy_((torch.rand(enc.embeddings.shape, generator=g) * 2 - 1).to(DEV))
+    bank = syn.audio_feature_bank(600, model.audio_in_dim, 16, seed=0)
+    intr = syn.intrinsics_for(hw, hw)
+    frames = []
+    for i in range(n_frames):
+        pose = syn.orbit_pose(yaw_deg=8.0 * i - 4.0, pitch_deg=2.0)
+        ro, rd = syn.get_rays(pose, intr, hw, hw)
+        frames.append(dict(ro=torch.from_numpy(ro).to(DEV)[None], rd=torch.from_numpy(rd).to(DEV)[None],
+                           auds=torch.from_numpy(syn.audio_window(bank, 8 + i, model.att)).to(DEV),
+                           pose6=convert_poses(torch.from_numpy(pose)[None]).to(DEV), eye=torch.tensor([[0.25]], device=DEV)))
+    return model, frames, torch.from_numpy(syn.get_bg_coords(hw, hw)).to(DEV)[None]
+
+
+@pytest.mark.parametrize("name,hw,opt_kw", [
+    ("configs[1]: head only, 450x450, wav2vec 44-d", 450, dict(torso=False)),
+    ("configs[4]: DeepSpeech 29-d with eye / individual codes, torso", 128, dict(torso=True, asr_model="deepspeech")),
+    ("32-d audio features (the reference's third branch)", 96, dict(torso=True, asr_model="hubert")),
+    ("configs[2] at full size: 512x512 head+torso", 512, dict(torso=True)),
+])
+def test_fused_frame_on_the_reference_configurations(name, hw, opt_kw):
+    """BASELINE.json's other configurations as parity cases: fused frame vs the op-by-op path, identical ray schedule,
+    image / depth / torso within 2e-3 (fp16 tables with O(1) entries)."""
+    from radnerf_b200 import frame
+    model, frames, bg = _custom_scene(hw, **opt_kw)
+    assert frame.supported(model), name
+    enc_ops = enc_fused = None
+    for i, f in enumerate(frames):
+        model.enc_a = enc_ops
+        ref = _render(model, f, bg, "ops")
+        enc_ops = model.enc_a.clone()
+        sched_ref = [(a, s) for a, s, _ in model.last_frame_stats]
+        model.enc_a = enc_fused
+        out = _render(model, f, bg, "fused")
+        torch.cuda.synchronize()
+        enc_fused = model.enc_a.clone()
+        assert [(a, s) for a, s, _ in frame.frame_stats(model)] == sched_ref, name
+        assert (enc_fused - enc_ops).abs().max().item() <= 2e-3 * max(1.0, enc_ops.abs().max().item())
+        assert (out["image"] - ref["image"]).abs().max().item() <= 2e-3, name
+        assert (out["depth"] - ref["depth"]).abs().max().item() <= 2e-3, name
+        if model.torso:
+            assert (out["torso_alpha"] - ref["torso_alpha"]).abs().max().item() <= 2e-3, name
