@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default=os.environ.get("RADNERF_PATH", "auto"), choices=["auto", "fused", "ops"])
     ap.add_argument("--hw", type=int, default=HW)
+    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU (fused path; 1 = strictly one frame at a time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     return ap.parse_args()
@@ -220,7 +221,7 @@ def run_ours(args):
 
     from radnerf_b200.sharding import FrameSharder
     sharder = FrameSharder(hw, hw, world, rank, dev)
-    gather_impl = "none" if world == 1 else ("peer stores over NVLink (symmetric memory) + barrier" if sharder.enable_peer_gather()
+    gather_impl = "none" if world == 1 else ("peer stores over NVLink (symmetric memory) + barrier" if sharder.enable_peer_gather(n_buffers=max(2, args.lanes))
                                               and os.environ.get("RADNERF_GATHER", "peer") == "peer" else "nccl all_gather + un-permute")
     if gather_impl.startswith("nccl"):
         sharder.peer = None
@@ -234,21 +235,42 @@ def run_ours(args):
                                eye=torch.from_numpy(f["eye"]).to(dev)))
     bg_local = sharder.shard(bg_t[0])[None]
 
-    def render_resident(i):
-        f = dev_frames[i % len(dev_frames)]
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=model.opt.fp16):
-            out = model.render(f["ro"], f["rd"], f["auds"], bg_local, f["pose6"], eye=f["eye"], index=0, bg_color=None,
-                               perturb=False, path=path, **kw)
-        return sharder.gather(out["image"][0])
+    lanes = max(1, args.lanes) if path == "fused" else 1
+    if path == "fused":
+        # `value`: the per-frame input blocks (pose, pose6, eye, audio window) are resident on the device; rays are generated
+        # on the device from the pose, `lanes` frames are in flight on separate streams (FramePipeline inside FrameStreamer;
+        # the lip-smoothing chain is kept by running the conditioning kernels in frame order on their own stream); no
+        # host<->device copies in the timed region.
+        from radnerf_b200.stream import FrameStreamer, pack_inputs
+        packed = [pack_inputs(f["pose"], f["auds"], f["pose6"], f["eye"]) for f in frames]
+        packed_dev = [p.to(dev) for p in packed]
+        resident = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
+                                 deliver=False, depth=lanes, **kw)
+
+        def render_resident(i):
+            if resident.in_flight() == resident.depth:
+                resident.collect()
+            resident.submit(packed_dev[i % len(packed_dev)])
+
+        def drain_resident():
+            while resident.in_flight():
+                resident.collect()
+            resident.pipe.sync()
+    else:
+        def render_resident(i):
+            f = dev_frames[i % len(dev_frames)]
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=model.opt.fp16):
+                out = model.render(f["ro"], f["rd"], f["auds"], bg_local, f["pose6"], eye=f["eye"], index=0, bg_color=None,
+                                   perturb=False, path=path, **kw)
+            return sharder.gather(out["image"][0])
+        drain_resident = None
 
     # ---- host inputs for `e2e`: one pinned block per frame (pose, pose6, eye, audio window); the public streaming API
     #      (radnerf_b200.stream.FrameStreamer) copies it in, generates the rays on the device, renders, all-gathers the tiles
     #      and copies the image back to pinned host memory -- the device->host copy of frame i overlaps frame i+1 (depth 2)
     if path == "fused":
-        from radnerf_b200.stream import FrameStreamer, pack_inputs
-        packed = [pack_inputs(f["pose"], f["auds"], f["pose6"], f["eye"]) for f in frames]
         streamer = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
-                                 deliver=(rank == 0), depth=2, **kw)
+                                 deliver=(rank == 0), depth=max(2, lanes), **kw)
         h2d_bytes, d2h_bytes = streamer.h2d_bytes, streamer.d2h_bytes
 
         def render_e2e(i):
@@ -300,7 +322,11 @@ def run_ours(args):
         barrier()
         l0 = abi.launch_count()
         fused = getattr(model, "_fused", None)
-        it0 = fused.loop_iterations() if fused is not None else 0
+
+        def loop_iters():   # over all frame lanes
+            sts = ([fused] if fused is not None else []) + list(getattr(model, "_fused_lanes", {}).values())
+            return sum(s.loop_iterations() for s in sts if s.workspace is not None)
+        it0 = loop_iters()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as cs:
             e0.record()
@@ -315,7 +341,7 @@ def run_ours(args):
         if fused is not None and fused.use_graph:
             # a captured frame was counted as its `capture_unroll` plain iterations plus ONE pass of the WHILE node's body;
             # replace that one pass by the body's real executions (lower bound when some frame needs < capture_unroll)
-            launches += 3 * (max(0, (fused.loop_iterations() - it0) - fused.capture_unroll * steps) - steps)
+            launches += 3 * (max(0, (loop_iters() - it0) - fused.capture_unroll * steps) - steps)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -323,7 +349,7 @@ def run_ours(args):
         return ms, launches, cs.summary()
 
     W = max(3, args.warmup)
-    ms, launches, clocks = timed(render_resident, args.steps, W)
+    ms, launches, clocks = timed(render_resident, args.steps, W, drain_resident)
     ms_e2e, _, _ = timed(render_e2e, args.steps, W, drain_e2e)
     fps, fps_e2e = args.steps / (ms / 1e3), args.steps / (ms_e2e / 1e3)
 
@@ -332,10 +358,12 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic", "impl": "ours",
             "config": {"workload": WORKLOAD % (hw, hw),
-                       "frame": [hw, hw], "rays_per_frame": hw * hw, "path": path,
+                       "frame": [hw, hw], "rays_per_frame": hw * hw, "path": path, "frames_in_flight": lanes,
                        "parallelism": "rays of each frame sharded by interleaved row tiles over %d GPU(s), all-gather of image tiles: %s" % (world, gather_impl),
-                       "l2": "the %d frames cycled through carry %.0f MB of distinct ray inputs (> 126 MB L2); hash tables and "
-                             "weights are re-used across frames by design" % (len(frames), len(frames) * hw * hw * 24 / 1e6)},
+                       "l2": "every frame regenerates its %.0f MB of rays from the pose and rewrites its %.0f MB workspace; with %d frames in "
+                             "flight the streamed working set is %.0f MB (> 126 MB L2 for >= 4 lanes); hash tables (8 MB) and weights are "
+                             "re-used across frames by design" % (hw * hw * 24 / 1e6, 21.0 * hw * hw / 262144, lanes,
+                                                                  lanes * (hw * hw * 24 / 1e6 + 21.0 * hw * hw / 262144 + 8.5 * hw * hw / 262144))},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "api": "radnerf_b200.stream.FrameStreamer (depth-2: the image copy-out of frame i overlaps frame i+1)" if path == "fused"
@@ -346,7 +374,7 @@ def run_ours(args):
     #      headline: ray sharding cuts latency, but a 512x512 frame cannot scale past its ~0.29 ms dependency chain
     if world > 1 and path == "fused":
         from radnerf_b200.stream import FrameStreamer as _FS
-        full = _FS(model, hw, hw, intr, bg_t[0], frames[0]["auds"].shape, use_eye=True, deliver=True, depth=2, **kw)
+        full = _FS(model, hw, hw, intr, bg_t[0], frames[0]["auds"].shape, use_eye=True, deliver=True, depth=max(2, lanes), **kw)
         model.enc_a = None
 
         def render_fp(i):

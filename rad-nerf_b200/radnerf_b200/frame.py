@@ -87,25 +87,17 @@ def supported(model):
         return False
 
 
-class FusedState:
-    def __init__(self, model):
-        dev = model.density_bitfield.device
-        self.dev = dev
-        self.versions = None
-        self.N = 0
-        self.workspace = None
-        self.head_consts = torch.zeros(3 * 64, device=dev)
-        self.torso_consts = torch.zeros(96, device=dev)
-        self.enc_a_state = torch.zeros(65, device=dev)  # [0..63] smoothed audio code, [64] validity flag (device side)
-        self.frames = 0
-        self.graphs = {}      # config key -> (CUDAGraph, static inputs, outputs)
-        self.side = torch.cuda.Stream(device=dev)
-        self.cond_event = torch.cuda.Event()
-        self.use_graph = True
-        self.last_static = None   # input buffers of the graph used by the last frame
-        self.capture_unroll = 1   # loop iterations captured as plain nodes; set from the warm-up frame before each capture
+class FusedShared:
+    """What every frame in flight shares: fp16 copies of tables / weight blobs (read-only for the kernels), the
+    lip-smoothing state that chains consecutive frames, the occupied-cell box."""
 
-    def refresh_weights(self, model):
+    def __init__(self, model):
+        self.dev = model.density_bitfield.device
+        self.versions = None
+        self.generation = 0
+        self.enc_a_state = torch.zeros(65, device=self.dev)  # [0..63] smoothed audio code, [64] validity flag (device side)
+
+    def refresh(self, model):
         params = getattr(self, "_params", None)
         if params is None:   # the module tree is fixed: walk it once, then only compare (pointer, version) per frame
             params = [model.encoder.embeddings, model.encoder_ambient.embeddings] + list(model.ambient_net.parameters()) + \
@@ -120,7 +112,7 @@ class FusedState:
         if versions == self.versions:
             return
         self.versions = versions
-        self.graphs.clear()  # captured graphs hold pointers to the old blobs
+        self.generation += 1   # lanes drop their captured graphs: they hold pointers to the old blobs
         self.h16 = {}  # fp16 copies of the small-net parameters used by the conditioning kernel
         self.table3 = pack_table(model.encoder)
         self.table2 = pack_table(model.encoder_ambient)
@@ -139,16 +131,6 @@ class FusedState:
                 il_pack(d[0].weight[:, :42], 64, 48), il_pack(d[1].weight, 64, 64), il_pack(d[2].weight, 16, 64),
                 il_pack(t[0].weight[:, :74], 32, 80), il_pack(t[1].weight, 32, 32), il_pack(t[2].weight, 16, 32)])
             assert self.torso_blob.numel() * 2 == abi.lib().rn_torso_blob_bytes()
-
-    def ensure_workspace(self, N):
-        if N != self.N:
-            nbytes = int(abi.lib().rn_frame_workspace_bytes(N))
-            self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)  # zeroed: the stats block is never reset by the library
-            self.ws_bytes = nbytes
-            self.N = N
-            self.torso_alpha = torch.empty(N, 1, device=self.dev)
-            self.torso_color = torch.empty(N, 3, device=self.dev)
-            self.graphs.clear()
 
     def occupied_box(self, model):
         """device [6]: bounding box of all occupied cells of the density bitfield (every cascade, world coordinates), inflated
@@ -176,6 +158,53 @@ class FusedState:
             self._occ_box.copy_(box)   # an empty grid leaves (+inf, -inf): every ray is pruned, as it would find nothing
             self._occ_tag = tag
         return self._occ_box
+
+
+class FusedState:
+    """Per-LANE state of the fused renderer (a lane = one frame in flight): workspace, hoisted-term vectors, captured
+    graphs and their input buffers, forked stream.  Weights and the smoothing state live in `shared` (attribute
+    look-ups fall through to it)."""
+
+    def __init__(self, model, shared=None):
+        dev = model.density_bitfield.device
+        self.dev = dev
+        self.shared = shared if shared is not None else FusedShared(model)
+        self.generation = -1
+        self.N = 0
+        self.workspace = None
+        self.head_consts = torch.zeros(3 * 64, device=dev)
+        self.torso_consts = torch.zeros(96, device=dev)
+        self.frames = 0
+        self.graphs = {}      # config key -> (CUDAGraph, static inputs, outputs)
+        self.side = torch.cuda.Stream(device=dev)
+        self.cond_event = torch.cuda.Event()
+        self.use_graph = True
+        self.last_static = None   # input buffers of the graph used by the last frame
+        self.capture_unroll = 1   # loop iterations captured as plain nodes; set from the warm-up frame before each capture
+
+    def __getattr__(self, name):   # only called when normal look-up fails: shared weights / state
+        if name == "shared":
+            raise AttributeError(name)
+        return getattr(self.shared, name)
+
+    def refresh_weights(self, model):
+        self.shared.refresh(model)
+        if self.generation != self.shared.generation:
+            self.generation = self.shared.generation
+            self.graphs.clear()
+
+    def occupied_box(self, model):
+        return self.shared.occupied_box(model)
+
+    def ensure_workspace(self, N):
+        if N != self.N:
+            nbytes = int(abi.lib().rn_frame_workspace_bytes(N))
+            self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)  # zeroed: the stats block is never reset by the library
+            self.ws_bytes = nbytes
+            self.N = N
+            self.torso_alpha = torch.empty(N, 1, device=self.dev)
+            self.torso_color = torch.empty(N, 3, device=self.dev)
+            self.graphs.clear()
 
     def loop_iterations(self):
         """march/evaluate/composite iterations executed since the workspace was created (device counter; forces a sync).
@@ -249,15 +278,24 @@ def conditioning_desc(model, st, auds, eye_t, pose6):
     return cd
 
 
-def advance_conditioning(model, auds, eye=None, poses=None):
-    """Run only the per-frame conditioning kernel (audio nets + lip-smoothing EMA) for a frame that is NOT rendered here:
-    a rank that renders a slice of a sequence calls this for the frames just before its slice so that its smoothing
-    state matches a run over the whole sequence (radnerf_b200.stream.render_sequence)."""
+def lane_state(model, lane=0):
+    """FusedState of frame lane `lane` (lane 0 is `model._fused`); all lanes share one FusedShared"""
     abi.lib()
-    st = getattr(model, "_fused", None)
-    if st is None:
-        st = model._fused = FusedState(model)
-    st.refresh_weights(model)
+    st0 = getattr(model, "_fused", None)
+    if st0 is None:
+        st0 = model._fused = FusedState(model)
+    if lane == 0:
+        return st0
+    lanes = getattr(model, "_fused_lanes", None)
+    if lanes is None:
+        lanes = model._fused_lanes = {}
+    if lane not in lanes:
+        lanes[lane] = FusedState(model, shared=st0.shared)
+    return lanes[lane]
+
+
+def _sync_smoothing_state(model, st):
+    """`model.enc_a` (the reference's attribute) mirrors the device-side state"""
     if model.smooth_lips:
         prev = getattr(model, "enc_a", None)
         if prev is None:
@@ -265,14 +303,55 @@ def advance_conditioning(model, auds, eye=None, poses=None):
         elif prev.data_ptr() != st.enc_a_state.data_ptr():
             st.enc_a_state[:64].copy_(prev.reshape(-1))
             st.enc_a_state[64] = 1.0
-    auds_t = auds.contiguous().float()
+
+
+def launch_conditioning(model, lane, auds, eye=None, poses=None):
+    """The conditioning kernel of ONE frame on the current stream, writing lane `lane`'s hoisted-term vectors and advancing
+    the shared lip-smoothing state.  Callers that keep several frames in flight (radnerf_b200.stream.FramePipeline) run these
+    in frame order on one stream and render the frame with render_frame(..., lane=lane, external_cond=True)."""
+    st = lane_state(model, lane)
+    st.refresh_weights(model)
+    _sync_smoothing_state(model, st)
+    auds_t = None if auds is None else auds.contiguous().float()
     eye_t = None if eye is None else eye.reshape(-1).float().contiguous()
     pose6 = poses.reshape(-1).float().contiguous() if model.torso else None
     st._keep = (auds_t, eye_t, pose6)   # alive until the kernel has run
-    cd = conditioning_desc(model, st, auds_t, eye_t, pose6)
+    # callers that stream frames pass the same (static) buffers every time: build the descriptor once per set of pointers
+    key = (None if auds_t is None else (auds_t.data_ptr(), tuple(auds_t.shape)), None if eye_t is None else eye_t.data_ptr(),
+           None if pose6 is None else pose6.data_ptr(), st.shared.generation)
+    cache = st.__dict__.setdefault("_cd_cache", {})
+    cd = cache.get(key)
+    if cd is None:
+        cache.clear()
+        cd = cache[key] = conditioning_desc(model, st, auds_t, eye_t, pose6)
     abi.check(abi.lib().rn_frame_conditioning(C.byref(cd), abi.cur_stream()))
-    if model.smooth_lips:
+    if model.smooth_lips and auds is not None:
         model.enc_a = st.enc_a_state[:64].view(1, 64)
+
+
+def replay_lane(model, lane):
+    """Replay lane `lane`'s last captured frame graph as is: the caller has written the frame's inputs into that graph's
+    input buffers (FusedState.last_static) and run launch_conditioning for the lane.  Returns the graph's output dict, or
+    None when there is nothing to replay (no graph yet, or weights / occupancy changed): call render_frame then."""
+    st = lane_state(model, lane)
+    gen = st.shared.generation
+    st.refresh_weights(model)
+    st.occupied_box(model)
+    entry = st.__dict__.get("last_entry")
+    if entry is None or gen != st.shared.generation or not st.graphs:
+        return None
+    graph, static, outs, n_kernels = entry
+    graph.replay()
+    abi.lib().rn_note_graph_replay(n_kernels)
+    st.frames += 1
+    return outs
+
+
+def advance_conditioning(model, auds, eye=None, poses=None):
+    """Run only the per-frame conditioning kernel (audio nets + lip-smoothing EMA) for a frame that is NOT rendered here:
+    a rank that renders a slice of a sequence calls this for the frames just before its slice so that its smoothing
+    state matches a run over the whole sequence (radnerf_b200.stream.render_sequence)."""
+    launch_conditioning(model, 0, auds, eye, poses)
 
 
 def head_desc(model, st, rays_o, rays_d, noises, dt_gamma, max_steps, T_thresh):
@@ -297,7 +376,8 @@ def head_desc(model, st, rays_o, rays_d, noises, dt_gamma, max_steps, T_thresh):
     return hd, (weights_sum, depth, image, nears, fars)
 
 
-def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_scalar, noises, dt_gamma, max_steps, T_thresh):
+def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_scalar, noises, dt_gamma, max_steps, T_thresh,
+            external_cond=False):
     """the frame's launch sequence (capturable: no host sync, outputs allocated with torch.empty)"""
     L = abi.lib()
     N = rays_o.shape[0]
@@ -308,14 +388,17 @@ def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_s
     #      + the first march (the head waits for `cond_event` only before its first network evaluation); the torso branch
     #      only meets the head in the final blend, so it fills the SMs the march / composite phases of the head loop leave
     #      idle.  Works the same under CUDA-graph capture (fork / join edges).
-    cd = conditioning_desc(model, st, auds, eye_t, pose6)
+    #      With external_cond the conditioning kernel already ran (launch_conditioning, frame pipelining) and only the
+    #      torso branch is forked.
     cur = torch.cuda.current_stream()
     results = {}
     torso_bg = torch.empty(N, 3, device=dev) if model.torso else None
     st.side.wait_stream(cur)
     with torch.cuda.stream(st.side):
-        abi.check(L.rn_frame_conditioning(C.byref(cd), abi.cur_stream()))
-        st.cond_event.record(st.side)
+        if not external_cond:
+            cd = conditioning_desc(model, st, auds, eye_t, pose6)
+            abi.check(L.rn_frame_conditioning(C.byref(cd), abi.cur_stream()))
+            st.cond_event.record(st.side)
         if model.torso:
             td = FrameTorsoDesc()
             td.N, td.grid_size = N, int(model.grid_size)
@@ -331,7 +414,7 @@ def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_s
 
     # ---- head
     hd, (weights_sum, depth, image, nears, fars) = head_desc(model, st, rays_o, rays_d, noises, dt_gamma, max_steps, T_thresh)
-    hd.consts_ready_event = st.cond_event.cuda_event
+    hd.consts_ready_event = None if external_cond else st.cond_event.cuda_event
     abi.check(L.rn_frame_head(C.byref(hd), stream))
 
     cur.wait_stream(st.side)  # join: the final blend needs the torso
@@ -345,7 +428,7 @@ def _launch(model, st, rays_o, rays_d, auds, bg_coords, pose6, eye_t, bg_t, bg_s
 
 
 def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=0, dt_gamma=0, bg_color=None, perturb=False,
-                 force_all_rays=False, max_steps=1024, T_thresh=1e-4, **kwargs):
+                 force_all_rays=False, max_steps=1024, T_thresh=1e-4, lane=0, external_cond=False, **kwargs):
     """Fused inference frame.  With `model._fused.use_graph` (default) the launch sequence is captured once per
     configuration into a CUDA graph and replayed: inputs are copied into the graph's static buffers and the returned
     tensors are the graph's static OUTPUT buffers -- they are overwritten by the next call (consume or clone them first)."""
@@ -353,10 +436,7 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
         raise RuntimeError("render_frame is the inference path; training goes through run_cuda")
     if not supported(model):
         raise NotImplementedError("model configuration outside the fused kernels' specialisation")
-    abi.lib()
-    st = getattr(model, "_fused", None)
-    if st is None:
-        st = model._fused = FusedState(model)
+    st = lane_state(model, lane)
     st.refresh_weights(model)
     st.occupied_box(model)   # refreshed here, outside any capture, when the bitfield changed
 
@@ -368,14 +448,8 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
     dev = rays_o.device
     st.ensure_workspace(N)
 
-    # lip-smoothing state: `model.enc_a` (the reference's attribute) mirrors the device-side state
-    if model.smooth_lips:
-        prev = getattr(model, "enc_a", None)
-        if prev is None:
-            st.enc_a_state.zero_()
-        elif prev.data_ptr() != st.enc_a_state.data_ptr():
-            st.enc_a_state[:64].copy_(prev.reshape(-1))
-            st.enc_a_state[64] = 1.0
+    if not external_cond:
+        _sync_smoothing_state(model, st)
     auds_t = None if auds is None else auds.contiguous().float()
     eye_t = None if eye is None else eye.reshape(-1).float().contiguous()
     pose6 = poses.reshape(-1).float().contiguous() if model.torso else None
@@ -389,7 +463,7 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
 
     if st.use_graph and not perturb:
         key = (N, None if auds_t is None else tuple(auds_t.shape), eye_t is not None, bg_t is not None, bg_scalar, float(dt_gamma),
-               int(max_steps), float(T_thresh), float(model.mean_density_torso), model.density_bitfield.data_ptr())
+               int(max_steps), float(T_thresh), float(model.mean_density_torso), model.density_bitfield.data_ptr(), bool(external_cond))
         entry = st.graphs.get(key)
         if entry is None:
             # small per-frame inputs live in ONE block [pose 4x4 | pose6 | eye | pad | auds] so that a streaming caller
@@ -408,21 +482,22 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
             # warm-up outside capture (lazy kernel attributes, module loading) on a scratch copy of the smoothing state
             saved = st.enc_a_state.clone()
             _launch(model, st, static["rays_o"], static["rays_d"], static["auds"], static["bg_coords"], static["pose6"], static["eye"],
-                    static["bg"], bg_scalar, None, dt_gamma, max_steps, T_thresh)
+                    static["bg"], bg_scalar, None, dt_gamma, max_steps, T_thresh, external_cond)
             st.enc_a_state.copy_(saved)
             torch.cuda.synchronize()
             # the warm-up frame tells how many loop iterations this kind of frame needs: capture that many as plain kernel
             # nodes, the (normally idle) remainder of the loop as one conditional WHILE node
-            st.capture_unroll = max(1, len(frame_stats(model)))
+            st.capture_unroll = max(1, len(frame_stats(model, st)))
             graph = torch.cuda.CUDAGraph()
             k0 = abi.launch_count()
             with torch.cuda.graph(graph, capture_error_mode="relaxed"):  # rn_frame_head captures the loop body on a helper stream
                 outs = _launch(model, st, static["rays_o"], static["rays_d"], static["auds"], static["bg_coords"], static["pose6"],
-                               static["eye"], static["bg"], bg_scalar, None, dt_gamma, max_steps, T_thresh)
+                               static["eye"], static["bg"], bg_scalar, None, dt_gamma, max_steps, T_thresh, external_cond)
             st.enc_a_state.copy_(saved)  # capture does not execute, but keep the invariant explicit
             entry = st.graphs[key] = (graph, static, outs, abi.launch_count() - k0)
         graph, static, outs, n_kernels = entry
         st.last_static = static
+        st.last_entry = entry
         # a caller that already wrote into the graph's input buffers (FrameStreamer) passes those very tensors: no copies
         for k, v in (("rays_o", rays_o), ("rays_d", rays_d), ("bg_coords", bg_coords), ("auds", auds_t), ("eye", eye_t),
                      ("pose6", pose6), ("bg", bg_t)):
@@ -434,8 +509,8 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
     else:
         noises = torch.rand(N, device=dev) if perturb else None
         results = _launch(model, st, rays_o, rays_d, auds_t, bg_coords, pose6, eye_t, bg_t, bg_scalar, noises, dt_gamma, max_steps,
-                          T_thresh)
-    if model.smooth_lips and auds is not None:
+                          T_thresh, external_cond)
+    if model.smooth_lips and auds is not None and not external_cond:
         model.enc_a = st.enc_a_state[:64].view(1, 64)
     st.frames += 1
     results['depth'] = results['depth'].view(*prefix)
@@ -443,9 +518,10 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
     return results
 
 
-def frame_stats(model):
-    """(n_alive, n_step, n_samples) per executed iteration of the last fused frame -- forces a sync; for tests/bench only"""
-    ctl = model._fused.ctl().cpu().numpy()
+def frame_stats(model, st=None):
+    """(n_alive, n_step, n_samples) per executed iteration of the last fused frame (of lane state `st`, default lane 0) --
+    forces a sync; for tests/bench only"""
+    ctl = (st if st is not None else model._fused).ctl().cpu().numpy()
     out = []
     for it in range(64):
         n_alive, n_step, step, done, n_samples = [int(v) for v in ctl[it][:5]]

@@ -44,8 +44,9 @@ class FrameSharder:
         self.peer = None   # (buffers, handles, ids32) once enable_peer_gather() succeeded
         self.parity = 0
 
-    def enable_peer_gather(self, group=None):
-        """switch gather() to direct peer stores.  Returns False (and keeps NCCL) if symmetric memory is unavailable."""
+    def enable_peer_gather(self, group=None, n_buffers=2):
+        """switch gather() to direct peer stores.  Returns False (and keeps NCCL) if symmetric memory is unavailable.
+        n_buffers frame buffers are rotated (or addressed by `slot`): one per frame that can be in flight."""
         if self.world == 1:
             return False
         if (self.W * 3) % 4:
@@ -53,7 +54,7 @@ class FrameSharder:
         try:
             import torch.distributed._symmetric_memory as symm
             bufs, hdls = [], []
-            for _ in range(2):
+            for _ in range(max(2, n_buffers)):
                 t = symm.empty(self.H * self.W, 3, dtype=torch.float32, device=self.device)
                 hdls.append(symm.rendezvous(t, group if group is not None else dist.group.WORLD))
                 bufs.append(t)
@@ -68,19 +69,22 @@ class FrameSharder:
         """[H*W, c] -> this rank's rows [n_local, c] (contiguous)"""
         return t if self.world == 1 else t.index_select(0, self.ids).contiguous()
 
-    def gather(self, local):
-        """[n_local, c] per rank -> [H*W, c] on every rank"""
+    def gather(self, local, slot=None):
+        """[n_local, c] per rank -> [H*W, c] on every rank.  slot: which peer frame buffer to use (frame lanes); default rotates."""
         if self.world == 1:
             return local
         local = local.contiguous()
         if self.peer is not None and local.dtype == torch.float32 and local.dim() == 2 and local.shape[1] == 3:
             from . import abi
             bufs, hdls, ids32 = self.peer
-            k, self.parity = self.parity, self.parity ^ 1
+            if slot is None:
+                k, self.parity = self.parity, (self.parity + 1) % len(bufs)
+            else:
+                k = slot % len(bufs)
             abi.check(abi.lib().rn_scatter_rows_to_peers(abi.ptr(local), abi.ptr(ids32), local.shape[0], self.W, hdls[k].buffer_ptrs_dev,
                                                          self.world, abi.cur_stream()))
             hdls[k].barrier(channel=0)   # every rank's rows have landed in every rank's buffer k
-            return bufs[k]               # valid until the gather after next
+            return bufs[k]               # valid until this buffer's next gather
         out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local)
         return out.index_select(0, self.unpermute)

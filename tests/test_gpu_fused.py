@@ -219,3 +219,42 @@ def test_fused_frame_on_the_reference_configurations(name, hw, opt_kw):
         assert (out["depth"] - ref["depth"]).abs().max().item() <= 2e-3, name
         if model.torso:
             assert (out["torso_alpha"] - ref["torso_alpha"]).abs().max().item() <= 2e-3, name
+
+
+def test_pipelined_frames_keep_the_lip_smoothing_chain():
+    """Three frames in flight (FramePipeline lanes) must produce the images of a strictly sequential run, including the
+    lip-smoothing EMA that makes frame i depend on frames < i (conditioning kernels run in frame order on their own stream)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from radnerf_b200.stream import FrameStreamer, pack_inputs
+    from radnerf_b200.rays import RayGenerator
+    hw, n = 64, 9
+    model = bench.make_model(DEV, seed=7)
+    assert model.smooth_lips
+    frames, intr, bg = bench.make_frames(hw, n)
+    bg_t = torch.from_numpy(bg).to(DEV)
+    kw = model.opt.render_kwargs()
+    raygen = RayGenerator(hw, hw, intr, torch.device(DEV))
+    model.enc_a = None
+    want = []
+    for f in frames:
+        ro, rd = raygen(torch.from_numpy(f["pose"]).to(DEV))
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            out = model.render(ro[None], rd[None], torch.from_numpy(f["auds"]).to(DEV), bg_t[None], torch.from_numpy(f["pose6"]).to(DEV),
+                               eye=torch.from_numpy(f["eye"]).to(DEV), index=0, bg_color=None, perturb=False, path="fused", **kw)
+        want.append(out["image"].reshape(-1, 3).cpu().clone())
+    model.enc_a = None
+    streamer = FrameStreamer(model, hw, hw, intr, bg_t, frames[0]["auds"].shape, use_eye=True, depth=3, **kw)
+    got = [img.clone() for img in streamer.render_all([pack_inputs(f["pose"], f["auds"], f["pose6"], f["eye"]) for f in frames])]
+    assert len(got) == n
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert torch.equal(a, b), i
+    # and the chain is really there: rendering frame 5 without its history gives a different image
+    model.enc_a = None
+    f = frames[5]
+    ro, rd = raygen(torch.from_numpy(f["pose"]).to(DEV))
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        lone = model.render(ro[None], rd[None], torch.from_numpy(f["auds"]).to(DEV), bg_t[None], torch.from_numpy(f["pose6"]).to(DEV),
+                            eye=torch.from_numpy(f["eye"]).to(DEV), index=0, bg_color=None, perturb=False, path="fused", **kw)
+    assert not torch.equal(lone["image"].reshape(-1, 3).cpu(), want[5])
