@@ -255,7 +255,7 @@ def run_ours(args):
         def drain_resident():
             while resident.in_flight():
                 resident.collect()
-            resident.pipe.sync()
+            resident.sync()
     else:
         def render_resident(i):
             f = dev_frames[i % len(dev_frames)]

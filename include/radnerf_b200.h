@@ -265,6 +265,30 @@ int rn_frame_finalize(uint32_t N, const float* weights_sum, float* depth, float*
                       const float* fars, const float* bg_color, float bg_scalar, const float* torso_alpha,
                       const float* torso_color, float* torso_bg_out, void* stream);
 
+/* ---- streamed frames: the per-frame host work of radnerf_b200.stream.FrameStreamer in ONE call ------------------------
+ * (the frame loop of Trainer.test, nerf/utils.py:905-960, in steady state: every buffer, stream, event and the lane's
+ * captured frame graph are fixed; see csrc/pipeline.cu for the choreography).  Events come from rn_event_create.
+ * phase bit 0: copy-in, rays, conditioning, frame graph [, scatter to peers]; bit 1: [staging + device->host copy,] ev_done.
+ * Both bits in one call when there is no cross-rank barrier to issue in between. */
+typedef struct rn_lane_submit {
+    void* lane_stream; void* cond_stream; void* copy_stream;
+    void* ev_in; void* ev_cond; void* ev_done; void* ev_staged; void* ev_delivered;
+    const void* packed_src; void* flat_dst; uint64_t packed_bytes;        /* input block: pinned host or device -> graph input block */
+    const float* pose; float fx, fy, cx, cy; uint32_t H, W;                /* rn_get_rays arguments; n_rays = 0 skips it */
+    const int32_t* pixel_ids; uint32_t n_rays; uint32_t graph_kernels;
+    float* rays_o; float* rays_d;
+    const rn_conditioning_desc* cond;
+    void* graph_exec;                                                      /* cudaGraphExec_t of the lane's frame */
+    const float* image_local; const int32_t* ids; const uint64_t* peers;   /* rn_scatter_rows_to_peers arguments; peers NULL skips it */
+    uint32_t n_local, run_pixels, world, phase;
+    const void* stage_src; void* stage_dst; void* host_dst; uint64_t image_bytes;   /* host_dst NULL: no delivery */
+} rn_lane_submit;
+int rn_lane_submit_frame(const rn_lane_submit* s);
+int rn_event_create(void** ev);
+int rn_event_destroy(void* ev);
+int rn_event_synchronize(void* ev);
+int rn_stream_wait_event(void* stream, void* ev);
+
 /* ------------------------------------------------------------------ diagnostics ---------------------- */
 
 /* one 128 x N x K fp16 GEMM tile through the hand-written tcgen05/TMEM path (out = A @ W^T, fp32 accumulate);

@@ -9,13 +9,37 @@ The device-to-host copy of frame i runs on a second stream while frame i+1 is re
 and a slot is reused only after the copy that read it has completed (event-ordered, no host sync on the submit path).
 `collect()` is the only blocking call.  Per-frame latency is unchanged; throughput is no longer render + copy but
 max(render, copy, host issue)."""
+import ctypes as C
 from collections import deque
 
 import numpy as np
 import torch
 
+from . import abi
 from .rays import RayGenerator
 from .sharding import FrameSharder
+
+
+_vp, _u32, _u64, _f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float
+
+
+class LaneSubmit(C.Structure):   # rn_lane_submit (include/radnerf_b200.h)
+    _fields_ = [("lane_stream", _vp), ("cond_stream", _vp), ("copy_stream", _vp),
+                ("ev_in", _vp), ("ev_cond", _vp), ("ev_done", _vp), ("ev_staged", _vp), ("ev_delivered", _vp),
+                ("packed_src", _vp), ("flat_dst", _vp), ("packed_bytes", _u64),
+                ("pose", _vp), ("fx", _f32), ("fy", _f32), ("cx", _f32), ("cy", _f32), ("H", _u32), ("W", _u32),
+                ("pixel_ids", _vp), ("n_rays", _u32), ("graph_kernels", _u32), ("rays_o", _vp), ("rays_d", _vp),
+                ("cond", _vp), ("graph_exec", _vp),
+                ("image_local", _vp), ("ids", _vp), ("peers", _vp),
+                ("n_local", _u32), ("run_pixels", _u32), ("world", _u32), ("phase", _u32),
+                ("stage_src", _vp), ("stage_dst", _vp), ("host_dst", _vp), ("image_bytes", _u64)]
+
+
+abi.register("rn_lane_submit_frame", [C.POINTER(LaneSubmit)])
+abi.register("rn_event_create", [C.POINTER(_vp)])
+abi.register("rn_event_destroy", [_vp])
+abi.register("rn_event_synchronize", [_vp])
+abi.register("rn_stream_wait_event", [_vp, _vp])
 
 
 def pack_inputs(pose, auds, pose6=None, eye=None):
@@ -112,6 +136,9 @@ class FrameStreamer:
         self.delivered = [torch.cuda.Event() for _ in range(depth)]
         self.pending = deque()
         self.static = [None] * depth
+        self.fast = [None] * depth      # per lane: (LaneSubmit, things it points to) once the lane's graph exists
+        self.fast_generation = -1
+        self.H, self.W = H, W
         self.h2d_bytes = 4 * self.n_in
         self.d2h_bytes = 12 * H * W
 
@@ -140,6 +167,8 @@ class FrameStreamer:
         from . import frame as _frame
         assert packed.numel() == self.n_in and (packed.is_cuda or packed.is_pinned())
         k = self.pipe.next_lane()
+        if self._submit_fast(k, packed):
+            return
         kw = dict(index=0, bg_color=None, perturb=False, **self.kw)
         st = self.static[k]
         if st is None or _frame.lane_state(self.model, k).last_static is not st:
@@ -159,18 +188,107 @@ class FrameStreamer:
             auds, pose6, eye = self._views(st["flat"])
             self.pipe.submit(st["rays_o"][None], st["rays_d"][None], auds, st["bg_coords"][None], pose6, eye=eye, post=self._post,
                              ready_on=ls, static_inputs=True, **kw)
-        self.pending.append(k)
+        self.pending.append((k, False))
+        self._arm_fast(k)
+
+    # ---- steady state: one C call per frame (csrc/pipeline.cu) ---------------------------------------------------------
+    def _arm_fast(self, k):
+        """after a frame went through the Python path on lane k, everything the lane needs is fixed: describe it once"""
+        from . import frame as _frame
+        st = _frame.lane_state(self.model, k)
+        entry = st.__dict__.get("last_entry")
+        static = self.static[k]
+        peer = self.sharder.peer if self.sharder.world > 1 else None
+        if entry is None or static is None or (self.sharder.world > 1 and peer is None) or not hasattr(entry[0], "raw_cuda_graph_exec"):
+            return   # no graph (perturbed frames), or the NCCL gather: stay on the Python path
+        graph, _, outs, n_kernels = entry
+        torch.cuda.synchronize(self.dev)   # the Python-path frame used torch events; start the C-event bookkeeping from idle
+        L = abi.lib()
+        ev = []
+        for _ in range(5):
+            e = _vp()
+            abi.check(L.rn_event_create(C.byref(e)))
+            ev.append(e.value)
+        auds, pose6, eye = self._views(static["flat"])
+        cd = _frame.conditioning_desc(self.model, st, auds.contiguous(), None if eye is None else eye.contiguous(),
+                                      pose6.contiguous() if self.model.torso else None)
+        s = LaneSubmit()
+        s.lane_stream, s.cond_stream, s.copy_stream = self.pipe.streams[k].cuda_stream, self.pipe.cond_stream.cuda_stream, self.copy_stream.cuda_stream
+        s.ev_in, s.ev_cond, s.ev_done, s.ev_staged, s.ev_delivered = ev
+        s.flat_dst, s.packed_bytes = static["flat"].data_ptr(), 4 * self.n_in
+        g = self.raygen
+        s.pose, s.fx, s.fy, s.cx, s.cy, s.H, s.W = static["pose"].data_ptr(), g.fx, g.fy, g.cx, g.cy, g.H, g.W
+        s.pixel_ids, s.n_rays = (None if g.ids is None else g.ids.data_ptr()), g.n
+        s.rays_o, s.rays_d = static["rays_o"].data_ptr(), static["rays_d"].data_ptr()
+        s.cond = C.cast(C.pointer(cd), _vp)
+        s.graph_exec, s.graph_kernels = graph.raw_cuda_graph_exec(), n_kernels
+        image = outs["image"]
+        s.image_local = image.data_ptr()
+        if peer is not None:
+            bufs, hdls, ids32 = peer
+            s.ids, s.peers, s.n_local, s.run_pixels, s.world = ids32.data_ptr(), hdls[k % len(bufs)].buffer_ptrs_dev, image.shape[0], self.W, self.sharder.world
+            s.stage_src = bufs[k % len(bufs)].data_ptr()
+        else:
+            s.stage_src = image.data_ptr()
+        s.stage_dst, s.host_dst = self.dev_stage[k].data_ptr(), (self.host_out[k].data_ptr() if self.deliver else None)
+        s.image_bytes = 12 * self.H * self.W
+        self.fast[k] = (s, cd, ev, entry, hdls[k % len(bufs)] if peer is not None else None)
+        self.fast_generation = st.shared.generation
+
+    def _submit_fast(self, k, packed):
+        f = self.fast[k]
+        if f is None:
+            return False
+        from . import frame as _frame
+        st = _frame.lane_state(self.model, k)
+        m = self.model
+        st.shared.refresh(m)
+        st.shared.occupied_box(m)
+        ea = getattr(m, "enc_a", None)
+        if (st.shared.generation != self.fast_generation or st.__dict__.get("last_entry") is not f[3]
+                or (m.smooth_lips and (ea is None or ea.data_ptr() != st.enc_a_state.data_ptr()))):
+            self.fast = [None] * self.depth   # weights / graph / smoothing state changed under us: back to the Python path
+            torch.cuda.synchronize(self.dev)
+            return False
+        s, barrier = f[0], f[4]
+        s.packed_src = packed.data_ptr()
+        self._keep = packed
+        L = abi.lib()
+        if barrier is None:
+            s.phase = 3
+            abi.check(L.rn_lane_submit_frame(C.byref(s)))
+        else:
+            s.phase = 1
+            abi.check(L.rn_lane_submit_frame(C.byref(s)))
+            with torch.cuda.stream(self.pipe.streams[k]):
+                barrier.barrier(channel=0)   # every rank's rows have landed in every rank's frame buffer of this lane
+            s.phase = 2
+            abi.check(L.rn_lane_submit_frame(C.byref(s)))
+        self.pipe.n += 1
+        self.pending.append((k, True))
+        return True
 
     def in_flight(self):
         return len(self.pending)
 
+    def sync(self):
+        """order the CURRENT stream after every frame submitted so far (device-side wait, no host block)"""
+        self.pipe.sync()
+        cur = abi.cur_stream()
+        for f in self.fast:
+            if f is not None:
+                abi.check(abi.lib().rn_stream_wait_event(cur, f[2][2]))   # the lane's ev_done
+
     def collect(self):
         """blocks until the oldest submitted frame is on the host; returns the pinned [H*W, 3] image (valid until `depth`
         more frames have been submitted)"""
-        slot = self.pending.popleft()
+        slot, fast = self.pending.popleft()
         if not self.deliver:
             return None
-        self.delivered[slot].synchronize()
+        if fast:
+            abi.check(abi.lib().rn_event_synchronize(self.fast[slot][2][4]) if self.fast[slot] is not None else 0)
+        else:
+            self.delivered[slot].synchronize()
         return self.host_out[slot]
 
     def render_all(self, packed_frames):
