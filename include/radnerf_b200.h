@@ -288,6 +288,13 @@ int rn_event_create(void** ev);
 int rn_event_destroy(void* ev);
 int rn_event_synchronize(void* ev);
 int rn_stream_wait_event(void* stream, void* ev);
+/* sizeof() of a public descriptor struct by name ("rn_lane_submit", ...), 0 if unknown: lets a binding check its mirror */
+uint32_t rn_sizeof(const char* name);
+
+/* diagnostics (tools/, not part of the operator contract) */
+void rn_debug_set_audio_prof(void* stamps);
+void rn_debug_set_max_iters(uint32_t n);
+void rn_debug_set_while_node(int on);
 
 /* ------------------------------------------------------------------ diagnostics ---------------------- */
 

@@ -13,6 +13,7 @@
 //
 // The split in two phases exists because the multi-GPU image assembly needs a cross-rank barrier between the scatter and
 // the staging copy, and that barrier is torch's symmetric-memory barrier, issued by the caller.
+#include <cstring>
 #include "common.cuh"
 #include "../../include/radnerf_b200.h"
 
@@ -90,4 +91,18 @@ extern "C" int rn_lane_submit_frame(const rn_lane_submit* s) {
         RN_CU(cudaEventRecord((cudaEvent_t)s->ev_done, ls));
     }
     return RN_OK;
+}
+
+// sizes of the public descriptor structs, so that a binding (radnerf_b200/frame.py, stream.py: ctypes.Structure mirrors) can
+// verify its layout against the library it loaded
+extern "C" uint32_t rn_sizeof(const char* name) {
+    if (!name) return 0;
+    const struct { const char* n; uint32_t s; } table[] = {
+        {"rn_grid_table", (uint32_t)sizeof(rn_grid_table)},           {"rn_conditioning_desc", (uint32_t)sizeof(rn_conditioning_desc)},
+        {"rn_frame_head_desc", (uint32_t)sizeof(rn_frame_head_desc)}, {"rn_frame_torso_desc", (uint32_t)sizeof(rn_frame_torso_desc)},
+        {"rn_lane_submit", (uint32_t)sizeof(rn_lane_submit)},
+    };
+    for (const auto& e : table)
+        if (strcmp(e.n, name) == 0) return e.s;
+    return 0;
 }

@@ -252,7 +252,7 @@ class FrameStreamer:
             return False
         s, barrier = f[0], f[4]
         s.packed_src = packed.data_ptr()
-        self._keep = packed
+        self.__dict__.setdefault("_keep", {})[k] = packed   # the async copy-in reads it: alive until the lane's next frame
         L = abi.lib()
         if barrier is None:
             s.phase = 3
@@ -283,7 +283,11 @@ class FrameStreamer:
         """blocks until the oldest submitted frame is on the host; returns the pinned [H*W, 3] image (valid until `depth`
         more frames have been submitted)"""
         slot, fast = self.pending.popleft()
-        if not self.deliver:
+        if not self.deliver:   # nothing to hand over: just wait for the frame itself (keeps the host `depth` frames ahead at most)
+            if fast and self.fast[slot] is not None:
+                abi.check(abi.lib().rn_event_synchronize(self.fast[slot][2][2]))
+            elif not fast:
+                self.pipe.ev_done[slot].synchronize()
             return None
         if fast:
             abi.check(abi.lib().rn_event_synchronize(self.fast[slot][2][4]) if self.fast[slot] is not None else 0)

@@ -58,3 +58,19 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|liboracle", src, flags=re.M):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_ctypes_mirrors_match_the_library_struct_layouts():
+    """the ctypes.Structure mirrors in frame.py / stream.py must have exactly the size of the C structs they stand for"""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "rad-nerf_b200"))
+    from radnerf_b200 import abi, frame, stream
+    L = abi.lib()
+    L.rn_sizeof.restype = C.c_uint32
+    L.rn_sizeof.argtypes = [C.c_char_p]
+    for name, mirror in (("rn_grid_table", frame.GridTable), ("rn_conditioning_desc", frame.ConditioningDesc),
+                         ("rn_frame_head_desc", frame.FrameHeadDesc), ("rn_frame_torso_desc", frame.FrameTorsoDesc),
+                         ("rn_lane_submit", stream.LaneSubmit)):
+        assert L.rn_sizeof(name.encode()) == C.sizeof(mirror) > 0, name
+    assert L.rn_sizeof(b"no_such_struct") == 0

@@ -183,3 +183,29 @@ def test_posemath_roundtrip():
     P[:, :3, 3] = torch.tensor([[0.07, 3.38, -0.23], [1, 2, 3]])
     out = convert_poses(P)
     assert out.shape == (2, 6) and torch.allclose(out[:, :3], e, atol=1e-6) and torch.allclose(out[:, 3:], P[:, :3, 3])
+
+
+def test_sequence_slices_partition_the_frames():
+    sys.path.insert(0, os.path.join(ROOT, "rad-nerf_b200"))
+    from radnerf_b200.stream import sequence_slice
+    for n in (0, 1, 7, 200, 201):
+        for world in (1, 2, 3, 8):
+            spans = [sequence_slice(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))             # contiguous, in order
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)   # balanced, larger slices first
+
+
+def test_pack_inputs_layout_matches_the_graph_input_block():
+    """[pose 4x4 | pose6 | eye | pad | audio window]: the layout render_frame's static input block and FrameStreamer rely on"""
+    sys.path.insert(0, os.path.join(ROOT, "rad-nerf_b200"))
+    if not torch.cuda.is_available():
+        pytest.skip("pinned host memory needs a CUDA driver")
+    from radnerf_b200.stream import pack_inputs
+    pose = np.arange(16, dtype=np.float32).reshape(4, 4)
+    auds = np.arange(8 * 44 * 16, dtype=np.float32).reshape(8, 44, 16) + 100
+    p = pack_inputs(pose, auds, pose6=np.arange(6) + 50, eye=np.array([[0.25]], np.float32)).numpy()
+    assert p.shape == (24 + 8 * 44 * 16,)
+    assert np.array_equal(p[:16], pose.reshape(-1)) and np.array_equal(p[16:22], np.arange(6) + 50) and p[22] == 0.25 and p[23] == 0
+    assert np.array_equal(p[24:], auds.reshape(-1))
