@@ -197,6 +197,7 @@ def test_sequence_slices_partition_the_frames():
             assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)   # balanced, larger slices first
 
 
+@pytest.mark.gpu
 def test_pack_inputs_layout_matches_the_graph_input_block():
     """[pose 4x4 | pose6 | eye | pad | audio window]: the layout render_frame's static input block and FrameStreamer rely on"""
     sys.path.insert(0, os.path.join(ROOT, "rad-nerf_b200"))
