@@ -351,6 +351,24 @@ def run_ours(args):
     W = max(3, args.warmup)
     ms, launches, clocks = timed(render_resident, args.steps, W, drain_resident)
     ms_e2e, _, _ = timed(render_e2e, args.steps, W, drain_e2e)
+    e2e_u8 = None
+    if path == "fused":
+        # the same end-to-end loop with the output stage on the device (uint8 frames, what the reference's video writer consumes)
+        streamer8 = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
+                                  deliver=(rank == 0), depth=max(2, lanes), output="uint8", **kw)
+
+        def render_u8(i):
+            if streamer8.in_flight() == streamer8.depth:
+                streamer8.collect()
+            streamer8.submit(packed[i % len(packed)])
+
+        def drain_u8():
+            while streamer8.in_flight():
+                streamer8.collect()
+        ms_u8, _, _ = timed(render_u8, args.steps, W, drain_u8)
+        e2e_u8 = {"value": args.steps / (ms_u8 / 1e3), "unit": UNIT, "h2d_bytes_per_step": streamer8.h2d_bytes,
+                  "d2h_bytes_per_step": streamer8.d2h_bytes, "what": "as e2e, but frames are converted to uint8 on the device "
+                  "((pred * 255).astype(uint8), the reference's host-side expression) before the copy-out"}
     fps, fps_e2e = args.steps / (ms / 1e3), args.steps / (ms_e2e / 1e3)
 
     stats = getattr(model, "last_frame_stats", None)
@@ -369,6 +387,8 @@ def run_ours(args):
                     "api": "radnerf_b200.stream.FrameStreamer (depth-2: the image copy-out of frame i overlaps frame i+1)" if path == "fused"
                            else "model.render per frame, synchronous copy-out",
                     "ms_per_step": ms_e2e / args.steps}}
+    if e2e_u8 is not None:
+        line["e2e_uint8"] = e2e_u8
 
     # ---- N > 1: the same job in FRAME-parallel mode (whole frames per GPU, no collective), reported next to the ray-sharded
     #      headline: ray sharding cuts latency, but a 512x512 frame cannot scale past its ~0.29 ms dependency chain

@@ -160,6 +160,10 @@ int rn_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, ui
 int rn_get_rays(const float* pose, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
                 const int32_t* pixel_ids, uint32_t n, float* rays_o, float* rays_d, void* stream);
 
+/* Output stage: fp32 image values in [0,1] -> uint8 on the device, exactly the host expression of the
+ * reference's video writer `(pred * 255).astype(np.uint8)` (nerf/utils.py:952-960).  n_values % 16 == 0. */
+int rn_image_to_uint8(const float* image, uint8_t* out, uint64_t n_values, void* stream);
+
 /* Multi-GPU frame assembly without a collective library (replaces ncclAllGather + un-permute for the ray-sharded frame,
  * SURVEY 8(e) "Inference frame"): this rank's finished image rows are stored directly into every rank's full-frame buffer
  * through peer mappings (NVLink / NVSwitch).  local [n_local,3] fp32; ids [n_local] pixel index of each row in the full frame,
@@ -282,6 +286,7 @@ typedef struct rn_lane_submit {
     const float* image_local; const int32_t* ids; const uint64_t* peers;   /* rn_scatter_rows_to_peers arguments; peers NULL skips it */
     uint32_t n_local, run_pixels, world, phase;
     const void* stage_src; void* stage_dst; void* host_dst; uint64_t image_bytes;   /* host_dst NULL: no delivery */
+    uint32_t to_uint8, reserved;   /* to_uint8: stage_src holds image_bytes/4 fp32 values; stage_dst / host_dst receive image_bytes/4 bytes */
 } rn_lane_submit;
 int rn_lane_submit_frame(const rn_lane_submit* s);
 int rn_event_create(void** ev);

@@ -82,10 +82,17 @@ extern "C" int rn_lane_submit_frame(const rn_lane_submit* s) {
         if (s->host_dst) {
             RN_REQUIRE(s->ev_staged && s->ev_delivered && s->stage_src && s->stage_dst, "delivery needs staging buffers and events");
             RN_CU(cudaStreamWaitEvent(ls, (cudaEvent_t)s->ev_delivered, 0));   // the copy that last read this staging slot has drained
-            RN_CU(cudaMemcpyAsync(s->stage_dst, s->stage_src, s->image_bytes, cudaMemcpyDeviceToDevice, ls));
+            uint64_t out_bytes = s->image_bytes;
+            if (s->to_uint8) {   // output stage on the device: a quarter of the bytes cross PCIe
+                out_bytes = s->image_bytes / 4;
+                int rc = rn_image_to_uint8((const float*)s->stage_src, (uint8_t*)s->stage_dst, out_bytes, ls);
+                if (rc) return rc;
+            } else {
+                RN_CU(cudaMemcpyAsync(s->stage_dst, s->stage_src, s->image_bytes, cudaMemcpyDeviceToDevice, ls));
+            }
             RN_CU(cudaEventRecord((cudaEvent_t)s->ev_staged, ls));
             RN_CU(cudaStreamWaitEvent(xs, (cudaEvent_t)s->ev_staged, 0));
-            RN_CU(cudaMemcpyAsync(s->host_dst, s->stage_dst, s->image_bytes, cudaMemcpyDeviceToHost, xs));
+            RN_CU(cudaMemcpyAsync(s->host_dst, s->stage_dst, out_bytes, cudaMemcpyDeviceToHost, xs));
             RN_CU(cudaEventRecord((cudaEvent_t)s->ev_delivered, xs));
         }
         RN_CU(cudaEventRecord((cudaEvent_t)s->ev_done, ls));

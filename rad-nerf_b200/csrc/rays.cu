@@ -27,10 +27,37 @@ get_rays_kernel(const float* __restrict__ pose, float fx, float fy, float cx, fl
     }
 }
 
+// fp32 image in [0,1] -> uint8, 16 values per thread (one 16-byte store): the reference does this on the host after the
+// device->host copy, `(pred * 255).astype(np.uint8)` (nerf/utils.py:952-960) -- fp32 multiply, truncation toward zero
+__global__ void __launch_bounds__(256)
+image_to_uint8_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, uint32_t n16) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n16; k += gridDim.x * blockDim.x) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(src + 4 * k + q);
+            w[q] = (uint32_t)(uint8_t)__fmul_rn(v.x, 255.0f) | ((uint32_t)(uint8_t)__fmul_rn(v.y, 255.0f) << 8) |
+                   ((uint32_t)(uint8_t)__fmul_rn(v.z, 255.0f) << 16) | ((uint32_t)(uint8_t)__fmul_rn(v.w, 255.0f) << 24);
+        }
+        dst[k] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 }  // namespace
 }  // namespace rn
 
 using namespace rn;
+
+extern "C" int rn_image_to_uint8(const float* image, uint8_t* out, uint64_t n_values, void* stream) {
+    if (n_values == 0) return RN_OK;
+    RN_REQUIRE(image && out, "null pointer");
+    RN_REQUIRE(n_values % 16 == 0 && n_values < (1ull << 35) && ((uintptr_t)image & 15) == 0 && ((uintptr_t)out & 15) == 0,
+               "n_values must be a multiple of 16 and the buffers 16-byte aligned");
+    const uint32_t n16 = (uint32_t)(n_values / 16);
+    image_to_uint8_kernel<<<wave_grid(n16, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(image),
+                                                                                  reinterpret_cast<uint4*>(out), n16);
+    return finish_launch("rn_image_to_uint8");
+}
 
 extern "C" int rn_get_rays(const float* pose, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
                            const int32_t* pixel_ids, uint32_t n, float* rays_o, float* rays_d, void* stream) {

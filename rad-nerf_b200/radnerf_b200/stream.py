@@ -32,7 +32,8 @@ class LaneSubmit(C.Structure):   # rn_lane_submit (include/radnerf_b200.h)
                 ("cond", _vp), ("graph_exec", _vp),
                 ("image_local", _vp), ("ids", _vp), ("peers", _vp),
                 ("n_local", _u32), ("run_pixels", _u32), ("world", _u32), ("phase", _u32),
-                ("stage_src", _vp), ("stage_dst", _vp), ("host_dst", _vp), ("image_bytes", _u64)]
+                ("stage_src", _vp), ("stage_dst", _vp), ("host_dst", _vp), ("image_bytes", _u64),
+                ("to_uint8", _u32), ("reserved", _u32)]
 
 
 abi.register("rn_lane_submit_frame", [C.POINTER(LaneSubmit)])
@@ -117,10 +118,13 @@ class FramePipeline:
 
 class FrameStreamer:
     def __init__(self, model, H, W, intrinsics, bg_coords, auds_shape, use_eye=True, sharder=None, deliver=True, depth=2,
-                 **render_kw):
+                 output="float32", **render_kw):
         """bg_coords: [H*W, 2] on the device (this rank's rows if `sharder` splits the frame); auds_shape: e.g. (8, 44, 16);
         deliver=False skips the device->host stage (ranks other than the one that consumes the frames); depth = frames in
-        flight (= lanes of the FramePipeline underneath)."""
+        flight (= lanes of the FramePipeline underneath); output="uint8" converts on the device -- the reference's
+        `(pred * 255).astype(np.uint8)` -- and copies a quarter of the bytes to the host."""
+        assert output in ("float32", "uint8") and (output == "float32" or (H * W * 3) % 16 == 0)
+        self.u8 = output == "uint8"
         self.model, self.kw, self.depth, self.deliver = model, render_kw, depth, deliver
         self.dev = bg_coords.device
         self.sharder = sharder if sharder is not None else FrameSharder(H, W, 1, 0, self.dev)
@@ -130,8 +134,9 @@ class FrameStreamer:
         self.n_in = 24 + int(np.prod(auds_shape))
         self.pipe = FramePipeline(model, lanes=depth)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
-        self.dev_stage = [torch.empty(H * W, 3, device=self.dev) for _ in range(depth)]
-        self.host_out = [torch.empty(H * W, 3).pin_memory() for _ in range(depth)]
+        odt = torch.uint8 if self.u8 else torch.float32
+        self.dev_stage = [torch.empty(H * W, 3, device=self.dev, dtype=odt) for _ in range(depth)]
+        self.host_out = [torch.empty(H * W, 3, dtype=odt).pin_memory() for _ in range(depth)]
         self.staged = [torch.cuda.Event() for _ in range(depth)]
         self.delivered = [torch.cuda.Event() for _ in range(depth)]
         self.pending = deque()
@@ -140,7 +145,7 @@ class FrameStreamer:
         self.fast_generation = -1
         self.H, self.W = H, W
         self.h2d_bytes = 4 * self.n_in
-        self.d2h_bytes = 12 * H * W
+        self.d2h_bytes = (3 if self.u8 else 12) * H * W
 
     def _views(self, flat):
         auds = flat[24:self.n_in].view(self.auds_shape)
@@ -153,7 +158,10 @@ class FrameStreamer:
         if self.deliver:
             ls = torch.cuda.current_stream(self.dev)
             ls.wait_event(self.delivered[k])          # the copy that last read this staging slot has drained
-            self.dev_stage[k].copy_(img)
+            if self.u8:
+                abi.check(abi.lib().rn_image_to_uint8(abi.ptr(img), abi.ptr(self.dev_stage[k]), img.numel(), abi.cur_stream()))
+            else:
+                self.dev_stage[k].copy_(img)
             self.staged[k].record(ls)
             with torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(self.staged[k])
@@ -232,6 +240,7 @@ class FrameStreamer:
             s.stage_src = image.data_ptr()
         s.stage_dst, s.host_dst = self.dev_stage[k].data_ptr(), (self.host_out[k].data_ptr() if self.deliver else None)
         s.image_bytes = 12 * self.H * self.W
+        s.to_uint8 = 1 if self.u8 else 0
         self.fast[k] = (s, cd, ev, entry, hdls[k % len(bufs)] if peer is not None else None)
         self.fast_generation = st.shared.generation
 

@@ -258,3 +258,26 @@ def test_pipelined_frames_keep_the_lip_smoothing_chain():
         lone = model.render(ro[None], rd[None], torch.from_numpy(f["auds"]).to(DEV), bg_t[None], torch.from_numpy(f["pose6"]).to(DEV),
                             eye=torch.from_numpy(f["eye"]).to(DEV), index=0, bg_color=None, perturb=False, path="fused", **kw)
     assert not torch.equal(lone["image"].reshape(-1, 3).cpu(), want[5])
+
+
+def test_uint8_output_stage_equals_the_reference_host_expression():
+    """FrameStreamer(output="uint8") must deliver (pred * 255).astype(np.uint8) of the fp32 frame (nerf/utils.py:952-960), through
+    both the first-frame Python path and the one-call C path"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from radnerf_b200.stream import FrameStreamer, pack_inputs
+    hw = 64
+    model = bench.make_model(DEV, seed=11)
+    frames, intr, bg = bench.make_frames(hw, 7)
+    bg_t = torch.from_numpy(bg).to(DEV)
+    kw = model.opt.render_kwargs()
+    packed = [pack_inputs(f["pose"], f["auds"], f["pose6"], f["eye"]) for f in frames]
+    model.enc_a = None
+    f32 = [img.clone().numpy() for img in FrameStreamer(model, hw, hw, intr, bg_t, frames[0]["auds"].shape, depth=2, **kw).render_all(packed)]
+    model.enc_a = None
+    u8 = [img.clone().numpy() for img in FrameStreamer(model, hw, hw, intr, bg_t, frames[0]["auds"].shape, depth=2, output="uint8", **kw).render_all(packed)]
+    assert len(u8) == len(f32) == 7
+    for a, b in zip(u8, f32):
+        assert a.dtype == np.uint8 and np.array_equal(a, (b * 255).astype(np.uint8))
+    assert u8[0].min() < 255   # not just background
