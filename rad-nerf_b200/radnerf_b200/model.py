@@ -417,103 +417,111 @@ class NeRFNetwork(nn.Module):
         return self.run_cuda(rays_o, rays_d, auds, bg_coords, poses, **kwargs)
 
     # ------------------------------------------------------------------------------------- occupancy maintenance
+    def _cell_centres(self):
+        """[H^3, 3] cell coordinates mapped to [-1, 1], listed in MORTON order: row n belongs to row n of `density_grid`.
+        Built once with morton3D_invert, so the maintenance passes below write whole grid rows instead of scattering."""
+        dev = self.density_bitfield.device
+        cache = getattr(self, "_cells", None)
+        if cache is None or cache.device != dev:
+            n = self.grid_size ** 3
+            if hasattr(self.ops.rm, "morton3D_invert"):
+                ijk = self.ops.rm.morton3D_invert(torch.arange(n, dtype=torch.int32, device=dev))
+            else:   # operator bundles without the inverse (CPU port): invert the forward map once
+                g = torch.arange(self.grid_size, dtype=torch.int32, device=dev)
+                ijk_lin = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+                ijk = torch.empty_like(ijk_lin)
+                ijk[self.ops.rm.morton3D(ijk_lin).long()] = ijk_lin
+            cache = self._cells = 2 * ijk.float() / (self.grid_size - 1) - 1
+        return cache
+
+    def _cascade_geometry(self, cas):
+        bound = min(2 ** cas, self.bound)
+        half_cell = bound / self.grid_size
+        return bound - half_cell, half_cell   # scale applied to the [-1,1] centres, half a cell in world units
+
     @torch.no_grad()
     def mark_untrained_grid(self, poses, intrinsic, S=64):
-        """cells no training camera sees get density -1 (renderer.py:318-381)"""
-        rm = self.ops.rm
+        """cells that no training camera sees get density -1 (renderer.py:318-381: in front of the camera and inside the
+        frustum widened by one cell).  All cells of a cascade are tested at once, cameras in chunks of S."""
         if isinstance(poses, np.ndarray):
             poses = torch.from_numpy(poses)
-        B = poses.shape[0]
-        fx, fy, cx, cy = intrinsic
+        fx, fy, cx, cy = [float(v) for v in intrinsic]
         dev = self.density_bitfield.device
-        axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-        count = torch.zeros_like(self.density_grid)
-        poses = poses.to(dev)
-        for xs in axis:
-            for ys in axis:
-                for zs in axis:
-                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
-                    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
-                    indices = rm.morton3D(coords).long()
-                    world_xyzs = (2 * coords.float() / (self.grid_size - 1) - 1).unsqueeze(0)
-                    for cas in range(self.cascade):
-                        bound = min(2 ** cas, self.bound)
-                        half_grid_size = bound / self.grid_size
-                        cas_world_xyzs = world_xyzs * (bound - half_grid_size)
-                        head = 0
-                        while head < B:
-                            tail = min(head + S, B)
-                            cam_xyzs = cas_world_xyzs - poses[head:tail, :3, 3].unsqueeze(1)
-                            cam_xyzs = cam_xyzs @ poses[head:tail, :3, :3]
-                            mask_z = cam_xyzs[:, :, 2] > 0
-                            mask_x = torch.abs(cam_xyzs[:, :, 0]) < cx / fx * cam_xyzs[:, :, 2] + half_grid_size * 2
-                            mask_y = torch.abs(cam_xyzs[:, :, 1]) < cy / fy * cam_xyzs[:, :, 2] + half_grid_size * 2
-                            count[cas, indices] += (mask_z & mask_x & mask_y).sum(0).reshape(-1)
-                            head += S
-        self.density_grid[count == 0] = -1
+        poses = poses.to(dev).float()
+        rot, origin = poses[:, :3, :3], poses[:, :3, 3]
+        centres = self._cell_centres()
+        block = 1 << 18   # cells per pass: bounds the [S, block, 3] intermediate
+        seen = torch.zeros_like(self.density_grid, dtype=torch.bool)
+        for cas in range(self.cascade):
+            scale, half_cell = self._cascade_geometry(cas)
+            for c0 in range(0, centres.shape[0], block):
+                world = centres[c0:c0 + block] * scale
+                for p0 in range(0, poses.shape[0], S):
+                    cam = (world.unsqueeze(0) - origin[p0:p0 + S].unsqueeze(1)) @ rot[p0:p0 + S]     # world -> camera, [S, n, 3]
+                    depth = cam[..., 2]
+                    inside = (depth > 0) & (cam[..., 0].abs() < cx / fx * depth + half_cell * 2) & \
+                             (cam[..., 1].abs() < cy / fy * depth + half_cell * 2)
+                    seen[cas, c0:c0 + block] |= inside.any(0)
+        self.density_grid[~seen] = -1
+
+    def _query_density_grid(self, enc_a, eye, chunk=1 << 19):
+        """density of every cell of every cascade at a jittered position inside the cell -> [cascade, H^3] (Morton order)"""
+        centres = self._cell_centres()
+        fresh = torch.empty_like(self.density_grid)
+        for cas in range(self.cascade):
+            scale, half_cell = self._cascade_geometry(cas)
+            for c0 in range(0, centres.shape[0], chunk):
+                pts = centres[c0:c0 + chunk] * scale
+                pts += (torch.rand_like(pts) * 2 - 1) * half_cell
+                sigma = self.density(pts, enc_a, eye)['sigma'].reshape(-1).detach()
+                fresh[cas, c0:c0 + chunk] = sigma.to(fresh.dtype) * self.density_scale
+        return fresh
+
+    def _query_torso_grid(self, pose6, enc_a, ind_code):
+        """torso alpha of every cell of the 2-D grid at a jittered position; stored x/y-transposed as the reference does"""
+        H = self.grid_size
+        g = torch.arange(H, dtype=torch.float32, device=self.density_bitfield.device)
+        gx, gy = torch.meshgrid(g, g, indexing='ij')
+        xy = torch.stack([gx.reshape(-1), gy.reshape(-1)], -1)             # cell (x, y), x-major
+        half_cell = 1 / H
+        pts = (2 * xy / (H - 1) - 1) * (1 - half_cell)
+        pts += (torch.rand_like(pts) * 2 - 1) * half_cell
+        alphas, _, _ = self.forward_torso(pts, pose6, enc_a, ind_code)
+        out = torch.zeros_like(self.density_grid_torso)
+        out[(xy[:, 1] * H + xy[:, 0]).long()] = alphas.squeeze(1).float()     # row = y * H + x
+        return out
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128):
-        """occupancy EMA + bitfield rebuild + mean sample count (renderer.py:383-501)"""
+        """occupancy maintenance between epochs (renderer.py:383-501): re-query the density at every cell for a random audio
+        window, dilate, merge into the running grid by max(decayed old, fresh) where both are valid, rebuild the bitfield
+        with threshold min(mean density, density_thresh); in the torso phase the same for the 2-D alpha grid (5x5 max-pool
+        as dilation); finally the average sample count of the last <= 16 training steps."""
         rm = self.ops.rm
         dev = self.density_bitfield.device
         rand_idx = random.randint(0, self.aud_features.shape[0] - 1)
         from .synthetic import audio_window
-        auds = torch.as_tensor(audio_window(np.asarray(self.aud_features.cpu()) if torch.is_tensor(self.aud_features)
-                                            else self.aud_features, rand_idx, self.att)).to(dev)
-        enc_a = self.encode_audio(auds)
+        feats = np.asarray(self.aud_features.cpu()) if torch.is_tensor(self.aud_features) else self.aud_features
+        enc_a = self.encode_audio(torch.as_tensor(audio_window(feats, rand_idx, self.att)).to(dev))
 
-        if not self.torso:
-            tmp_grid = torch.zeros_like(self.density_grid)
+        if not self.torso:   # the head grid is frozen while the torso trains
             eye = self.eye_area[[rand_idx]].to(dev) if self.exp_eye else None
-            axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-            for xs in axis:
-                for ys in axis:
-                    for zs in axis:
-                        xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
-                        coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
-                        indices = rm.morton3D(coords).long()
-                        xyzs = 2 * coords.float() / (self.grid_size - 1) - 1
-                        for cas in range(self.cascade):
-                            bound = min(2 ** cas, self.bound)
-                            half_grid_size = bound / self.grid_size
-                            cas_xyzs = xyzs * (bound - half_grid_size)
-                            cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half_grid_size
-                            sigmas = self.density(cas_xyzs, enc_a, eye)['sigma'].reshape(-1).detach().to(tmp_grid.dtype)
-                            sigmas *= self.density_scale
-                            tmp_grid[cas, indices] = sigmas
-            tmp_grid = rm.morton3D_dilation(tmp_grid)
-            valid_mask = (self.density_grid >= 0) & (tmp_grid >= 0)
-            self.density_grid[valid_mask] = torch.maximum(self.density_grid[valid_mask] * decay, tmp_grid[valid_mask])
-            self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
+            fresh = rm.morton3D_dilation(self._query_density_grid(enc_a, eye))
+            both_valid = (self.density_grid >= 0) & (fresh >= 0)
+            self.density_grid[both_valid] = torch.maximum(self.density_grid[both_valid] * decay, fresh[both_valid])
+            self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()   # untrained (-1) cells count as empty
             self.iter_density += 1
-            density_thresh = min(self.mean_density, self.density_thresh)
-            self.density_bitfield = rm.packbits(self.density_grid, density_thresh, self.density_bitfield)
-
-        if self.torso:
+            self.density_bitfield = rm.packbits(self.density_grid, min(self.mean_density, self.density_thresh), self.density_bitfield)
+        else:
             from .posemath import convert_poses
-            tmp_grid_torso = torch.zeros_like(self.density_grid_torso)
-            rand_idx = random.randint(0, self.poses.shape[0] - 1)
-            pose = convert_poses(self.poses[[rand_idx]]).to(dev)
-            ind_code = self.individual_codes_torso[[rand_idx]] if self.opt.ind_dim_torso > 0 else None
-            axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-            half_grid_size = 1 / self.grid_size
-            for xs in axis:
-                for ys in axis:
-                    xx, yy = torch.meshgrid(xs, ys, indexing='ij')
-                    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1)], dim=-1)
-                    indices = (coords[:, 1] * self.grid_size + coords[:, 0]).long()  # x/y transposed, as the reference
-                    xys = 2 * coords.float() / (self.grid_size - 1) - 1
-                    xys = xys * (1 - half_grid_size)
-                    xys += (torch.rand_like(xys) * 2 - 1) * half_grid_size
-                    alphas, _, _ = self.forward_torso(xys, pose, enc_a, ind_code)
-                    tmp_grid_torso[indices] = alphas.squeeze(1).float()
-            tmp_grid_torso = F.max_pool2d(tmp_grid_torso.view(1, 1, self.grid_size, self.grid_size), kernel_size=5, stride=1,
-                                          padding=2).view(-1)
-            self.density_grid_torso = torch.maximum(self.density_grid_torso * decay, tmp_grid_torso)
+            k = random.randint(0, self.poses.shape[0] - 1)
+            ind_code = self.individual_codes_torso[[k]] if self.opt.ind_dim_torso > 0 else None
+            fresh = self._query_torso_grid(convert_poses(self.poses[[k]]).to(dev), enc_a, ind_code)
+            fresh = F.max_pool2d(fresh.view(1, 1, self.grid_size, self.grid_size), kernel_size=5, stride=1, padding=2).view(-1)
+            self.density_grid_torso = torch.maximum(self.density_grid_torso * decay, fresh)
             self.mean_density_torso = torch.mean(self.density_grid_torso).item()
 
-        total_step = min(16, self.local_step)
-        if total_step > 0:
-            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        steps = min(16, self.local_step)
+        if steps > 0:
+            self.mean_count = int(self.step_counter[:steps, 0].sum().item() / steps)
         self.local_step = 0
