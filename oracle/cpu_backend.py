@@ -71,13 +71,16 @@ class GridEncoderCPU(nn.Module):
         self.align_corners = align_corners
         self.register_buffer('offsets', torch.from_numpy(offsets))
         self.embeddings = nn.Parameter(torch.empty(int(offsets[-1]), level_dim).uniform_(-1e-4, 1e-4))
+        # per-level scales as the DEVICE computes them (CUDA exp2f differs from libm by an ulp on some levels);
+        # None = libm.  Set from a golden file's `scales` when outputs must agree with the CUDA path to fp32 rounding.
+        self.device_scales = None
 
     def forward(self, inputs, bound=1):
         inputs = (inputs + bound) / (2 * bound)
         prefix = list(inputs.shape[:-1])
         out, _ = O.grid_encode_forward(_np(inputs.reshape(-1, self.input_dim).float()), _np(self.embeddings), _np(self.offsets),
                                        self.per_level_scale, self.base_resolution, False, self.gridtype_id,
-                                       self.align_corners, self.interp_id)
+                                       self.align_corners, self.interp_id, scales=self.device_scales)
         return torch.from_numpy(out).view(prefix + [self.output_dim])
 
 

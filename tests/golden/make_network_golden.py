@@ -53,6 +53,11 @@ def main():
     opt = Options(torso=True, smooth_lips=False, fp16=False)
     net = NeRFNetwork(types.SimpleNamespace(**{**vars(opt), "test_train": False})).eval()
     fill_parameters(net)
+    # level scales as CUDA's exp2f produces them (recorded from the device in the grid goldens; same L / H / resolution)
+    scales = np.load(os.path.join(HERE, "grid_g3_f32.npz"))["scales"]
+    for e in (net.encoder, net.encoder_ambient, net.torso_encoder):
+        assert e.num_levels == len(scales) and e.base_resolution == 16
+        e.device_scales = scales
     c = inputs()
     out = {}
     with torch.no_grad():
