@@ -40,13 +40,14 @@ def _outputs(device, ops=None, autocast=False):
     return {k: v.float().cpu().numpy() for k, v in out.items()}
 
 
-def _compare(got, tol):
+def _compare(got, tol, torso_tol=None):
     g = np.load(GOLD)
     assert set(got) == set(g.files)
     for k in g.files:
         a, b = got[k].reshape(g[k].shape), g[k]
         err = float(np.abs(a - b).max())
-        assert err <= tol * max(1.0, float(np.abs(b).max())), (k, err)
+        t = torso_tol if (torso_tol is not None and k.startswith("torso_")) else tol
+        assert err <= t * max(1.0, float(np.abs(b).max())), (k, err)
 
 
 def test_network_mirror_cpu_port_matches_the_reference_class():
@@ -61,7 +62,10 @@ def test_network_mirror_cuda_fp32_matches_the_reference_class():
     saved = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     try:
-        _compare(_outputs("cuda"), 2e-5)   # measured 1.06e-5 on sigma = exp(h): fp32 summation order of cuBLAS vs the CPU GEMM
+        # head: measured 1.06e-5 on sigma = exp(h) (fp32 summation order of cuBLAS vs the CPU GEMM).  torso: its inputs go through
+        # the frequency encoder, which on the GPU is `__sinf` as in the reference's CUDA build (-use_fast_math) while the golden's
+        # CPU run used libm (<= 2e-3 apart at 2^9 rad, tests/test_oracle_golden.py): 5.4e-5 measured on alpha
+        _compare(_outputs("cuda"), 2e-5, torso_tol=5e-4)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
 
