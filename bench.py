@@ -38,8 +38,8 @@ N_FRAMES_DISTINCT = 64  # distinct poses / audio windows cycled through
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default=os.environ.get("RADNERF_PATH", "auto"), choices=["auto", "fused", "ops"])
     ap.add_argument("--hw", type=int, default=HW)
@@ -315,20 +315,22 @@ def run_ours(args):
 
     def timed(fn, steps, warmup, drain=None):
         model.enc_a = None
-        for i in range(warmup):
-            fn(i)
-        if drain:
-            drain()
-        barrier()
-        l0 = abi.launch_count()
-        fused = getattr(model, "_fused", None)
-
-        def loop_iters():   # over all frame lanes
-            sts = ([fused] if fused is not None else []) + list(getattr(model, "_fused_lanes", {}).values())
-            return sum(s.loop_iterations() for s in sts if s.workspace is not None)
-        it0 = loop_iters()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # the clock sampler (nvidia-smi -lms 100) starts before the warm-up so that it is already reporting when the timed
+        # region -- a few tenths of a second -- runs; warm-up and timed steps are the same load
         with ClockSampler(local) as cs:
+            for i in range(warmup):
+                fn(i)
+            if drain:
+                drain()
+            barrier()
+            l0 = abi.launch_count()
+            fused = getattr(model, "_fused", None)
+
+            def loop_iters():   # over all frame lanes
+                sts = ([fused] if fused is not None else []) + list(getattr(model, "_fused_lanes", {}).values())
+                return sum(s.loop_iterations() for s in sts if s.workspace is not None)
+            it0 = loop_iters()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i in range(steps):
                 fn(warmup + i)
