@@ -5,8 +5,11 @@ arguments, same result keys) but issues a fixed sequence of launches with no hos
 (audio nets, lip smoothing, hoisted first-layer terms) -> device-driven march / fused-network / composite loop -> torso ->
 final blend.  Host work per frame is a handful of ctypes calls; everything data-dependent stays on the device.
 
-State cached on the model (`model._fused`): fp16 copies of the three hash tables and the interleaved fp16 weight blobs
-(rebuilt only when a parameter's version counter changes), the workspace, and the lip-smoothing state.
+State cached on the model: `FusedShared` -- packed fp16 copies of the three hash tables, the interleaved fp16 weight blobs
+(rebuilt only when a parameter's version counter changes), the lip-smoothing state, the occupied-cell box -- and one
+`FusedState` per frame LANE (`model._fused` = lane 0, `lane_state(model, k)`): workspace, hoisted-term vectors, captured
+CUDA graphs with their input buffers.  Several lanes = several frames in flight (radnerf_b200.stream.FramePipeline), with
+`launch_conditioning` / `render_frame(..., lane=k, external_cond=True)` / `replay_lane` as the building blocks.
 """
 import ctypes as C
 

@@ -1,14 +1,20 @@
 """Host-facing frame pipeline of the fused renderer: the loop the reference runs in Trainer.test (nerf/utils.py:905-960) --
 per frame: pose / audio window / eye value arrive on the host, the frame is rendered, `preds.detach().cpu()` brings the
-image back -- restated as a depth-2 pipeline:
+image back -- restated as a pipeline with several frames in flight:
 
-    pinned host block --(ONE H2D copy)--> graph input block --> rays on device --> fused frame graph --> [NCCL all-gather]
-        --> device staging slot --(copy stream, D2H)--> pinned host image slot
+    pinned host block --(ONE H2D copy)--> lane's graph input block --> rays on device --> conditioning kernel (frame order,
+        own stream) --> lane's frame graph --> [peer stores / NCCL all-gather] --> staging slot [fp32 or uint8]
+        --(copy stream, D2H)--> pinned host image slot
 
-The device-to-host copy of frame i runs on a second stream while frame i+1 is rendered; staging and host slots alternate,
-and a slot is reused only after the copy that read it has completed (event-ordered, no host sync on the submit path).
-`collect()` is the only blocking call.  Per-frame latency is unchanged; throughput is no longer render + copy but
-max(render, copy, host issue)."""
+* FramePipeline   K frame "lanes" on K streams sharing one set of weights; keeps the lip-smoothing chain exact.
+* FrameStreamer   drives the lanes from host inputs.  The first frame of a lane goes through Python (it captures the lane's
+                  CUDA graph); from then on a frame is ONE C call (rn_lane_submit_frame, csrc/pipeline.cu) with raw stream /
+                  event / graph handles, because issuing it from Python cost more host time than a ray-sharded frame needs
+                  on 4-8 GPUs.  `collect()` is the only blocking call.
+* render_sequence frame-parallel rendering of a known sequence over ranks (whole frames per GPU, no collective).
+
+Staging and host slots belong to a lane and are reused only after the copy that read them has completed (event-ordered, no
+host sync on the submit path)."""
 import ctypes as C
 from collections import deque
 
@@ -303,6 +309,16 @@ class FrameStreamer:
         else:
             self.delivered[slot].synchronize()
         return self.host_out[slot]
+
+    def close(self):
+        """wait for everything in flight and release the C-side events"""
+        torch.cuda.synchronize(self.dev)
+        for f in self.fast:
+            if f is not None:
+                for e in f[2]:
+                    abi.lib().rn_event_destroy(e)
+        self.fast = [None] * self.depth
+        self.pending.clear()
 
     def render_all(self, packed_frames):
         """generator over host images, keeping `depth` frames in flight"""
