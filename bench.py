@@ -185,6 +185,15 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
+    # context, next to the CPU number this arm is about: the reference's OWN CUDA extensions (oracle/_ref, built from
+    # /root/reference by oracle/build_ref.py) driven in the reference's op order on this box's GPU, if there is one
+    if not args.no_ref_cuda:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                line["ref_cuda"] = ref_cuda_frame_rate(torch.device("cuda", 0), args.hw, 30)
+        except Exception as e:  # noqa: BLE001
+            line["ref_cuda"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line))
 
 
@@ -416,11 +425,6 @@ def run_ours(args):
     if rank == 0:
         from radnerf_b200 import roofline
         line["roofline"], line["kernels"] = roofline.measure(model, dev_frames[0], bg_local, kw, path)
-        if world == 1 and not args.no_ref_cuda:
-            try:
-                line["ref_cuda"] = ref_cuda_frame_rate(dev, hw, min(args.steps, 30))
-            except Exception as e:  # the reference build is optional equipment
-                line["ref_cuda"] = {"unavailable": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             fps_cpu, threads, nsamp = cpu_frame_rate(hw, 1)
             line["cpu_baseline"] = {"value": fps_cpu, "unit": UNIT, "cores": threads, "kind": "port",
