@@ -182,7 +182,7 @@ int rn_scatter_rows_to_peers(const float* local, const int32_t* ids, uint32_t n_
  * linear interpolation, hidden width 64 (torso 32), SH degree 4.  Tables are fp16 (the reference's autocast path). */
 
 typedef struct rn_grid_table {
-    const void* table_f16;   /* [rows, 2] fp16 */
+    const void* table_f16;   /* [rows', 4] fp16: packed copy, row = [features of the cell (2) | features of its +x neighbour (2)] */
     const int32_t* offsets;  /* [17] the encoder's offsets (gridencoder/grid.py:118-131): level sizes and wrap rules */
     float S;                 /* log2(per_level_scale) */
     uint32_t H;              /* base resolution */

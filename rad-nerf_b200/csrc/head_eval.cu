@@ -125,8 +125,8 @@ head_eval_kernel(HeadEvalParams p, const FrameCur* cur) {
                    aCIN = umma::smem_u32(sCIN);
     const uint32_t aW = umma::smem_u32(s_blob);
     const uint32_t aOnes = umma::smem_u32(s_ones), aB0 = umma::smem_u32(s_biasop[0]), aB1 = umma::smem_u32(s_biasop[1]), aB2 = umma::smem_u32(s_biasop[2]);
-    const uint32_t* table3 = reinterpret_cast<const uint32_t*>(p.table3);
-    const uint32_t* table2 = reinterpret_cast<const uint32_t*>(p.table2);
+    const uint2* table3 = reinterpret_cast<const uint2*>(p.table3);
+    const uint2* table2 = reinterpret_cast<const uint2*>(p.table2);
 
     long long c_enc3 = 0, c_enc2 = 0, c_mma = 0, c_epi = 0, c_tile = 0, c_last = 0;
     const bool prof = p.prof != nullptr && t == 0;

@@ -69,7 +69,9 @@ static __device__ __noinline__ void mma_stage(uint32_t tmem_acc, uint32_t a0, ui
 }
 
 // ---- specialised grid level: tiled indexing, linear interpolation, align_corners = false, 2 fp16 features -------------
-// row(corner) = ((base + corner_delta) & mask) | or_off inside the packed fp16 copy of the table:
+// The packed fp16 copy of the table has 8-byte rows [features of the cell | features of its +x neighbour] (the neighbour of a
+// wrapping level is the wrapped one), so the two x-corners of every pair come from ONE load.
+// row(corner) = ((base + corner_delta) & mask) | or_off inside that copy:
 //   dense level   (index < size, no wrap): base includes the level's first row, mask = ~0, or_off = 0
 //   capped level  (power-of-two size):     mask = size - 1, or_off = first row, which must be a multiple of size
 // -- one logic op per corner instead of an and plus a 64-bit add (6 -> 3-4 instructions per gathered corner).
@@ -104,7 +106,7 @@ __device__ __forceinline__ void accum2(float2& acc, float w, uint32_t g) {
 // accumulation (see accum2); the index math is specialised: base = p0 + p1*s1 + p2*s2,
 // corner = (base + dx + dy*s1 + dz*s2) & mask.
 template <int D>
-static __device__ __noinline__ void fast_encode(const float (&x)[D], const uint32_t* __restrict__ table32, const FastLevel* __restrict__ lv,
+static __device__ __noinline__ void fast_encode(const float (&x)[D], const uint2* __restrict__ table64, const FastLevel* __restrict__ lv,
                                                 uint8_t* dst, uint32_t row, uint32_t Kdst, uint32_t dcol0) {
     bool oob = false;
 #pragma unroll
@@ -124,20 +126,21 @@ static __device__ __noinline__ void fast_encode(const float (&x)[D], const uint3
                 pg[d] = (uint32_t)fl;
                 fr[j][d] = pos - (float)pg[d];
             }
-            const uint32_t* __restrict__ tb = table32;
+            const uint2* __restrict__ tb = table64;
             if (oob) {
 #pragma unroll
                 for (int k = 0; k < (1 << D); ++k) g[j][k] = 0u;
             } else if constexpr (D == 3) {
                 const uint32_t b00 = pg[0] + pg[1] * L.s1 + pg[2] * L.s2 + L.base_add, b10 = b00 + L.s1, b01 = b00 + L.s2, b11 = b10 + L.s2;
-                g[j][0] = __ldg(tb + ((b00 & L.mask) | L.or_off)); g[j][1] = __ldg(tb + (((b00 + 1) & L.mask) | L.or_off));
-                g[j][2] = __ldg(tb + ((b10 & L.mask) | L.or_off)); g[j][3] = __ldg(tb + (((b10 + 1) & L.mask) | L.or_off));
-                g[j][4] = __ldg(tb + ((b01 & L.mask) | L.or_off)); g[j][5] = __ldg(tb + (((b01 + 1) & L.mask) | L.or_off));
-                g[j][6] = __ldg(tb + ((b11 & L.mask) | L.or_off)); g[j][7] = __ldg(tb + (((b11 + 1) & L.mask) | L.or_off));
+                // a row of the packed table holds the cell's features AND those of its +x neighbour (8 bytes): one load per x-pair
+                const uint2 q0 = __ldg(tb + ((b00 & L.mask) | L.or_off)), q1 = __ldg(tb + ((b10 & L.mask) | L.or_off));
+                const uint2 q2 = __ldg(tb + ((b01 & L.mask) | L.or_off)), q3 = __ldg(tb + ((b11 & L.mask) | L.or_off));
+                g[j][0] = q0.x; g[j][1] = q0.y; g[j][2] = q1.x; g[j][3] = q1.y;
+                g[j][4] = q2.x; g[j][5] = q2.y; g[j][6] = q3.x; g[j][7] = q3.y;
             } else {
                 const uint32_t b0 = pg[0] + pg[1] * L.s1 + L.base_add, b1 = b0 + L.s1;
-                g[j][0] = __ldg(tb + ((b0 & L.mask) | L.or_off)); g[j][1] = __ldg(tb + (((b0 + 1) & L.mask) | L.or_off));
-                g[j][2] = __ldg(tb + ((b1 & L.mask) | L.or_off)); g[j][3] = __ldg(tb + (((b1 + 1) & L.mask) | L.or_off));
+                const uint2 q0 = __ldg(tb + ((b0 & L.mask) | L.or_off)), q1 = __ldg(tb + ((b1 & L.mask) | L.or_off));
+                g[j][0] = q0.x; g[j][1] = q0.y; g[j][2] = q1.x; g[j][3] = q1.y;
             }
         }
         uint32_t packed[4];

@@ -138,7 +138,7 @@ torso_eval_kernel(TorsoEvalParams p) {
             const float dx1 = __half2float(__float2half_rn(__uint_as_float(v[1])));
             const float y0 = fminf(fmaxf(__fadd_rn(x0, dx0), -1.f), 1.f), y1 = fminf(fmaxf(__fadd_rn(x1, dx1), -1.f), 1.f);
             float x[2] = {__fmul_rn(__fadd_rn(y0, 1.0f), 0.5f), __fmul_rn(__fadd_rn(y1, 1.0f), 0.5f)};
-            fast_encode<2>(x, reinterpret_cast<const uint32_t*>(p.table), lv, sTIN, t, 80, 0);
+            fast_encode<2>(x, reinterpret_cast<const uint2*>(p.table), lv, sTIN, t, 80, 0);
         }
         // ---- torso L1 (K = 80) -> 32
         mma_stage(tmem_acc, aTIN, 80, 0, aW + T_WT1, 80, 0, 0, 0, 0, 0, 32, mbar, phase, bar_id, t);

@@ -221,11 +221,15 @@ class FusedState:
 
 
 def pack_table(enc):
-    """fp16 copy of a GridEncoder's table for the fused kernels: same rows, but every level whose size is a power of two
-    (the size-capped, wrapping levels) starts at a multiple of its size, so that the kernels can form a row index as
-    ((i & (size-1)) | first_row) -- see rn_grid_table.packed_offsets.  Returns (table [rows', 2] fp16, first rows [L] int32)."""
+    """fp16 copy of a GridEncoder's table for the fused kernels (rn_grid_table):
+      * every level whose size is a power of two (the size-capped, wrapping levels) starts at a multiple of its size, so a row
+        index is ((i & (size-1)) | first_row);
+      * a row holds the cell's two features AND the two features of its +x neighbour (row i+1 of the level, wrapped for a
+        wrapping level), so the kernels fetch both x-corners of a pair with one 8-byte load.
+    Returns (table [rows', 4] fp16, first rows [L] int32)."""
     offs = enc.offsets.cpu().numpy().astype(np.int64)
     emb = enc.embeddings.detach()
+    assert emb.shape[1] == 2
     first, cur = [], 0
     for l in range(len(offs) - 1):
         size = int(offs[l + 1] - offs[l])
@@ -233,9 +237,11 @@ def pack_table(enc):
         cur = (cur + align - 1) // align * align
         first.append(cur)
         cur += size
-    out = torch.zeros(cur, emb.shape[1], dtype=torch.float16, device=emb.device)
+    out = torch.zeros(cur, 4, dtype=torch.float16, device=emb.device)
     for l, f in enumerate(first):
-        out[f:f + int(offs[l + 1] - offs[l])] = emb[int(offs[l]):int(offs[l + 1])].to(torch.float16)
+        lvl = emb[int(offs[l]):int(offs[l + 1])].to(torch.float16)
+        out[f:f + lvl.shape[0], :2] = lvl
+        out[f:f + lvl.shape[0], 2:] = torch.roll(lvl, -1, 0)   # +x neighbour; the last row's wraps (only used by wrapping levels)
     return out, torch.tensor(first, dtype=torch.int32, device=emb.device)
 
 
