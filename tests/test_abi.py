@@ -47,6 +47,19 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == -1 and b"output_dim" in lib.rn_last_error_string()
     rc = lib.rn_sh_encode_forward(None, None, 4, 3, 9, None, None)
     assert rc == -2 and b"degree" in lib.rn_last_error_string()
+    # the fused-frame / streaming entry points validate their descriptors before touching the device
+    import ctypes as C
+    from radnerf_b200 import frame, stream
+    assert lib.rn_frame_head(None, None) == -1 and b"null descriptor" in lib.rn_last_error_string()
+    hd = frame.FrameHeadDesc()
+    hd.N = 64
+    assert lib.rn_frame_head(C.byref(hd), None) == -1 and b"null pointer" in lib.rn_last_error_string()
+    assert lib.rn_frame_conditioning(None, None) == -1
+    s = stream.LaneSubmit()
+    s.phase = 1
+    assert lib.rn_lane_submit_frame(C.byref(s)) == -1 and b"phase 1 needs" in lib.rn_last_error_string()
+    assert lib.rn_scatter_rows_to_peers(None, None, 8, 3, None, 2, None) == -1
+    assert lib.rn_image_to_uint8(None, None, 0, None) == 0       # empty input is a no-op, as everywhere in the ABI
 
 
 def test_product_never_imports_the_oracle():
