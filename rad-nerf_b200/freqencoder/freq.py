@@ -1,58 +1,54 @@
-"""FreqEncoder -- sin/cos positional encoding on libradnerf_b200.  Drop-in for /root/reference/freqencoder/freq.py
-(same class/attributes, `_freq_encoder` autograd contract: inputs cast to fp32, outputs fp32)."""
+"""Frequency (sin / cos) positional encoding on libradnerf_b200.
+
+Public surface of the reference's freqencoder/freq.py: `FreqEncoder(input_dim=3, degree=4)` with `.input_dim`, `.degree`,
+`.output_dim = input_dim * (1 + 2 * degree)`, `forward(inputs, **kw)`, and the functional `freq_encode(x, degree, width)`.
+Layout per row (freqencoder.cu:30-58): [x | per octave k: sin(2^k x), cos(2^k x)], computed in fp32 regardless of autocast.
+The kernels use the fast `__sinf` path exactly as the reference's `-use_fast_math` build does."""
 import torch
-import torch.nn as nn
-from torch.autograd import Function
+from torch import nn
 from torch.amp import custom_bwd, custom_fwd
 
-from radnerf_b200 import abi as _L
+from radnerf_b200 import abi
 
 
-class _freq_encoder(Function):
+class FreqEncodeFn(torch.autograd.Function):
+    """forward: rn_freq_encode_forward; backward: rn_freq_encode_backward (needs the forward's outputs: d sin = cos)"""
+
     @staticmethod
-    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)  # force float32 for better precision
-    def forward(ctx, inputs, degree, output_dim):
-        # inputs: [B, input_dim] float -> [B, output_dim] float
-        if not inputs.is_cuda:
-            inputs = inputs.cuda()
-        inputs = inputs.contiguous()
-        B, input_dim = inputs.shape
-        outputs = torch.empty(B, output_dim, dtype=inputs.dtype, device=inputs.device)
-        _L.check(_L.lib().rn_freq_encode_forward(_L.ptr(inputs), B, input_dim, degree, output_dim, _L.ptr(outputs),
-                                                 _L.cur_stream()))
-        ctx.save_for_backward(inputs, outputs)
-        ctx.dims = [B, input_dim, degree, output_dim]
-        return outputs
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, n_octaves, width):
+        x, _ = abi.rows(x.cuda() if not x.is_cuda else x)
+        y = x.new_empty(x.shape[0], width)
+        abi.call("rn_freq_encode_forward", x, x.shape[0], x.shape[1], n_octaves, width, y)
+        ctx.save_for_backward(x, y)
+        ctx.meta = (n_octaves, width)
+        return y
 
     @staticmethod
     @custom_bwd(device_type="cuda")
-    def backward(ctx, grad):
-        grad = grad.contiguous()
-        inputs, outputs = ctx.saved_tensors
-        B, input_dim, degree, output_dim = ctx.dims
-        grad_inputs = torch.empty_like(inputs)
-        _L.check(_L.lib().rn_freq_encode_backward(_L.ptr(grad), _L.ptr(outputs), B, input_dim, degree, output_dim,
-                                                  _L.ptr(grad_inputs), _L.cur_stream()))
-        return grad_inputs, None, None
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        n_octaves, width = ctx.meta
+        dx = torch.empty_like(x)
+        abi.call("rn_freq_encode_backward", dy.contiguous(), y, x.shape[0], x.shape[1], n_octaves, width, dx)
+        return dx, None, None
 
 
-freq_encode = _freq_encoder.apply
+freq_encode = FreqEncodeFn.apply
 
 
 class FreqEncoder(nn.Module):
     def __init__(self, input_dim=3, degree=4):
         super().__init__()
-        self.input_dim = input_dim
-        self.degree = degree
-        self.output_dim = input_dim + input_dim * 2 * degree
+        self.input_dim, self.degree = input_dim, degree
+        self.output_dim = input_dim * (1 + 2 * degree)
+
+    def extra_repr(self):
+        return f"input_dim={self.input_dim} degree={self.degree} output_dim={self.output_dim}"
 
     def __repr__(self):
-        return f"FreqEncoder: input_dim={self.input_dim} degree={self.degree} output_dim={self.output_dim}"
+        return "FreqEncoder: " + self.extra_repr()
 
     def forward(self, inputs, **kwargs):
-        # inputs: [..., input_dim] -> [..., output_dim]
-        prefix_shape = list(inputs.shape[:-1])
-        inputs = inputs.reshape(-1, self.input_dim)
-        outputs = freq_encode(inputs, self.degree, self.output_dim)
-        outputs = outputs.reshape(prefix_shape + [self.output_dim])
-        return outputs
+        flat = inputs.reshape(-1, self.input_dim)
+        return freq_encode(flat, self.degree, self.output_dim).view(*inputs.shape[:-1], self.output_dim)

@@ -1,195 +1,136 @@
-"""GridEncoder -- multi-resolution hash / tiled grid encoding on libradnerf_b200 (sm_100a).
+"""Multi-resolution hash / tiled grid encoder on libradnerf_b200 (sm_100a).
 
-Drop-in for /root/reference/gridencoder/grid.py: same class, constructor arguments, attributes, state-dict keys
-(`embeddings` fp32 [rows, C], `offsets` int32 [L+1]) and autograd/AMP contract (`_grid_encode`, grid.py:24-89).
-Differences are internal: the CUDA kernel writes [B, L*C] rows directly (no [L,B,C] buffer + permute copy,
-grid.py:47,57), consumes the incoming gradient in that layout (no permute copy, grid.py:75) and accumulates the
-table gradient in fp32 (the reference accumulates fp16 atomics under autocast, grid.py:77).
-"""
+Public surface of the reference's gridencoder/grid.py: `GridEncoder(input_dim=3, num_levels=16, level_dim=2, per_level_scale=2,
+base_resolution=16, log2_hashmap_size=19, desired_resolution=None, gridtype='hash', align_corners=False,
+interpolation='linear')` with the state-dict keys `embeddings` (fp32 [rows, C]) and `offsets` (int32 [L+1]), `forward(inputs,
+bound=1)`, `grad_total_variation(...)`, and the functional `grid_encode(...)` with the reference's positional arguments.
+
+What differs is below the surface: the kernel writes [B, L*C] rows directly (the reference fills [L, B, C] and permute-copies,
+grid.py:47,57), the backward consumes the gradient in that same layout and accumulates the table gradient in fp32 (the
+reference uses fp16 atomics under autocast, grid.py:77)."""
+import math
+
 import numpy as np
-
 import torch
-import torch.nn as nn
-from torch.autograd import Function
+from torch import nn
 from torch.amp import custom_bwd, custom_fwd
 
-from radnerf_b200 import abi as _L
+from radnerf_b200 import abi
 
-_gridtype_to_id = {
-    'hash': 0,
-    'tiled': 1,
-}
-
-_interp_to_id = {
-    'linear': 0,
-    'smoothstep': 1,
-}
-
-_RN_F32, _RN_F16 = 0, 1
-_LAYOUT_LBC, _LAYOUT_BLC = 0, 1
+GRID_TYPES = {'hash': 0, 'tiled': 1}
+INTERPOLATIONS = {'linear': 0, 'smoothstep': 1}
+_gridtype_to_id, _interp_to_id = GRID_TYPES, INTERPOLATIONS   # names other code may import
+F32, F16 = 0, 1            # RN_F32 / RN_F16
+ROWS_BLC = 1               # RN_LAYOUT_BLC: [B, L*C]
 
 
-def _dtype_id(t):
-    if t.dtype == torch.float32:
-        return _RN_F32
-    if t.dtype == torch.float16:
-        return _RN_F16
-    raise RuntimeError(f"GridEncoder: embeddings must be float32 or float16, got {t.dtype}")
+def _table_dtype_id(t):
+    try:
+        return {torch.float32: F32, torch.float16: F16}[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"GridEncoder: embeddings must be float32 or float16, got {t.dtype}") from None
 
 
-class _grid_encode(Function):
+def level_offsets(input_dim, num_levels, level_dim, per_level_scale, base_resolution, log2_hashmap_size, align_corners):
+    """first row of every level (+ total): a level has min(2^log2_hashmap_size, points^D) rows rounded up to a multiple of 8,
+    points = ceil(H * s^l) (+1 unless align_corners) -- the table geometry every RAD-NeRF checkpoint is laid out in"""
+    cap, rows, starts = 2 ** log2_hashmap_size, 0, []
+    for lvl in range(num_levels):
+        points = int(np.ceil(base_resolution * per_level_scale ** lvl)) + (0 if align_corners else 1)
+        starts.append(rows)
+        rows += 8 * math.ceil(min(cap, points ** input_dim) / 8)
+    return np.asarray(starts + [rows], dtype=np.int32)
+
+
+class GridEncodeFn(torch.autograd.Function):
+    """(x in [0,1]^D, table, offsets) -> features [B, L*C]; optional d(features)/dx for input gradients"""
+
     @staticmethod
     @custom_fwd(device_type="cuda")
-    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0,
-                align_corners=False, interpolation=0):
-        # inputs: [B, D], float in [0, 1]; embeddings: [sO, C]; offsets: [L + 1] int32.  RETURN: [B, L * C]
-        _L.require_cuda(inputs, embeddings, offsets)
-        if inputs.dtype != torch.float32:
+    def forward(ctx, x, table, offsets, per_level_scale, base_resolution, want_input_grad=False, gridtype=0, align_corners=False,
+                interpolation=0):
+        abi.require_cuda(x, table, offsets)
+        if x.dtype != torch.float32:
             raise RuntimeError("GridEncoder: inputs must be float32 (coordinates are never reduced in precision)")
-        inputs = inputs.contiguous()
-
-        B, D = inputs.shape
-        L = offsets.shape[0] - 1
-        C = embeddings.shape[1]
-        S = np.log2(per_level_scale)
-        H = base_resolution
-
-        emb_dtype_in = embeddings.dtype
-        # manual autocast handling, as the reference (grid.py:41-44): half tables only when C is even
-        if torch.is_autocast_enabled() and C % 2 == 0:
-            embeddings = embeddings.to(torch.half)
-        embeddings = embeddings.contiguous()
-        offsets = offsets.contiguous()
-
-        outputs = torch.empty(B, L * C, device=inputs.device, dtype=embeddings.dtype)
-        dy_dx = torch.empty(B, L * D * C, device=inputs.device, dtype=embeddings.dtype) if calc_grad_inputs else None
-
-        _L.check(_L.lib().rn_grid_encode_forward(
-            _L.ptr(inputs), _L.ptr(embeddings), _L.ptr(offsets), _L.ptr(outputs), B, D, C, L, float(S), H,
-            _L.ptr(dy_dx), gridtype, int(bool(align_corners)), interpolation, _dtype_id(embeddings), _LAYOUT_BLC,
-            _L.cur_stream()))
-
-        ctx.save_for_backward(inputs, embeddings, offsets, dy_dx)
-        ctx.dims = [B, D, C, L, S, H, gridtype, interpolation]
-        ctx.align_corners = align_corners
-        ctx.emb_dtype_in = emb_dtype_in
-        return outputs
+        param_dtype = table.dtype
+        if torch.is_autocast_enabled() and table.shape[1] % 2 == 0:   # the reference's own autocast rule (grid.py:41-44)
+            table = table.half()
+        x, table, offsets = x.contiguous(), table.contiguous(), offsets.contiguous()
+        n, dim = x.shape
+        levels, feats = offsets.numel() - 1, table.shape[1]
+        log2_scale = float(np.log2(per_level_scale))
+        y = table.new_empty(n, levels * feats)
+        jac = table.new_empty(n, levels * dim * feats) if want_input_grad else None
+        abi.call("rn_grid_encode_forward", x, table, offsets, y, n, dim, feats, levels, log2_scale, base_resolution, jac, gridtype,
+                 int(bool(align_corners)), interpolation, _table_dtype_id(table), ROWS_BLC)
+        ctx.save_for_backward(x, table, offsets, jac)
+        ctx.geometry = (log2_scale, base_resolution, gridtype, int(bool(align_corners)), interpolation, param_dtype)
+        return y
 
     @staticmethod
     @custom_bwd(device_type="cuda")
-    def backward(ctx, grad):
-        inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
-        B, D, C, L, S, H, gridtype, interpolation = ctx.dims
-        align_corners = ctx.align_corners
-
-        grad = grad.contiguous()  # [B, L*C], consumed in place of the reference's [L,B,C] permuted copy
-        if grad.dtype != embeddings.dtype:
-            grad = grad.to(embeddings.dtype)
-
-        # fp32 accumulation target for the scatter-add, whatever the table dtype
-        grad_embeddings = torch.zeros(embeddings.shape, device=embeddings.device, dtype=torch.float32)
-        grad_inputs = torch.empty_like(inputs, dtype=embeddings.dtype) if dy_dx is not None else None
-
-        _L.check(_L.lib().rn_grid_encode_backward(
-            _L.ptr(grad), _L.ptr(inputs), _L.ptr(embeddings), _L.ptr(offsets), _L.ptr(grad_embeddings), B, D, C, L,
-            float(S), H, _L.ptr(dy_dx), _L.ptr(grad_inputs), gridtype, int(bool(align_corners)), interpolation,
-            _dtype_id(embeddings), _LAYOUT_BLC, _RN_F32, _L.cur_stream()))
-
-        if dy_dx is not None:
-            grad_inputs = grad_inputs.to(inputs.dtype)
-        if grad_embeddings.dtype != ctx.emb_dtype_in:
-            grad_embeddings = grad_embeddings.to(ctx.emb_dtype_in)
-        return grad_inputs, grad_embeddings, None, None, None, None, None, None, None
+    def backward(ctx, dy):
+        x, table, offsets, jac = ctx.saved_tensors
+        log2_scale, base_resolution, gridtype, align, interpolation, param_dtype = ctx.geometry
+        n, dim = x.shape
+        levels, feats = offsets.numel() - 1, table.shape[1]
+        dy = dy.contiguous().to(table.dtype)
+        dtable = torch.zeros(table.shape, device=table.device, dtype=torch.float32)     # fp32 scatter target
+        dx = torch.empty_like(x, dtype=table.dtype) if jac is not None else None
+        abi.call("rn_grid_encode_backward", dy, x, table, offsets, dtable, n, dim, feats, levels, log2_scale, base_resolution, jac, dx,
+                 gridtype, align, interpolation, _table_dtype_id(table), ROWS_BLC, F32)
+        return (None if dx is None else dx.to(x.dtype)), dtable.to(param_dtype), None, None, None, None, None, None, None
 
 
-grid_encode = _grid_encode.apply
+grid_encode = GridEncodeFn.apply
 
 
 class GridEncoder(nn.Module):
-    def __init__(self, input_dim=3, num_levels=16, level_dim=2, per_level_scale=2, base_resolution=16,
-                 log2_hashmap_size=19, desired_resolution=None, gridtype='hash', align_corners=False,
-                 interpolation='linear'):
+    def __init__(self, input_dim=3, num_levels=16, level_dim=2, per_level_scale=2, base_resolution=16, log2_hashmap_size=19,
+                 desired_resolution=None, gridtype='hash', align_corners=False, interpolation='linear'):
         super().__init__()
-
-        # the finest resolution desired at the last level, if provided, overrides per_level_scale
-        if desired_resolution is not None:
+        if desired_resolution is not None:   # finest resolution given: derive the geometric growth factor from it
             per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1))
-
-        self.input_dim = input_dim
-        self.num_levels = num_levels
-        self.level_dim = level_dim
-        self.per_level_scale = per_level_scale
-        self.log2_hashmap_size = log2_hashmap_size
-        self.base_resolution = base_resolution
+        self.input_dim, self.num_levels, self.level_dim = input_dim, num_levels, level_dim
+        self.per_level_scale, self.base_resolution, self.log2_hashmap_size = per_level_scale, base_resolution, log2_hashmap_size
         self.output_dim = num_levels * level_dim
-        self.gridtype = gridtype
-        self.gridtype_id = _gridtype_to_id[gridtype]
-        self.interpolation = interpolation
-        self.interp_id = _interp_to_id[interpolation]
+        self.gridtype, self.gridtype_id = gridtype, GRID_TYPES[gridtype]
+        self.interpolation, self.interp_id = interpolation, INTERPOLATIONS[interpolation]
         self.align_corners = align_corners
-
-        # level table: rows per level capped at 2^log2_hashmap_size and rounded up to a multiple of 8 (grid.py:118-127)
-        offsets = []
-        offset = 0
         self.max_params = 2 ** log2_hashmap_size
-        for i in range(num_levels):
-            resolution = int(np.ceil(base_resolution * per_level_scale ** i))
-            params_in_level = min(self.max_params, (resolution if align_corners else resolution + 1) ** input_dim)
-            params_in_level = int(np.ceil(params_in_level / 8) * 8)
-            offsets.append(offset)
-            offset += params_in_level
-        offsets.append(offset)
-        offsets = torch.from_numpy(np.array(offsets, dtype=np.int32))
+        offsets = torch.from_numpy(level_offsets(input_dim, num_levels, level_dim, per_level_scale, base_resolution,
+                                                 log2_hashmap_size, align_corners))
         self.register_buffer('offsets', offsets)
-
         self.n_params = offsets[-1] * level_dim
-
-        self.embeddings = nn.Parameter(torch.empty(offset, level_dim))
-
+        self.embeddings = nn.Parameter(torch.empty(int(offsets[-1]), level_dim))
         self.reset_parameters()
 
     def reset_parameters(self):
-        std = 1e-4
-        self.embeddings.data.uniform_(-std, std)
+        nn.init.uniform_(self.embeddings, -1e-4, 1e-4)
 
     def __repr__(self):
-        return f"GridEncoder: input_dim={self.input_dim} num_levels={self.num_levels} level_dim={self.level_dim} resolution={self.base_resolution} -> {int(round(self.base_resolution * self.per_level_scale ** (self.num_levels - 1)))} per_level_scale={self.per_level_scale:.4f} params={tuple(self.embeddings.shape)} gridtype={self.gridtype} align_corners={self.align_corners} interpolation={self.interpolation}"
+        finest = int(round(self.base_resolution * self.per_level_scale ** (self.num_levels - 1)))
+        return (f"GridEncoder: input_dim={self.input_dim} num_levels={self.num_levels} level_dim={self.level_dim} "
+                f"resolution={self.base_resolution} -> {finest} per_level_scale={self.per_level_scale:.4f} "
+                f"params={tuple(self.embeddings.shape)} gridtype={self.gridtype} align_corners={self.align_corners} "
+                f"interpolation={self.interpolation}")
 
     def forward(self, inputs, bound=1):
-        # inputs: [..., input_dim], normalized real world positions in [-bound, bound]
-        # return: [..., num_levels * level_dim]
-        inputs = (inputs + bound) / (2 * bound)  # map to [0, 1]
+        unit = ((inputs + bound) / (2 * bound)).view(-1, self.input_dim)     # [-bound, bound] -> [0, 1]
+        feats = grid_encode(unit, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution, unit.requires_grad,
+                            self.gridtype_id, self.align_corners, self.interp_id)
+        return feats.view(*inputs.shape[:-1], self.output_dim)
 
-        prefix_shape = list(inputs.shape[:-1])
-        inputs = inputs.view(-1, self.input_dim)
-
-        outputs = grid_encode(inputs, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
-                              inputs.requires_grad, self.gridtype_id, self.align_corners, self.interp_id)
-        outputs = outputs.view(prefix_shape + [self.output_dim])
-        return outputs
-
-    # always run in float precision!
-    @torch.autocast(device_type="cuda", enabled=False)
+    @torch.autocast(device_type="cuda", enabled=False)   # total variation is always evaluated in fp32
     def grad_total_variation(self, weight=1e-7, inputs=None, bound=1, B=1000000):
-        # inputs: [..., input_dim], float in [-b, b], location to calculate TV loss.
-        D = self.input_dim
-        C = self.embeddings.shape[1]
-        L = self.offsets.shape[0] - 1
-        S = np.log2(self.per_level_scale)
-        H = self.base_resolution
-
-        if inputs is None:
-            inputs = torch.rand(B, self.input_dim, device=self.embeddings.device)
-        else:
-            inputs = (inputs + bound) / (2 * bound)
-            inputs = inputs.view(-1, self.input_dim)
-            B = inputs.shape[0]
-
+        """adds weight * d(TV)/d(table) at `inputs` (or B random points) INTO embeddings.grad -- call between backward() and step()"""
         if self.embeddings.grad is None:
             raise ValueError('grad is None, should be called after loss.backward() and before optimizer.step()!')
-
-        inputs = inputs.to(self.embeddings.dtype).contiguous()
-        _L.check(_L.lib().rn_grad_total_variation(
-            _L.ptr(inputs), _L.ptr(self.embeddings), _L.ptr(self.embeddings.grad), _L.ptr(self.offsets), float(weight),
-            B, D, C, L, float(S), H, self.gridtype_id, int(bool(self.align_corners)), _dtype_id(self.embeddings),
-            _L.cur_stream()))
+        if inputs is None:
+            pts = torch.rand(B, self.input_dim, device=self.embeddings.device)
+        else:
+            pts = ((inputs + bound) / (2 * bound)).view(-1, self.input_dim)
+        pts = pts.to(self.embeddings.dtype).contiguous()
+        abi.call("rn_grad_total_variation", pts, self.embeddings, self.embeddings.grad, self.offsets, float(weight), pts.shape[0],
+                 self.input_dim, self.embeddings.shape[1], self.offsets.numel() - 1, float(np.log2(self.per_level_scale)),
+                 self.base_resolution, self.gridtype_id, int(bool(self.align_corners)), _table_dtype_id(self.embeddings))

@@ -94,6 +94,23 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def call(name, *args):
+    """Invoke ABI function `name` on torch's current stream: tensors become device pointers (None -> NULL), scalars pass
+    through, the stream is appended, a non-zero return code raises RuntimeError with the library's message."""
+    fn = getattr(lib(), name)
+    check(fn(*[ptr(a) if (a is None or torch.is_tensor(a)) else a for a in args], cur_stream()), name)
+
+
+def rows(t, width=None, dtype=torch.float32):
+    """[..., width] tensor -> (contiguous 2-D `dtype` view on the device, leading shape); the library has no CPU path"""
+    require_cuda(t)
+    lead = tuple(t.shape[:-1])
+    flat = t.reshape(-1, t.shape[-1] if width is None else width)
+    if dtype is not None and flat.dtype != dtype:
+        flat = flat.to(dtype)
+    return flat.contiguous(), lead
+
+
 def launch_count():
     return int(lib().rn_launch_count())
 

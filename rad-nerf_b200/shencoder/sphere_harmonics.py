@@ -1,65 +1,55 @@
-"""SHEncoder -- real spherical-harmonics direction encoding on libradnerf_b200.  Drop-in for
-/root/reference/shencoder/sphere_harmonics.py (same class/attributes and `_sh_encoder` autograd contract)."""
+"""Real spherical-harmonics direction encoding on libradnerf_b200.
+
+Public surface of the reference's shencoder/sphere_harmonics.py: `SHEncoder(input_dim=3, degree=4)` (degree 1..8,
+`output_dim = degree^2`), `forward(inputs, size=1)` which scales directions by 1/size first, and the functional
+`sh_encode(x, degree, need_input_grad)`.  fp32 regardless of autocast; the Jacobian is only materialised when the caller
+asks for input gradients (shencoder.cu:27-438)."""
 import torch
-import torch.nn as nn
-from torch.autograd import Function
+from torch import nn
 from torch.amp import custom_bwd, custom_fwd
 
-from radnerf_b200 import abi as _L
+from radnerf_b200 import abi
 
 
-class _sh_encoder(Function):
+class SHEncodeFn(torch.autograd.Function):
     @staticmethod
-    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)  # force float32 for better precision
-    def forward(ctx, inputs, degree, calc_grad_inputs=False):
-        # inputs: [B, input_dim], float in [-1, 1] -> [B, degree^2]
-        _L.require_cuda(inputs)
-        inputs = inputs.contiguous()
-        B, input_dim = inputs.shape
-        output_dim = degree ** 2
-        outputs = torch.empty(B, output_dim, dtype=inputs.dtype, device=inputs.device)
-        dy_dx = torch.empty(B, input_dim * output_dim, dtype=inputs.dtype, device=inputs.device) if calc_grad_inputs else None
-        _L.check(_L.lib().rn_sh_encode_forward(_L.ptr(inputs), _L.ptr(outputs), B, input_dim, degree, _L.ptr(dy_dx),
-                                               _L.cur_stream()))
-        ctx.save_for_backward(inputs, dy_dx)
-        ctx.dims = [B, input_dim, degree]
-        return outputs
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, dirs, degree, need_input_grad=False):
+        dirs, _ = abi.rows(dirs)
+        n, d = dirs.shape
+        y = dirs.new_empty(n, degree * degree)
+        jac = dirs.new_empty(n, d * degree * degree) if need_input_grad else None
+        abi.call("rn_sh_encode_forward", dirs, y, n, d, degree, jac)
+        ctx.save_for_backward(dirs, jac)
+        ctx.degree = degree
+        return y
 
     @staticmethod
     @custom_bwd(device_type="cuda")
-    def backward(ctx, grad):
-        inputs, dy_dx = ctx.saved_tensors
-        if dy_dx is not None:
-            grad = grad.contiguous()
-            B, input_dim, degree = ctx.dims
-            grad_inputs = torch.zeros_like(inputs)
-            _L.check(_L.lib().rn_sh_encode_backward(_L.ptr(grad), _L.ptr(inputs), B, input_dim, degree, _L.ptr(dy_dx),
-                                                    _L.ptr(grad_inputs), _L.cur_stream()))
-            return grad_inputs, None, None
-        else:
+    def backward(ctx, dy):
+        dirs, jac = ctx.saved_tensors
+        if jac is None:
             return None, None, None
+        ddirs = torch.zeros_like(dirs)
+        abi.call("rn_sh_encode_backward", dy.contiguous(), dirs, dirs.shape[0], dirs.shape[1], ctx.degree, jac, ddirs)
+        return ddirs, None, None
 
 
-sh_encode = _sh_encoder.apply
+sh_encode = SHEncodeFn.apply
 
 
 class SHEncoder(nn.Module):
     def __init__(self, input_dim=3, degree=4):
         super().__init__()
-        self.input_dim = input_dim  # coord dims, must be 3
-        self.degree = degree  # 1 ~ 8
-        self.output_dim = degree ** 2
-        assert self.input_dim == 3, "SH encoder only support input dim == 3"
-        assert self.degree > 0 and self.degree <= 8, "SH encoder only supports degree in [1, 8]"
+        if input_dim != 3:
+            raise AssertionError("SH encoder only support input dim == 3")
+        if not 1 <= degree <= 8:
+            raise AssertionError("SH encoder only supports degree in [1, 8]")
+        self.input_dim, self.degree, self.output_dim = input_dim, degree, degree * degree
 
     def __repr__(self):
         return f"SHEncoder: input_dim={self.input_dim} degree={self.degree}"
 
     def forward(self, inputs, size=1):
-        # inputs: [..., input_dim], normalized real world positions in [-size, size] -> [..., degree^2]
-        inputs = inputs / size  # [-1, 1]
-        prefix_shape = list(inputs.shape[:-1])
-        inputs = inputs.reshape(-1, self.input_dim)
-        outputs = sh_encode(inputs, self.degree, inputs.requires_grad)
-        outputs = outputs.reshape(prefix_shape + [self.output_dim])
-        return outputs
+        unit = (inputs / size).reshape(-1, self.input_dim)
+        return sh_encode(unit, self.degree, unit.requires_grad).view(*inputs.shape[:-1], self.output_dim)
