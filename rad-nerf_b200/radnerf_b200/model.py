@@ -17,7 +17,7 @@ uses that as the reference-CUDA comparison arm.
 """
 import math
 import random
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 import torch
