@@ -296,6 +296,34 @@ int rn_stream_wait_event(void* stream, void* ev);
 /* sizeof() of a public descriptor struct by name ("rn_lane_submit", ...), 0 if unknown: lets a binding check its mirror */
 uint32_t rn_sizeof(const char* name);
 
+/* ------------------------------------------------------------------ training-step tail -------------- */
+
+/* One sweep over every trainable tensor for what the reference ends a training step with (nerf/utils.py:1171-1182):
+ * `scaler.step(optimizer)` on torch.optim.Adam (main.py:204; groups from NeRFNetwork.get_params, nerf/network.py:329-361)
+ * [+ `optimizer.zero_grad()` of the next step, :1164] and `ema.update()` (torch_ema, :1181-1182).
+ * A tensor is cut into chunks of RN_ADAM_CHUNK elements; `first_chunk` of tensor t = sum of ceil(n / RN_ADAM_CHUNK) of the
+ * tensors before it, n_chunks = the total.  The descriptor array lives in DEVICE memory, the group table in HOST memory
+ * (it changes every step with the learning-rate schedule and travels as a kernel argument). */
+#define RN_ADAM_CHUNK 4096u
+#define RN_ADAM_MAX_GROUPS 32u
+#define RN_ADAM_ZERO_GRADS 1u      /* flags bit 0: leave every gradient zeroed (the next step's zero_grad) */
+typedef struct rn_adam_tensor {
+    float* param; float* grad; float* exp_avg; float* exp_avg_sq;   /* [n] fp32 each */
+    float* step;                 /* device scalar: optimiser steps this tensor has taken (torch keeps state['step'] the same way
+                                    for its fused/capturable Adam); advanced by rn_adam_step unless the step is skipped */
+    float* ema;                  /* rn_ema_update only: the shadow copy */
+    uint64_t n;
+    uint32_t first_chunk, group;
+} rn_adam_tensor;
+typedef struct rn_adam_group { double lr, beta1, beta2, eps, weight_decay; } rn_adam_group;
+/* grad_scale / found_inf: nullable device scalars with torch.amp.GradScaler's meaning (gradients are divided by
+ * *grad_scale; *found_inf != 0 skips the whole step -- parameters, moments and step counters untouched, gradients still
+ * zeroed when asked).  Arithmetic: torch/optim/adam.py `_single_tensor_adam` (amsgrad / maximize off), fp32. */
+int rn_adam_step(const rn_adam_tensor* tensors, uint32_t n_tensors, uint32_t n_chunks, const rn_adam_group* groups,
+                 uint32_t n_groups, const float* grad_scale, const float* found_inf, uint32_t flags, void* stream);
+/* shadow -= (1 - decay) * (shadow - param) for every tensor (param, ema, n, first_chunk of the descriptors are used) */
+int rn_ema_update(const rn_adam_tensor* tensors, uint32_t n_tensors, uint32_t n_chunks, double decay, void* stream);
+
 /* diagnostics (tools/, not part of the operator contract) */
 void rn_debug_set_audio_prof(void* stamps);
 void rn_debug_set_max_iters(uint32_t n);

@@ -313,3 +313,18 @@ def sh_encode_backward(grad, dy_dx, D, degree):
     gi = np.zeros((B, D), np.float32)
     lib().o_sh_encode_backward(_p(grad), u32(B), u32(D), u32(degree), _p(dy_dx), _p(gi))
     return gi
+
+
+def adam_step(p, g, m, v, lr, betas, eps, weight_decay, step, inv_scale=1.0):
+    """one torch.optim.Adam step on flat fp32 arrays, IN PLACE on p, m, v (step is 1-based); see oracle.c o_adam_step"""
+    for a in (p, m, v):
+        assert a.dtype == np.float32 and a.flags.c_contiguous
+    g = _f32(g)
+    lib().o_adam_step(_p(p), _p(g), _p(m), _p(v), C.c_uint64(p.size), C.c_double(lr), C.c_double(betas[0]),
+                      C.c_double(betas[1]), C.c_double(eps), C.c_double(weight_decay), C.c_double(step), C.c_float(inv_scale))
+
+
+def ema_update(shadow, p, decay):
+    """torch_ema update IN PLACE on shadow"""
+    assert shadow.dtype == np.float32 and shadow.flags.c_contiguous
+    lib().o_ema_update(_p(shadow), _p(_f32(p)), C.c_uint64(shadow.size), C.c_double(decay))

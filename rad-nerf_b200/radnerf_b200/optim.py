@@ -1,0 +1,239 @@
+"""Training-step tail on the device: `FusedAdam` and `ParamEMA`.
+
+The reference ends a step with `scaler.step(optimizer); scaler.update(); ...; ema.update()` (nerf/utils.py:1171-1182) on
+`torch.optim.Adam(model.get_params(lr, lr_net), betas=(0.9, 0.99), eps=1e-15)` (main.py:204) and
+`torch_ema.ExponentialMovingAverage(model.parameters(), decay=0.95)` (nerf/utils.py:641).  Both classes here keep those
+constructors, `param_groups` / `state` / `state_dict()` layouts and call sequences -- `torch.amp.GradScaler`,
+`LambdaLR` and the reference's checkpoint code work on them unchanged -- and do the arithmetic in ONE launch of
+csrc/optim_tail.cu over every tensor (rn_adam_step / rn_ema_update) instead of ~10 foreach sweeps plus a host sync.
+
+GradScaler contract: `_step_supports_amp_scaling = True`, so `scaler.step(opt)` hands over `opt.grad_scale` /
+`opt.found_inf` as device scalars (torch/amp/grad_scaler.py, the fused-optimizer protocol) and never calls `.item()`;
+the kernel divides by the scale and skips the step on the device.  Step counters are device scalars
+(`state[p]['step']`, like torch's own fused Adam).  There is no CPU path: parameters must live on a CUDA device.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+
+CHUNK = 4096           # RN_ADAM_CHUNK
+MAX_GROUPS = 32        # RN_ADAM_MAX_GROUPS
+
+
+class AdamTensor(C.Structure):      # rn_adam_tensor
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("step", C.c_void_p), ("ema", C.c_void_p), ("n", C.c_uint64), ("first_chunk", C.c_uint32), ("group", C.c_uint32)]
+
+
+class AdamGroup(C.Structure):       # rn_adam_group
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double)]
+
+
+abi.register("rn_adam_step", [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(AdamGroup), C.c_uint32, C.c_void_p, C.c_void_p,
+                              C.c_uint32, C.c_void_p])
+abi.register("rn_ema_update", [C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_void_p])
+
+
+def chunk_layout(sizes):
+    """first chunk of every tensor and the total, for tensors of `sizes` elements cut into CHUNK-element pieces"""
+    first, total = [], 0
+    for n in sizes:
+        first.append(total)
+        total += (int(n) + CHUNK - 1) // CHUNK
+    return first, total
+
+
+def _descriptor_table(rows, device):
+    """rows: list of dict(param=, grad=, exp_avg=, exp_avg_sq=, step=, ema=, n=, group=) of data pointers -> device blob"""
+    first, total = chunk_layout([r["n"] for r in rows])
+    arr = (AdamTensor * len(rows))()
+    for d, r, f in zip(arr, rows, first):
+        for k in ("param", "grad", "exp_avg", "exp_avg_sq", "step", "ema"):
+            setattr(d, k, r.get(k) or 0)
+        d.n, d.first_chunk, d.group = r["n"], f, r.get("group", 0)
+    blob = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(device)
+    return blob, total
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam (amsgrad / maximize off) over fp32 CUDA parameters in one kernel launch per step.
+
+    zero_grads=True additionally leaves every gradient zeroed by the same sweep, so the `optimizer.zero_grad()` that opens
+    the next step (nerf/utils.py:1164) has nothing left to do (it is then skipped, gradients stay allocated)."""
+    _step_supports_amp_scaling = True
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, zero_grads=False):
+        if not 0.0 <= lr:
+            raise ValueError(f"Invalid learning rate: {lr}")
+        if not 0.0 <= eps:
+            raise ValueError(f"Invalid epsilon value: {eps}")
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError(f"Invalid beta parameter at index 0: {betas[0]}")
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError(f"Invalid beta parameter at index 1: {betas[1]}")
+        if not 0.0 <= weight_decay:
+            raise ValueError(f"Invalid weight_decay value: {weight_decay}")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        if len(self.param_groups) > MAX_GROUPS:
+            raise ValueError(f"FusedAdam supports at most {MAX_GROUPS} parameter groups")
+        self.zero_grads = bool(zero_grads)
+        self._key = None            # data pointers the device descriptor table was built for
+        self._table = None
+        self._n_tensors = self._n_chunks = 0
+        self._grads_are_zero = False
+        if self.zero_grads:         # any gradient written by a backward pass invalidates "the sweep left them zeroed"
+            for group in self.param_groups:
+                for p in group["params"]:
+                    p.register_post_accumulate_grad_hook(self._on_grad)
+
+    def _on_grad(self, _p):
+        self._grads_are_zero = False
+
+    # ---- state -------------------------------------------------------------------------------------------------------
+    def _init_state(self, p):
+        st = self.state[p]
+        if len(st) == 0:
+            abi.require_cuda(p)
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("FusedAdam: parameters must be contiguous fp32 tensors")
+            st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        return st
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        for p, st in self.state.items():      # a checkpoint written by torch.optim.Adam keeps `step` on the host
+            if "step" in st:
+                st["step"] = torch.as_tensor(st["step"], dtype=torch.float32).to(p.device).reshape(())
+            for k in ("exp_avg", "exp_avg_sq"):
+                if k in st:
+                    st[k] = st[k].to(p.device, torch.float32).contiguous()
+        self._key = None
+
+    def zero_grad(self, set_to_none=False):
+        """the sweep of the previous step() already zeroed the gradients when zero_grads is on"""
+        if self.zero_grads and self._grads_are_zero and not set_to_none:
+            return
+        super().zero_grad(set_to_none=set_to_none)
+
+    # ---- step --------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        rows, device = [], None
+        for gi, group in enumerate(self.param_groups):
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                g = p.grad
+                if g.is_sparse or g.dtype != torch.float32 or not g.is_contiguous():
+                    raise RuntimeError("FusedAdam: gradients must be dense contiguous fp32 tensors")
+                st = self._init_state(p)
+                device = p.device
+                rows.append(dict(param=p.data_ptr(), grad=g.data_ptr(), exp_avg=st["exp_avg"].data_ptr(),
+                                 exp_avg_sq=st["exp_avg_sq"].data_ptr(), step=st["step"].data_ptr(), n=p.numel(), group=gi))
+        if not rows:
+            return loss
+        key = tuple((r["param"], r["grad"], r["exp_avg"], r["exp_avg_sq"], r["step"], r["group"]) for r in rows)
+        if key != self._key:        # first step, or a gradient / state tensor was re-allocated: one small H2D copy
+            self._table, self._n_chunks = _descriptor_table(rows, device)
+            self._n_tensors, self._key = len(rows), key
+        groups = (AdamGroup * len(self.param_groups))()
+        for d, group in zip(groups, self.param_groups):
+            d.lr, d.beta1, d.beta2 = float(group["lr"]), float(group["betas"][0]), float(group["betas"][1])
+            d.eps, d.weight_decay = float(group["eps"]), float(group["weight_decay"])
+        scale = getattr(self, "grad_scale", None)
+        found = getattr(self, "found_inf", None)
+        with torch.cuda.device(device):
+            fn = abi.lib().rn_adam_step
+            abi.check(fn(abi.ptr(self._table), self._n_tensors, self._n_chunks, groups, len(self.param_groups),
+                         abi.ptr(_scalar_f32(scale, device)), abi.ptr(_scalar_f32(found, device)), 1 if self.zero_grads else 0,
+                         abi.cur_stream()), "rn_adam_step")
+        self._grads_are_zero = self.zero_grads
+        return loss
+
+
+def _scalar_f32(t, device):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or t.device != device:
+        t = t.to(device=device, dtype=torch.float32)
+    return t.reshape(-1)[:1].contiguous()
+
+
+class ParamEMA:
+    """torch_ema.ExponentialMovingAverage (the subset the reference's Trainer uses: update / store / copy_to / restore /
+    state_dict / load_state_dict; nerf/utils.py:641, 1069-1080, 1181-1182, 1322-1389), one launch per update."""
+
+    def __init__(self, parameters, decay, use_num_updates=True):
+        if decay < 0.0 or decay > 1.0:
+            raise ValueError("Decay must be between 0 and 1")
+        self.decay = decay
+        self.num_updates = 0 if use_num_updates else None
+        self.params = [p for p in parameters if p.requires_grad]
+        for p in self.params:
+            abi.require_cuda(p)
+        self.shadow_params = [p.clone().detach() for p in self.params]
+        self.collected_params = None
+        self._table = None
+        self._key = None
+
+    def _build(self):
+        key = tuple((p.data_ptr(), s.data_ptr()) for p, s in zip(self.params, self.shadow_params))
+        if key != self._key:
+            rows = [dict(param=p.data_ptr(), ema=s.data_ptr(), n=p.numel()) for p, s in zip(self.params, self.shadow_params)]
+            self._table, self._n_chunks = _descriptor_table(rows, self.params[0].device)
+            self._key = key
+
+    def current_decay(self):
+        """torch_ema: decay = min(decay, (1 + num_updates) / (10 + num_updates)) after counting this update"""
+        if self.num_updates is None:
+            return self.decay
+        return min(self.decay, (1 + self.num_updates) / (10 + self.num_updates))
+
+    @torch.no_grad()
+    def update(self):
+        if not self.params:
+            return
+        if self.num_updates is not None:
+            self.num_updates += 1
+        for p in self.params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("ParamEMA: parameters must be contiguous fp32 tensors")
+        self._build()
+        with torch.cuda.device(self.params[0].device):
+            abi.check(abi.lib().rn_ema_update(abi.ptr(self._table), len(self.params), self._n_chunks, float(self.current_decay()),
+                                              abi.cur_stream()), "rn_ema_update")
+
+    @torch.no_grad()
+    def copy_to(self):
+        for s, p in zip(self.shadow_params, self.params):
+            p.copy_(s)
+
+    def store(self):
+        self.collected_params = [p.clone() for p in self.params]
+
+    @torch.no_grad()
+    def restore(self):
+        if self.collected_params is None:
+            raise RuntimeError("This ExponentialMovingAverage has no `store()`ed weights to `restore()`")
+        for c, p in zip(self.collected_params, self.params):
+            p.copy_(c)
+
+    def state_dict(self):
+        return {"decay": self.decay, "num_updates": self.num_updates, "shadow_params": self.shadow_params,
+                "collected_params": self.collected_params}
+
+    def load_state_dict(self, state):
+        self.decay, self.num_updates = state["decay"], state["num_updates"]
+        self.shadow_params = [s.to(p.device, torch.float32).contiguous() for s, p in zip(state["shadow_params"], self.params)]
+        cp = state.get("collected_params")
+        self.collected_params = None if cp is None else [c.to(p.device) for c, p in zip(cp, self.params)]
+        self._key = None

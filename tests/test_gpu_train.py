@@ -25,21 +25,34 @@ def _head_model(seed=0):
     return model.to(DEV)
 
 
-def test_training_step_has_finite_gradients_everywhere_and_learns():
+@pytest.mark.parametrize("tail", ["torch", "fused"])
+def test_training_step_has_finite_gradients_everywhere_and_learns(tail):
+    """tail: torch.optim.Adam as main.py:204 builds it, or the one-sweep FusedAdam (radnerf_b200.optim) in its place"""
     from radnerf_b200 import synthetic as syn
+    from radnerf_b200.optim import FusedAdam
     from radnerf_b200.train import train_step
     model = _head_model()
     batch = syn.batch_to(syn.training_batch(128, 128, 4096, frame_index=3), DEV)
-    opt = torch.optim.Adam(model.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15)
+    if tail == "torch":
+        opt = torch.optim.Adam(model.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15)
+    else:
+        opt = FusedAdam(model.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15, zero_grads=True)
     scaler = torch.amp.GradScaler("cuda")
+    names = ("encoder.embeddings", "encoder_ambient.embeddings", "sigma_net.net.0.weight", "color_net.net.1.weight",
+             "ambient_net.net.0.weight", "audio_net.encoder_conv.0.weight", "audio_att_net.attentionNet.0.weight",
+             "individual_codes")
+    before = {n: dict(model.named_parameters())[n].detach().clone() for n in names}
     losses = [float(train_step(model, batch, opt, scaler, lambda_amb=0.1))]
     assert np.isfinite(losses[0])
     # one step touched every trainable group: tables (sparse rows), MLPs, audio nets, the indexed individual code
-    for name in ("encoder.embeddings", "encoder_ambient.embeddings", "sigma_net.net.0.weight", "color_net.net.1.weight",
-                 "ambient_net.net.0.weight", "audio_net.encoder_conv.0.weight", "audio_att_net.attentionNet.0.weight",
-                 "individual_codes"):
-        g = dict(model.named_parameters())[name].grad
-        assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0, name
+    for name in names:
+        p = dict(model.named_parameters())[name]
+        assert p.grad is not None and torch.isfinite(p.grad).all() and torch.isfinite(p).all(), name
+        assert not torch.equal(p.detach(), before[name]), name          # the optimiser moved it
+        if tail == "torch":
+            assert p.grad.abs().sum() > 0, name
+        else:
+            assert not p.grad.any(), name                                # the sweep left the gradient zeroed for the next step
     counter = model.step_counter[(model.local_step - 1) % 16]
     assert 0 < int(counter[0]) <= 16 * 4096 and 0 < int(counter[1]) <= 4096     # samples / rays the marcher emitted (raymarching.cu:448-452)
     for _ in range(40):
