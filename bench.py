@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--hw", type=int, default=HW)
     ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU (fused path; 1 = strictly one frame at a time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE configs[3]) of the N=1 line")
     ap.add_argument("--no-ref-cuda", action="store_true")
     return ap.parse_args()
 
@@ -192,6 +193,11 @@ def run_reference_arm(args):
             import torch
             if torch.cuda.is_available():
                 line["ref_cuda"] = ref_cuda_frame_rate(torch.device("cuda", 0), args.hw, 30)
+                if not args.no_train:
+                    from oracle import ref_backend
+                    line["ref_cuda_train"] = training_rate(torch.device("cuda", 0), ops=ref_backend.RefOps(train=True), tail="torch")
+                    line["ref_cuda_train"]["what"] = ("the same training loop on the reference's CUDA extensions (oracle/_ref) in the "
+                                                      "reference's op order, torch.optim.Adam + GradScaler as main.py / nerf/utils.py run them")
         except Exception as e:  # noqa: BLE001
             line["ref_cuda"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line))
@@ -430,9 +436,74 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": fps_cpu, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "1 full %dx%d head+torso frame on the CPU port (oracle C kernels, OpenMP, + torch-CPU "
                                               "MLPs, fp32), %d sample slots" % (hw, hw, nsamp)}
+        if world == 1 and not args.no_train:
+            try:
+                line["train"] = training_rate(dev)
+            except Exception as e:  # noqa: BLE001  (context next to the headline, never the reason the line is missing)
+                line["train"] = {"unavailable": repr(e)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def training_rate(dev, n_rays=65536, steps=48, ops=None, tail="fused", graphed=False):
+    """BASELINE configs[3] on one GPU, steady state: head training step on 2^16 rays (march_rays_train -> encoders + MLPs ->
+    composite_rays_train, backward, GradScaler, FusedAdam one-sweep tail), occupancy-grid update every 16 steps inside the
+    timed region (nerf/utils.py:1153-1182).  The first 16 steps (unknown mean_count: worst-case buffers + a host read per
+    step, raymarching.py:213-256) and the first grid update are warm-up, as in any run longer than 16 steps."""
+    import torch
+    from radnerf_b200 import synthetic as syn
+    from radnerf_b200.model import NeRFNetwork, Options
+    from radnerf_b200.optim import FusedAdam
+    from radnerf_b200.train import GraphedTrainStep, train_step
+    torch.manual_seed(0)
+    m = NeRFNetwork(Options(torso=False, fp16=True, exp_eye=True), ops=ops)
+    grid = syn.head_density_grid(128, semi_axes=(0.34, 0.24, 0.37))
+    m.density_grid.copy_(torch.from_numpy(grid))
+    m.mean_density = float(np.clip(grid, 0, None).mean())
+    m.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, min(m.mean_density, m.density_thresh))))
+    m = m.to(dev)
+    m.aud_features = torch.from_numpy(syn.audio_feature_bank(600, 44, 16, seed=0))     # main.py:210-212
+    m.eye_area = torch.full((600, 1), 0.25)
+    batches = [syn.batch_to(syn.training_batch(512, 512, n_rays, frame_index=i), dev) for i in range(8)]
+    if tail == "fused":
+        opt = FusedAdam(m.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15, zero_grads=True)
+    else:
+        opt = torch.optim.Adam(m.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15)      # main.py:204
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 0.1 ** (it / 200000))
+    scaler = torch.amp.GradScaler("cuda")
+    g = [0]
+    # graphed=True replays the step as one CUDA graph between grid updates (radnerf_b200.train.GraphedTrainStep).  Measured in
+    # round 1: a replay takes 10.3 ms where the op-by-op step takes 8.5 ms, and every grid update costs a 25-160 ms re-capture --
+    # the step is bound by its device work, not by launches -- so the op-by-op step is what this leg times
+    graphed = GraphedTrainStep(m, opt, scaler) if (graphed and tail == "fused") else None
+
+    def one(i):
+        if g[0] % m.opt.update_extra_interval == 0 and g[0] > 0:
+            with torch.autocast("cuda", dtype=torch.float16):
+                m.update_extra_state()
+        g[0] += 1
+        loss = graphed(batches[i % 8]) if graphed is not None else train_step(m, batches[i % 8], opt, scaler, None)
+        sched.step()
+        return loss
+    for i in range(20):
+        one(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = one(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    samples = float(m.step_counter[:, 0].float().mean())
+    how = "torch.optim.Adam, op by op" if tail != "fused" else "FusedAdam one-sweep tail, op by op"
+    if graphed is not None:
+        how = "FusedAdam tail, step replayed as a CUDA graph (%d captures, %d replays in the run%s)" % (
+            graphed.captures, graphed.replays, "" if graphed.fallback_reason is None else "; FELL BACK to op-by-op: " + graphed.fallback_reason)
+    return {"workload": "RAD-NeRF head training step (BASELINE configs[3]): %d rays/batch, fp16 autocast, grid update every 16 steps, "
+                        "%s" % (n_rays, how), "ms_per_step": ms, "rays_per_s": n_rays / ms * 1e3, "samples_per_step": samples,
+            "msamples_per_s": samples / ms / 1e3, "steps": steps, "loss": float(loss)}
 
 
 def ref_cuda_frame_rate(dev, hw, steps):

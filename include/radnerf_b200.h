@@ -307,6 +307,9 @@ uint32_t rn_sizeof(const char* name);
 #define RN_ADAM_CHUNK 4096u
 #define RN_ADAM_MAX_GROUPS 32u
 #define RN_ADAM_ZERO_GRADS 1u      /* flags bit 0: leave every gradient zeroed (the next step's zero_grad) */
+#define RN_ADAM_GROUPS_ON_DEVICE 2u /* flags bit 1: `groups` is a DEVICE table kept current with rn_adam_groups_store -- for a
+                                      step captured in a CUDA graph, whose kernel arguments are frozen while the learning
+                                      rate moves on */
 typedef struct rn_adam_tensor {
     float* param; float* grad; float* exp_avg; float* exp_avg_sq;   /* [n] fp32 each */
     float* step;                 /* device scalar: optimiser steps this tensor has taken (torch keeps state['step'] the same way
@@ -321,8 +324,25 @@ typedef struct rn_adam_group { double lr, beta1, beta2, eps, weight_decay; } rn_
  * zeroed when asked).  Arithmetic: torch/optim/adam.py `_single_tensor_adam` (amsgrad / maximize off), fp32. */
 int rn_adam_step(const rn_adam_tensor* tensors, uint32_t n_tensors, uint32_t n_chunks, const rn_adam_group* groups,
                  uint32_t n_groups, const float* grad_scale, const float* found_inf, uint32_t flags, void* stream);
+/* writes the HOST table `groups` into the device table `groups_dev` [>= n_groups] in stream order (a kernel whose argument
+ * is the table: no host memory is read after the call returns) */
+int rn_adam_groups_store(const rn_adam_group* groups, uint32_t n_groups, rn_adam_group* groups_dev, void* stream);
 /* shadow -= (1 - decay) * (shadow - param) for every tensor (param, ema, n, first_chunk of the descriptors are used) */
 int rn_ema_update(const rn_adam_tensor* tensors, uint32_t n_tensors, uint32_t n_chunks, double decay, void* stream);
+
+/* ------------------------------------------------------------------ streaming audio hand-off --------- */
+
+/* replaces ASR.get_next_feat (nerf/asr.py:160-183; consumer nerf/gui.py:186): the [RN_RING_DEPTH, dim, RN_RING_WINDOW] block
+ * of one video frame from the ASR feature ring `ring [size, dim]` (asr.py:103) in one launch.  Window k = rows
+ * (start[k] + j) mod size, j < 16; start[k] < 0 = an all-zero window (asr.py:109).  snapshot[k] >= 0: the window is a COPY
+ * held in slot snapshot[k] of `snapshots [RN_RING_DEPTH, 16, dim]` (the reference's torch.cat for a window that wraps
+ * around the ring end); fresh[k] != 0 takes that copy now.  snapshot[k] < 0: read live from the ring (the reference's
+ * slice views show later overwrites).  `out` may point anywhere, e.g. into a frame lane's input block. */
+#define RN_RING_WINDOW 16
+#define RN_RING_DEPTH 8
+typedef struct rn_ring_windows { int32_t start[RN_RING_DEPTH]; int32_t snapshot[RN_RING_DEPTH]; int32_t fresh[RN_RING_DEPTH]; } rn_ring_windows;
+int rn_feature_window(const float* ring, uint32_t size, uint32_t dim, const rn_ring_windows* windows, float* snapshots,
+                      float* out, void* stream);
 
 /* diagnostics (tools/, not part of the operator contract) */
 void rn_debug_set_audio_prof(void* stamps);

@@ -407,6 +407,120 @@ grid_backward_kernel(const T* __restrict__ grad, const float* __restrict__ input
     }
 }
 
+// Warp-aggregated variant for D == 2 -- the ambient grid.  Its input is the network's own 2-D output, tanh(ambient_net(...)),
+// a smooth function of position and audio that the ambient regulariser (nerf/utils.py:783-806) pulls towards one point: the
+// 32 samples of a warp fall into the SAME cell on the coarse levels, and so do most of the batch's other warps.  One vector
+// atomic per (lane, corner) then serialises on a handful of L2 addresses (measured: 1.77 ms for 206 k samples, 5x the 3-D
+// table's backward and a third of the whole training step).  Here the lanes of a warp that share a cell (match.any on the
+// packed cell coordinate) are summed with shuffles first and ONE lane issues the four atomics; a warp whose lanes spread over
+// more than kMaxGroups cells (fine levels, uniform inputs) keeps the per-lane atomics.  All 32 lanes stay in the loop (the
+// sample loop is uniform per CTA) so every shuffle runs with the full mask.
+constexpr int kMaxGroups = 8;
+
+template <typename T, typename G, int C>
+__global__ void __launch_bounds__(256)
+grid_backward_shared_cell_kernel(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
+                                 G* __restrict__ grad_table, const T* __restrict__ dy_dx, T* __restrict__ grad_inputs, uint32_t B,
+                                 uint32_t L, float S, uint32_t H, uint32_t gridtype, uint32_t align_corners, uint32_t interp,
+                                 uint32_t layout) {
+    constexpr int D = 2;
+    constexpr uint32_t FULL = 0xffffffffu;
+    __shared__ LevelMeta meta[MAX_LEVELS];
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x)
+        make_level_meta(meta[l], l, offsets, S, H, D, gridtype, align_corners != 0);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+
+    for (uint32_t base = blockIdx.x * blockDim.x; base < B; base += gridDim.x * blockDim.x) {
+        const uint32_t b = base + threadIdx.x;
+        const bool in_range = b < B;
+        float x[D] = {0.0f, 0.0f};
+        bool valid = in_range;
+        if (in_range) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                x[d] = __ldg(inputs + (size_t)b * D + d);
+                if (x[d] < 0 || x[d] > 1) valid = false;   // reference returns before touching the table (gridencoder.cu:275-280)
+            }
+        }
+        float gin[D] = {0.0f, 0.0f};
+
+        for (uint32_t l = 0; l < L; ++l) {
+            float gf[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) gf[c] = 0.0f;
+            if (in_range) {
+                const T* gp = (layout == RN_LAYOUT_BLC) ? grad + (size_t)b * L * C + (size_t)l * C
+                                                        : grad + ((size_t)l * B + b) * C;
+                const Row<T, C> g = load_row<T, C>(gp);
+#pragma unroll
+                for (int c = 0; c < C; ++c) gf[c] = to_f(g.v[c]);
+                if (dy_dx) {
+                    const T* dp = dy_dx + ((size_t)b * L + l) * D * C;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) gin[d] = __fmaf_rn(gf[c], to_f(__ldg(dp + d * C + c)), gin[d]);
+                    }
+                }
+            }
+            const LevelMeta m = meta[l];
+            G* __restrict__ gt = grad_table + (size_t)m.offset * C;
+            Cell<D> cell = {};
+            uint32_t key = FULL;                            // never a real cell: coordinates stay below 2^16
+            if (valid) {
+                cell = locate<D>(x, m, align_corners != 0, interp);
+                key = cell.pg[0] | (cell.pg[1] << 16);
+            }
+            const uint32_t peers = __match_any_sync(FULL, key);
+            const bool leader = valid && lane == (uint32_t)(__ffs(peers) - 1);
+            uint32_t leaders = __ballot_sync(FULL, leader);
+            const uint32_t n_valid = __popc(__ballot_sync(FULL, valid));
+            const uint32_t n_groups = __popc(leaders);
+            if (n_groups <= kMaxGroups && n_groups < n_valid) {     // warp-uniform: few cells, at least one shared
+                while (leaders) {
+                    const int src = __ffs(leaders) - 1;
+                    leaders &= leaders - 1;
+                    const uint32_t group_key = __shfl_sync(FULL, key, src);   // outside the `&&`: every lane must execute the shuffle
+                    const bool mine = valid && key == group_key;
+                    float v[4][C];
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k) {
+                        const float w = mine ? corner_weight<D>(cell, k) : 0.0f;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) v[k][c] = w * gf[c];
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c) v[k][c] += __shfl_xor_sync(FULL, v[k][c], off);
+                        }
+                    }
+                    if ((int)lane == src) {
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k) scatter_row<G, C>(gt + (size_t)corner_row<D>(m, cell.pg, k) * C, v[k]);
+                    }
+                }
+            } else if (valid) {
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                    const float w = corner_weight<D>(cell, k);
+                    float v[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) v[c] = w * gf[c];
+                    scatter_row<G, C>(gt + (size_t)corner_row<D>(m, cell.pg, k) * C, v);
+                }
+            }
+        }
+        if (dy_dx && grad_inputs && in_range) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) grad_inputs[(size_t)b * D + d] = from_f<T>(gin[d]);
+        }
+    }
+}
+
 // ======================================================================================================
 // total-variation gradient (API parity; RAD-NeRF's trainer never calls it)   (gridencoder.cu:505-609)
 // ======================================================================================================
@@ -520,8 +634,13 @@ template <typename T, typename G, int D, int C>
 int launch_backward(const BwdArgs& a) {
     const uint32_t threads = 256;
     const uint32_t grid = wave_grid(a.B, threads, 32);
-    grid_backward_kernel<T, G, D, C><<<grid, threads, 0, a.st>>>((const T*)a.grad, a.inputs, a.offsets, (G*)a.gt,
-        (const T*)a.dy_dx, (T*)a.gin, a.B, a.L, a.S, a.H, a.gridtype, a.ac, a.interp, a.layout);
+    if constexpr (D == 2) {   // the ambient / torso grids: lanes of a warp that share a cell are summed before the atomics
+        grid_backward_shared_cell_kernel<T, G, C><<<grid, threads, 0, a.st>>>((const T*)a.grad, a.inputs, a.offsets, (G*)a.gt,
+            (const T*)a.dy_dx, (T*)a.gin, a.B, a.L, a.S, a.H, a.gridtype, a.ac, a.interp, a.layout);
+    } else {
+        grid_backward_kernel<T, G, D, C><<<grid, threads, 0, a.st>>>((const T*)a.grad, a.inputs, a.offsets, (G*)a.gt,
+            (const T*)a.dy_dx, (T*)a.gin, a.B, a.L, a.S, a.H, a.gridtype, a.ac, a.interp, a.layout);
+    }
     return finish_launch("rn_grid_encode_backward");
 }
 

@@ -53,13 +53,14 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 
 __global__ void __launch_bounds__(kThreads)
 adam_tail_kernel(const rn_adam_tensor* __restrict__ tensors, uint32_t n_tensors, GroupTable groups,
-                 const float* __restrict__ grad_scale, const float* __restrict__ found_inf, uint32_t zero_grads) {
+                 const rn_adam_group* __restrict__ groups_dev, const float* __restrict__ grad_scale,
+                 const float* __restrict__ found_inf, uint32_t zero_grads) {
     __shared__ rn_adam_tensor T;
     __shared__ Hyper H;
     if (threadIdx.x == 0) {
         const uint32_t t = find_tensor(tensors, n_tensors, blockIdx.x);
         T = tensors[t];
-        const rn_adam_group& G = groups.g[T.group];
+        const rn_adam_group G = groups_dev ? groups_dev[T.group] : groups.g[T.group];
         const double step = (double)(*T.step) + 1.0;
         const double bc1 = 1.0 - pow(G.beta1, step);
         const double bc2 = 1.0 - pow(G.beta2, step);
@@ -131,6 +132,11 @@ adam_tail_kernel(const rn_adam_tensor* __restrict__ tensors, uint32_t n_tensors,
     }
 }
 
+// the group table of the next launches, written into device memory in stream order (see rn_adam_groups_store)
+__global__ void adam_store_groups_kernel(GroupTable groups, uint32_t n, rn_adam_group* __restrict__ dst) {
+    if (threadIdx.x < n) dst[threadIdx.x] = groups.g[threadIdx.x];
+}
+
 // step += 1 for every tensor of the launch unless the step was skipped (torch's fused Adam rolls its device-side step
 // back on found_inf the same way)
 __global__ void adam_advance_kernel(const rn_adam_tensor* __restrict__ tensors, uint32_t n_tensors,
@@ -175,24 +181,46 @@ ema_update_kernel(const rn_adam_tensor* __restrict__ tensors, uint32_t n_tensors
 
 using namespace rn;
 
-extern "C" int rn_adam_step(const rn_adam_tensor* tensors, uint32_t n_tensors, uint32_t n_chunks, const rn_adam_group* groups,
-                            uint32_t n_groups, const float* grad_scale, const float* found_inf, uint32_t flags, void* stream) {
-    if (n_tensors == 0 || n_chunks == 0) return RN_OK;
-    RN_REQUIRE(tensors && groups, "null pointer");
+static int fill_group_table(GroupTable& table, const rn_adam_group* groups, uint32_t n_groups) {
+    RN_REQUIRE(groups, "null pointer");
     RN_REQUIRE(n_groups >= 1 && n_groups <= RN_ADAM_MAX_GROUPS, "between 1 and RN_ADAM_MAX_GROUPS parameter groups");
-    GroupTable table;
-    for (uint32_t i = 0; i < RN_ADAM_MAX_GROUPS; ++i) table.g[i] = groups[i < n_groups ? i : 0];
     for (uint32_t i = 0; i < n_groups; ++i) {
         RN_REQUIRE(groups[i].beta1 >= 0.0 && groups[i].beta1 < 1.0 && groups[i].beta2 >= 0.0 && groups[i].beta2 < 1.0,
                    "betas must lie in [0, 1)");
         RN_REQUIRE(groups[i].eps >= 0.0 && groups[i].weight_decay >= 0.0, "eps and weight_decay must be >= 0");
     }
-    adam_tail_kernel<<<n_chunks, kThreads, 0, (cudaStream_t)stream>>>(tensors, n_tensors, table, grad_scale, found_inf,
+    for (uint32_t i = 0; i < RN_ADAM_MAX_GROUPS; ++i) table.g[i] = groups[i < n_groups ? i : 0];
+    return RN_OK;
+}
+
+extern "C" int rn_adam_step(const rn_adam_tensor* tensors, uint32_t n_tensors, uint32_t n_chunks, const rn_adam_group* groups,
+                            uint32_t n_groups, const float* grad_scale, const float* found_inf, uint32_t flags, void* stream) {
+    if (n_tensors == 0 || n_chunks == 0) return RN_OK;
+    RN_REQUIRE(tensors && groups, "null pointer");
+    GroupTable table = {};
+    const rn_adam_group* on_device = nullptr;
+    if (flags & RN_ADAM_GROUPS_ON_DEVICE) {
+        RN_REQUIRE(n_groups >= 1 && n_groups <= RN_ADAM_MAX_GROUPS, "between 1 and RN_ADAM_MAX_GROUPS parameter groups");
+        on_device = groups;
+    } else {
+        const int rc = fill_group_table(table, groups, n_groups);
+        if (rc != RN_OK) return rc;
+    }
+    adam_tail_kernel<<<n_chunks, kThreads, 0, (cudaStream_t)stream>>>(tensors, n_tensors, table, on_device, grad_scale, found_inf,
                                                                         flags & RN_ADAM_ZERO_GRADS);
     int rc = finish_launch("rn_adam_step");
     if (rc != RN_OK) return rc;
     adam_advance_kernel<<<div_up(n_tensors, 128u), 128, 0, (cudaStream_t)stream>>>(tensors, n_tensors, found_inf);
     return finish_launch("rn_adam_step (advance)");
+}
+
+extern "C" int rn_adam_groups_store(const rn_adam_group* groups, uint32_t n_groups, rn_adam_group* groups_dev, void* stream) {
+    RN_REQUIRE(groups_dev, "null pointer");
+    GroupTable table = {};
+    const int rc = fill_group_table(table, groups, n_groups);
+    if (rc != RN_OK) return rc;
+    adam_store_groups_kernel<<<1, RN_ADAM_MAX_GROUPS, 0, (cudaStream_t)stream>>>(table, n_groups, groups_dev);
+    return finish_launch("rn_adam_groups_store");
 }
 
 extern "C" int rn_ema_update(const rn_adam_tensor* tensors, uint32_t n_tensors, uint32_t n_chunks, double decay, void* stream) {

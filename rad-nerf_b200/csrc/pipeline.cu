@@ -109,6 +109,7 @@ extern "C" uint32_t rn_sizeof(const char* name) {
         {"rn_frame_head_desc", (uint32_t)sizeof(rn_frame_head_desc)}, {"rn_frame_torso_desc", (uint32_t)sizeof(rn_frame_torso_desc)},
         {"rn_lane_submit", (uint32_t)sizeof(rn_lane_submit)},
         {"rn_adam_tensor", (uint32_t)sizeof(rn_adam_tensor)},         {"rn_adam_group", (uint32_t)sizeof(rn_adam_group)},
+        {"rn_ring_windows", (uint32_t)sizeof(rn_ring_windows)},
     };
     for (const auto& e : table)
         if (strcmp(e.n, name) == 0) return e.s;

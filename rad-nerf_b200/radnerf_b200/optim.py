@@ -34,6 +34,7 @@ class AdamGroup(C.Structure):       # rn_adam_group
 
 abi.register("rn_adam_step", [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(AdamGroup), C.c_uint32, C.c_void_p, C.c_void_p,
                               C.c_uint32, C.c_void_p])
+abi.register("rn_adam_groups_store", [C.POINTER(AdamGroup), C.c_uint32, C.c_void_p, C.c_void_p])
 abi.register("rn_ema_update", [C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_void_p])
 
 
@@ -84,6 +85,8 @@ class FusedAdam(torch.optim.Optimizer):
         self._table = None
         self._n_tensors = self._n_chunks = 0
         self._grads_are_zero = False
+        self._groups_dev = None     # device copy of the group table, only used by a step captured in a CUDA graph
+        self.device_groups = False
         if self.zero_grads:         # any gradient written by a backward pass invalidates "the sweep left them zeroed"
             for group in self.param_groups:
                 for p in group["params"]:
@@ -120,6 +123,23 @@ class FusedAdam(torch.optim.Optimizer):
             return
         super().zero_grad(set_to_none=set_to_none)
 
+    def _host_groups(self):
+        groups = (AdamGroup * len(self.param_groups))()
+        for d, group in zip(groups, self.param_groups):
+            d.lr, d.beta1, d.beta2 = float(group["lr"]), float(group["betas"][0]), float(group["betas"][1])
+            d.eps, d.weight_decay = float(group["eps"]), float(group["weight_decay"])
+        return groups
+
+    def publish_groups(self):
+        """write the current hyper-parameters (the scheduler's learning rates) into the device table, in stream order on the
+        current stream: what a step captured with device_groups=True reads when the graph is replayed after this call"""
+        device = _first_device(self)
+        if self._groups_dev is None:
+            self._groups_dev = torch.zeros(MAX_GROUPS * C.sizeof(AdamGroup), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            abi.check(abi.lib().rn_adam_groups_store(self._host_groups(), len(self.param_groups), abi.ptr(self._groups_dev),
+                                                     abi.cur_stream()), "rn_adam_groups_store")
+
     # ---- step --------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, closure=None):
@@ -145,19 +165,28 @@ class FusedAdam(torch.optim.Optimizer):
         if key != self._key:        # first step, or a gradient / state tensor was re-allocated: one small H2D copy
             self._table, self._n_chunks = _descriptor_table(rows, device)
             self._n_tensors, self._key = len(rows), key
-        groups = (AdamGroup * len(self.param_groups))()
-        for d, group in zip(groups, self.param_groups):
-            d.lr, d.beta1, d.beta2 = float(group["lr"]), float(group["betas"][0]), float(group["betas"][1])
-            d.eps, d.weight_decay = float(group["eps"]), float(group["weight_decay"])
         scale = getattr(self, "grad_scale", None)
         found = getattr(self, "found_inf", None)
+        flags = 1 if self.zero_grads else 0
         with torch.cuda.device(device):
-            fn = abi.lib().rn_adam_step
-            abi.check(fn(abi.ptr(self._table), self._n_tensors, self._n_chunks, groups, len(self.param_groups),
-                         abi.ptr(_scalar_f32(scale, device)), abi.ptr(_scalar_f32(found, device)), 1 if self.zero_grads else 0,
-                         abi.cur_stream()), "rn_adam_step")
+            if self.device_groups:      # captured step: the table lives on the device, publish_groups() keeps it current
+                if self._groups_dev is None:
+                    raise RuntimeError("FusedAdam: call publish_groups() before a step with device_groups=True")
+                groups, flags = C.cast(C.c_void_p(self._groups_dev.data_ptr()), C.POINTER(AdamGroup)), flags | 2
+            else:
+                groups = self._host_groups()
+            abi.check(abi.lib().rn_adam_step(abi.ptr(self._table), self._n_tensors, self._n_chunks, groups, len(self.param_groups),
+                                             abi.ptr(_scalar_f32(scale, device)), abi.ptr(_scalar_f32(found, device)), flags,
+                                             abi.cur_stream()), "rn_adam_step")
         self._grads_are_zero = self.zero_grads
         return loss
+
+
+def _first_device(opt):
+    for group in opt.param_groups:
+        for p in group["params"]:
+            return p.device
+    raise RuntimeError("FusedAdam: no parameters")
 
 
 def _scalar_f32(t, device):

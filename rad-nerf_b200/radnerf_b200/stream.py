@@ -146,6 +146,7 @@ class FrameStreamer:
         self.staged = [torch.cuda.Event() for _ in range(depth)]
         self.delivered = [torch.cuda.Event() for _ in range(depth)]
         self.pending = deque()
+        self.ring_read = [torch.cuda.Event() for _ in range(depth)]
         self.static = [None] * depth
         self.fast = [None] * depth      # per lane: (LaneSubmit, things it points to) once the lane's graph exists
         self.fast_generation = -1
@@ -175,14 +176,39 @@ class FrameStreamer:
                 self.delivered[k].record(self.copy_stream)
         return img
 
-    def submit(self, packed):
+    def submit(self, packed, ring=None):
         """packed: pinned host block from pack_inputs() (or the same block already on the device).  Enqueues copy-in, ray
-        generation, conditioning, the frame and copy-out; never blocks."""
+        generation, conditioning, the frame and copy-out; never blocks.
+
+        ring: a radnerf_b200.audio_ring.FeatureRing (streaming mode, the reference's `--asr` GUI loop, nerf/gui.py:180-187).
+        `packed` then holds only the 24-float head [pose | pose6 | eye | pad]; the frame's audio window never exists on the
+        host: the ring's gather kernel writes it straight into the lane's input block."""
         from . import frame as _frame
-        assert packed.numel() == self.n_in and (packed.is_cuda or packed.is_pinned())
         k = self.pipe.next_lane()
-        if self._submit_fast(k, packed):
-            return
+        if ring is not None:
+            assert packed.numel() == 24 and (packed.is_cuda or packed.is_pinned()) and ring.dim * 128 == self.n_in - 24
+            cur = torch.cuda.current_stream(self.dev)
+            ls = self.pipe.streams[k]
+            st = self.static[k]
+            armed = self.fast[k] is not None and st is not None
+            full = None if armed else torch.empty(self.n_in, dtype=torch.float32, device=self.dev)
+            if full is not None:
+                full.record_stream(ls)
+            ls.wait_stream(cur)                        # the ring rows pushed so far on the caller's stream are in place
+            with torch.cuda.stream(ls):                # ... and the lane's previous frame has finished reading its block
+                ring.next_window(out=st["flat"][24:self.n_in] if armed else full[24:])
+                self.ring_read[k].record(ls)
+            cur.wait_event(self.ring_read[k])          # a later push must not overwrite rows this gather still reads
+            if armed and self._submit_fast(k, packed, head_only=True):
+                return
+            if armed:                                  # the fast path was disarmed under us (weights / graph changed)
+                full = st["flat"][:self.n_in].clone()
+            full[:24].copy_(packed, non_blocking=True)
+            packed = full                              # a complete device block: carry on through the Python path
+        else:
+            assert packed.numel() == self.n_in and (packed.is_cuda or packed.is_pinned())
+            if self._submit_fast(k, packed):
+                return
         kw = dict(index=0, bg_color=None, perturb=False, **self.kw)
         st = self.static[k]
         if st is None or _frame.lane_state(self.model, k).last_static is not st:
@@ -250,7 +276,7 @@ class FrameStreamer:
         self.fast[k] = (s, cd, ev, entry, hdls[k % len(bufs)] if peer is not None else None)
         self.fast_generation = st.shared.generation
 
-    def _submit_fast(self, k, packed):
+    def _submit_fast(self, k, packed, head_only=False):
         f = self.fast[k]
         if f is None:
             return False
@@ -267,6 +293,7 @@ class FrameStreamer:
             return False
         s, barrier = f[0], f[4]
         s.packed_src = packed.data_ptr()
+        s.packed_bytes = 4 * (24 if head_only else self.n_in)   # streaming: the audio part is already in the lane's block
         self.__dict__.setdefault("_keep", {})[k] = packed   # the async copy-in reads it: alive until the lane's next frame
         L = abi.lib()
         if barrier is None:

@@ -115,3 +115,109 @@ def train_step(model, batch, optimizer, scaler=None, sync=None, lambda_amb=0.1, 
             sync.finish()
         optimizer.step()
     return loss.detach()
+
+
+class GraphedTrainStep:
+    """`train_step` replayed as ONE CUDA graph per step (single GPU, FusedAdam tail, fp16 autocast).
+
+    Once the marcher sizes its buffers from `mean_count` (after the first occupancy update, raymarching.py:213-229) every
+    shape in the step is fixed until the next update, so the whole step -- march, encoders, MLPs, compositing, loss,
+    backward, GradScaler inf check, the optimiser sweep and the scaler update -- can be captured once and replayed: one
+    launch per step.  What moves between steps stays outside the frozen kernel arguments: the batch is copied into static
+    input tensors, the learning rates go through FusedAdam's device-side group table (`publish_groups`), the marcher's
+    noise comes from torch's graph-safe generator, the `(samples, rays)` counter row is copied to where the eager step would
+    have written it.  A change of `mean_count` (every update_extra_state) or of the batch shape re-captures into the same
+    memory pool.  Steps before `mean_count` is known run eagerly, and so does everything if capture fails
+    (`self.fallback_reason` says why).
+
+    Status (round 1, one B200, 2^16 rays, ~0.7 M samples): NOT the default.  The capture is correct
+    (tests/test_gpu_train.py), but a replay takes 10.3 ms against 8.5 ms for the op-by-op step and each re-capture costs
+    25-160 ms (tools/train_bench.py graphed:steady): the step is bound by its ~400 kernels' device work -- a third of it was
+    atomic contention in the 2-D grid backward, fixed in csrc/gridencoder_impl.cuh -- not by launch overhead.  It stays as the
+    capture-safe scaffolding (static inputs, device-side learning rates, counter bookkeeping) for a fused training step."""
+
+    KEYS = ("rays_o", "rays_d", "auds", "bg_coords", "poses", "eye", "rgb", "face_mask", "bg_color")
+
+    def __init__(self, model, optimizer, scaler, lambda_amb=0.1, phase=None):
+        from .optim import FusedAdam
+        if not isinstance(optimizer, FusedAdam):
+            raise TypeError("GraphedTrainStep needs radnerf_b200.optim.FusedAdam (its step is capturable: no host reads)")
+        self.model, self.opt, self.scaler, self.lambda_amb, self.phase = model, optimizer, scaler, lambda_amb, phase
+        self.graph = None
+        self.key = None
+        self.static = None
+        self.loss = None
+        self.warm = False
+        self.fallback_reason = None
+        self.captures = 0
+        self.replays = 0
+        self.capture_ms = []       # host time of every (re-)capture, synchronisation and instantiation included
+        self.pool = None           # every capture allocates from the same private pool: no cudaMalloc after the first one
+
+    def _eager(self, batch):
+        self.opt.device_groups = False
+        return train_step(self.model, batch, self.opt, self.scaler, None, self.lambda_amb, self.phase)
+
+    def _load(self, batch):
+        dev = self.static["rays_o"].device
+        for k in self.KEYS:
+            if self.static.get(k) is not None:
+                self.static[k].copy_(torch.as_tensor(batch[k]), non_blocking=True)
+        idx = batch.get("index", 0)
+        self.static["index"].copy_(torch.as_tensor(idx, dtype=torch.long).reshape(-1)[:1].to(dev, non_blocking=True))
+
+    def _capture(self, batch):
+        import time
+        t0 = time.perf_counter()
+        m = self.model
+        dev = batch["rays_o"].device
+        previous = self.graph  # stays alive until the new graph exists, so the shared pool keeps its memory
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()
+        self.static = {k: (torch.as_tensor(batch[k]).to(dev).clone() if batch.get(k) is not None else None) for k in self.KEYS}
+        self.static["index"] = torch.zeros(1, dtype=torch.long, device=dev)
+        self._load(batch)
+        self.opt.publish_groups()
+        self.opt.device_groups = True
+        local_step = m.local_step
+        self.counter_row = local_step % 16
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g, pool=self.pool):
+                self.loss = train_step(m, self.static, self.opt, self.scaler, None, self.lambda_amb, self.phase)
+        finally:
+            m.local_step = local_step      # capture ran the host bookkeeping of one step without executing it
+        self.graph = g
+        del previous
+        self.captures += 1
+        self.capture_ms.append((time.perf_counter() - t0) * 1e3)
+
+    def __call__(self, batch):
+        m = self.model
+        amp = bool(m.opt.fp16)
+        shapes = tuple((k, tuple(torch.as_tensor(batch[k]).shape)) for k in self.KEYS if batch.get(k) is not None)
+        if self.fallback_reason is not None or not amp or m.mean_count <= 0 or not self.warm:
+            self.warm = self.warm or m.mean_count > 0      # one eager step in the steady regime: lazy initialisations, grads exist
+            return self._eager(batch)
+        key = (int(m.mean_count), shapes, self.phase)
+        if key != self.key:
+            try:
+                self._capture(batch)
+                self.key = key
+            except Exception as e:  # noqa: BLE001
+                self.fallback_reason = repr(e)[:300]
+                self.graph, self.key = None, None
+                torch.cuda.synchronize()
+                return self._eager(batch)
+        else:
+            self._load(batch)
+            self.opt.publish_groups()
+        self.graph.replay()
+        self.replays += 1
+        # host bookkeeping of run_cuda's training branch: the counter row of this step, the step index
+        row = m.local_step % 16
+        if row != self.counter_row:
+            m.step_counter[row].copy_(m.step_counter[self.counter_row])
+        m.local_step += 1
+        return self.loss.detach()

@@ -124,6 +124,44 @@ def test_grid_backward_vs_reference_golden_and_oracle(abi, oracle, name):
         assert maxabs(N_(ge16.float()), o_ge) <= 4e-3 * scale
 
 
+@pytest.mark.parametrize("half", [False, True])
+def test_grid_backward_2d_clustered_inputs_warp_aggregation(abi, oracle, half):
+    """the ambient grid's real input: coordinates clustered around one point (plus exact duplicates, a few out-of-range
+    rows and a ragged tail), so that the lanes of a warp share cells on the coarse levels and the warp-aggregated path of
+    grid_backward_shared_cell_kernel runs; uniform rows mixed in keep the per-lane path in the same launch.
+    Oracle: double accumulation.  Tolerance: fp32 summation order only (1e-5 of the largest sum; 1e-3 for fp16 gradients,
+    where the oracle rounds each contribution to half and we keep fp32)"""
+    rng = np.random.default_rng(21)
+    B, D, C, L, H = 20011, 2, 2, 16, 16
+    offs, pls = oracle.grid_offsets(D, L, C, H, 16, desired_resolution=2048)     # the ambient grid of nerf/network.py
+    x = (0.52 + 0.004 * rng.standard_normal((B, D))).astype(np.float32)
+    x[1000:1400] = x[1000]                                   # exact duplicates: whole warps on one point
+    x[5000:7000] = rng.random((2000, D), dtype=np.float32)   # uniform rows: every lane its own cell
+    x[::977] = 1.5                                           # out of range: no table contribution
+    grad = rng.standard_normal((B, L * C)).astype(np.float16 if half else np.float32)
+    n_rows = int(offs[-1])
+    xt, ot, gt_ = T(x), T(offs), T(grad)
+    table = torch.zeros(n_rows, C, device=DEV, dtype=torch.float16 if half else torch.float32)
+    ge = torch.zeros(n_rows, C, device=DEV, dtype=torch.float32)
+    S = float(np.log2(pls))
+    abi.check(abi.lib().rn_grid_encode_backward(abi.ptr(gt_), abi.ptr(xt), abi.ptr(table), abi.ptr(ot), abi.ptr(ge), B, D, C, L, S, H,
+                                                None, None, 0, 0, 0, int(half), 1, 0, abi.cur_stream()))
+    sc = device_scales(abi, np.log2(pls), H, L)
+    o_ge, _ = oracle.grid_encode_backward(grad, x, offs, pls, H, n_rows, C, scales=sc)
+    scale = float(np.abs(o_ge).max())
+    assert scale > 50.0                                      # thousands of samples really pile onto single rows
+    assert maxabs(N_(ge).astype(np.float64), o_ge) <= (1e-3 if half else 1e-5) * scale
+    # and through the reference's fp16 accumulation target.  Every atomic add rounds the running sum to 11 bits, and here
+    # hundreds to thousands of adds land on one row whose sum reaches ~100 (half ulp 0.06): the target itself is only good
+    # to a few percent of the largest sum (the reference's own kernel has the same property); fewer adds -- what the warp
+    # aggregation gives -- can only make it better
+    if half:
+        ge16 = torch.zeros(n_rows, C, device=DEV, dtype=torch.float16)
+        abi.check(abi.lib().rn_grid_encode_backward(abi.ptr(gt_), abi.ptr(xt), abi.ptr(table), abi.ptr(ot), abi.ptr(ge16), B, D, C, L, S,
+                                                    H, None, None, 0, 0, 0, 1, 1, 1, abi.cur_stream()))
+        assert maxabs(N_(ge16.float()).astype(np.float64), o_ge) <= 5e-2 * scale
+
+
 def test_grid_tv_gradient(abi, oracle):
     for name in ("g2_f32_dy", "g3_hash_sm_f32", "g2_align_c1"):
         c = gc.grid_case(name)

@@ -78,3 +78,46 @@ def test_training_render_is_deterministic_for_fixed_noise():
                      int(model.step_counter[(model.local_step - 1) % 16][0])))
     assert outs[0][2] == outs[1][2] and outs[0][2] > 0
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_graphed_step_replays_the_whole_step_and_follows_the_schedule():
+    """GraphedTrainStep: eager until mean_count is known, then one capture and replays; the optimiser's device-side step
+    counters advance once per call, the learning rate reaches the captured sweep through the device group table (lr = 0
+    freezes the parameters), a change of mean_count re-captures, the marcher's counter rows are filled as the eager step
+    fills them"""
+    from radnerf_b200 import synthetic as syn
+    from radnerf_b200.optim import FusedAdam
+    from radnerf_b200.train import GraphedTrainStep
+    model = _head_model()
+    batches = [syn.batch_to(syn.training_batch(128, 128, 4096, frame_index=i), DEV) for i in range(3)]
+    opt = FusedAdam(model.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15, zero_grads=True)
+    scaler = torch.amp.GradScaler("cuda")
+    step = GraphedTrainStep(model, opt, scaler)
+    losses = [float(step(batches[i % 3])) for i in range(4)]           # mean_count unknown: eager
+    assert step.captures == 0 and step.replays == 0
+    model.mean_count = int(model.step_counter[:4, 0].float().mean().item() * 1.2)
+    model.local_step = 0
+    losses += [float(step(batches[i % 3])) for i in range(12)]         # 1 eager (warm), 1 capture, 11 replays
+    assert step.fallback_reason is None, step.fallback_reason
+    assert step.captures == 1 and step.replays == 11
+    assert all(np.isfinite(losses))
+    p = model.sigma_net.net[0].weight
+    assert float(opt.state[p]["step"]) == 16                            # every call took exactly one optimiser step
+    assert model.local_step == 12
+    rows = model.step_counter[:12, 0]
+    assert int(rows.min()) > 0 and len(set(rows.tolist())) > 1          # every step's (samples, rays) row was recorded
+    before = {n: q.detach().clone() for n, q in model.named_parameters() if q.grad is not None}
+    for g in opt.param_groups:
+        g["lr"] = 0.0
+    step(batches[0])
+    assert step.captures == 1                                           # a new learning rate is not a new graph
+    for n, q in model.named_parameters():
+        if n in before:
+            assert torch.equal(q.detach(), before[n]), n
+    for g, lr in zip(opt.param_groups, [5e-4, 5e-3, 5e-3, 5e-4, 5e-4, 5e-4, 2.5e-3, 5e-4]):
+        g["lr"] = lr
+    step(batches[1])
+    assert not torch.equal(p.detach(), before["sigma_net.net.0.weight"])
+    model.mean_count += 128                                             # what update_extra_state does every 16 steps
+    step(batches[2])
+    assert step.captures == 2 and step.fallback_reason is None

@@ -21,7 +21,7 @@ import torch
 from radnerf_b200 import synthetic as syn
 from radnerf_b200.model import NeRFNetwork, Options
 from radnerf_b200.optim import FusedAdam
-from radnerf_b200.train import head_loss, train_step
+from radnerf_b200.train import GraphedTrainStep, head_loss, train_step
 
 dev = torch.device("cuda", 0)
 n_rays = int(os.environ.get("N_RAYS", 65536))
@@ -56,6 +56,7 @@ def run(kind, regime):
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 0.1 ** (it / 200000))
     scaler = torch.amp.GradScaler("cuda")
     g = 0
+    graphed = GraphedTrainStep(model, opt, scaler) if kind == "graphed" else None
 
     def one(i):
         nonlocal g
@@ -63,7 +64,7 @@ def run(kind, regime):
             with torch.autocast("cuda", dtype=torch.float16):
                 model.update_extra_state()
         g += 1
-        loss = train_step(model, batches[i % 8], opt, scaler, None)
+        loss = graphed(batches[i % 8]) if graphed is not None else train_step(model, batches[i % 8], opt, scaler, None)
         sched.step()
         return loss
 
@@ -81,7 +82,19 @@ def run(kind, regime):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     samples = float(model.step_counter[:, 0].float().mean())
-    return {"optimizer": kind, "regime": regime, "ms_per_step": ms, "host_ms_per_step": (time.perf_counter() - t0) * 1e3 / steps,
+    replay_ms = None
+    if graphed is not None:    # replays only: no grid update, no re-capture in between
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for i in range(12):
+            graphed(batches[i % 8])
+        r1.record()
+        torch.cuda.synchronize()
+        replay_ms = r0.elapsed_time(r1) / 12
+    extra = {} if graphed is None else {"captures": graphed.captures, "replays": graphed.replays, "fallback_reason": graphed.fallback_reason,
+                                             "capture_ms": graphed.capture_ms, "replay_only_ms_per_step": replay_ms}
+    return {**extra, "optimizer": kind, "regime": regime, "ms_per_step": ms, "host_ms_per_step": (time.perf_counter() - t0) * 1e3 / steps,
             "rays_per_s": n_rays / ms * 1e3, "samples_per_step": samples, "msamples_per_s": samples / ms / 1e3,
             "loss": float(loss), "mean_count": int(model.mean_count), "steps": steps}, model, opt, scaler
 
@@ -116,9 +129,10 @@ def phases(model, opt, scaler, reps=8):
 
 
 results = []
-for kind, regime in (("torch", "cold"), ("torch", "steady"), ("fused", "steady")):
+runs = [tuple(a.split(":")) for a in sys.argv[1:]] or [("torch", "cold"), ("torch", "steady"), ("fused", "steady"), ("graphed", "steady")]
+for kind, regime in runs:
     r, model, opt, scaler = run(kind, regime)
-    if regime == "steady":
+    if regime == "steady" and kind != "graphed":
         r["phases_ms"] = phases(model, opt, scaler)
     results.append(r)
     print(json.dumps(r), flush=True)
