@@ -4,7 +4,10 @@ Gives the model mirror a complete CPU execution of the inference frame: the refe
 (oracle.c, OpenMP over the host cores) for encode / march / composite, torch-CPU nn.Linear/Conv1d for the small MLPs
 and the audio nets.  Used by bench.py for the `cpu_baseline` object and the `--impl reference` arm (the reference has no
 CPU implementation of its own -- its extensions are CUDA-only -- so this port IS the CPU baseline), and by tests.
-Inference only (no autograd through the oracle ops).
+CPUOps() is the inference bundle; CPUOps(train=True) adds autograd through the oracle ops (grid encoder forward/backward with
+dy_dx, march_rays_train, composite_rays_train forward/backward, trunc_exp's clamped backward) so that a whole training step --
+the reference's NeRFNetwork / NeRFRenderer.run_cuda / Trainer.train_step, or our mirror -- runs and differentiates on the CPU
+(tests/golden/make_train_golden.py, tests/test_train_parity.py).
 """
 import numpy as np
 import torch
@@ -78,10 +81,37 @@ class GridEncoderCPU(nn.Module):
     def forward(self, inputs, bound=1):
         inputs = (inputs + bound) / (2 * bound)
         prefix = list(inputs.shape[:-1])
-        out, _ = O.grid_encode_forward(_np(inputs.reshape(-1, self.input_dim).float()), _np(self.embeddings), _np(self.offsets),
-                                       self.per_level_scale, self.base_resolution, False, self.gridtype_id,
-                                       self.align_corners, self.interp_id, scales=self.device_scales)
-        return torch.from_numpy(out).view(prefix + [self.output_dim])
+        flat = inputs.reshape(-1, self.input_dim).float()
+        if torch.is_grad_enabled() and (flat.requires_grad or self.embeddings.requires_grad):
+            out = _GridFnCPU.apply(flat, self.embeddings, self)
+        else:
+            out, _ = O.grid_encode_forward(_np(flat), _np(self.embeddings), _np(self.offsets), self.per_level_scale,
+                                           self.base_resolution, False, self.gridtype_id, self.align_corners, self.interp_id,
+                                           scales=self.device_scales)
+            out = torch.from_numpy(out)
+        return out.view(prefix + [self.output_dim])
+
+
+class _GridFnCPU(torch.autograd.Function):
+    """_grid_encode (gridencoder/grid.py:27-89) on the oracle kernels, fp32: dy_dx only when the input needs a gradient"""
+
+    @staticmethod
+    def forward(ctx, x, emb, enc):
+        want = bool(x.requires_grad)
+        out, dy = O.grid_encode_forward(_np(x), _np(emb), _np(enc.offsets), enc.per_level_scale, enc.base_resolution, want,
+                                        enc.gridtype_id, enc.align_corners, enc.interp_id, scales=enc.device_scales)
+        ctx.save_for_backward(x, emb)
+        ctx.enc, ctx.dy = enc, dy
+        return torch.from_numpy(out)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, emb = ctx.saved_tensors
+        enc = ctx.enc
+        ge, gi = O.grid_encode_backward(_np(grad.contiguous().float()), _np(x), _np(enc.offsets), enc.per_level_scale,
+                                        enc.base_resolution, emb.shape[0], emb.shape[1], dy_dx=ctx.dy, gridtype=enc.gridtype_id,
+                                        align_corners=enc.align_corners, interpolation=enc.interp_id, scales=enc.device_scales)
+        return (None if gi is None else torch.from_numpy(gi.astype(np.float32))), torch.from_numpy(ge.astype(np.float32)), None
 
 
 class FreqEncoderCPU(nn.Module):
@@ -123,8 +153,75 @@ def get_encoder(encoding, input_dim=3, multires=6, degree=4, num_levels=16, leve
     return enc, enc.output_dim
 
 
+# ------------------------------------------------------------------------------------------------ training (autograd) halves
+TRAIN_NOISE = None    # per-ray start offsets for perturb=True, set by the caller ([N] float32 in [0,1)); None draws np.random
+
+
+class _CompositeTrainCPU(torch.autograd.Function):
+    """_composite_rays_train (raymarching/raymarching.py:283-342) on the oracle kernels"""
+
+    @staticmethod
+    def forward(ctx, sigmas, rgbs, ambient, deltas, rays, T_thresh=1e-4):
+        sigmas, rgbs, ambient = sigmas.float().contiguous(), rgbs.float().contiguous(), ambient.float().contiguous()
+        ws, am, dp, im = O.composite_rays_train_forward(_np(sigmas), _np(rgbs), _np(ambient), _np(deltas), _np(rays), T_thresh)
+        ws, am, dp, im = (torch.from_numpy(a) for a in (ws, am, dp, im))
+        ctx.save_for_backward(sigmas, rgbs, deltas, rays, ws, im)
+        ctx.T_thresh = T_thresh
+        return ws, am, dp, im
+
+    @staticmethod
+    def backward(ctx, g_ws, g_am, g_dp, g_im):
+        sigmas, rgbs, deltas, rays, ws, im = ctx.saved_tensors
+        gs, gr, ga = O.composite_rays_train_backward(_np(g_ws.contiguous()), _np(g_am.contiguous()), _np(g_im.contiguous()), _np(sigmas),
+                                                     _np(rgbs), _np(deltas), _np(rays), _np(ws), _np(im), ctx.T_thresh)
+        return torch.from_numpy(gs), torch.from_numpy(gr), torch.from_numpy(ga), None, None, None
+
+
+class _TruncExpCPU(torch.autograd.Function):
+    """activation.py:5-17"""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * torch.exp(ctx.saved_tensors[0].clamp(-15, 15))
+
+
+class _RMTrain(_RM):
+    @staticmethod
+    def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None, mean_count=-1, perturb=False,
+                         align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024):
+        """_march_rays_train.forward (raymarching/raymarching.py:195-262); rays are visited in order"""
+        o, d = _np(rays_o).reshape(-1, 3), _np(rays_d).reshape(-1, 3)
+        N = o.shape[0]
+        M = N * max_steps
+        if not force_all_rays and mean_count > 0:
+            if align > 0:
+                mean_count += align - mean_count % align
+            M = mean_count
+        if perturb:
+            noises = np.random.rand(N).astype(np.float32) if TRAIN_NOISE is None else np.asarray(TRAIN_NOISE, np.float32)[:N]
+        else:
+            noises = np.zeros(N, np.float32)
+        x, dd, dl, rays, counter = O.march_rays_train(o, d, bound, _np(density_bitfield), C, H, _np(nears), _np(fars), noises, M, dt_gamma,
+                                                      max_steps)
+        if step_counter is not None:
+            step_counter.copy_(torch.from_numpy(counter))
+        if force_all_rays or mean_count <= 0:
+            m = int(counter[0])
+            if align > 0:
+                m += align - m % align
+            x, dd, dl = x[:m], dd[:m], dl[:m]
+        return torch.from_numpy(x), torch.from_numpy(dd), torch.from_numpy(dl), torch.from_numpy(rays)
+
+    composite_rays_train = staticmethod(_CompositeTrainCPU.apply)
+
+
 class CPUOps:
-    def __init__(self):
-        self.rm = _RM
+    def __init__(self, train=False):
+        self.rm = _RMTrain if train else _RM
         self.get_encoder = get_encoder
-        self.trunc_exp = torch.exp
+        self.trunc_exp = _TruncExpCPU.apply if train else torch.exp
