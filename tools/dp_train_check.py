@@ -34,7 +34,11 @@ def make():
 
 model = make()
 sync = GradSync(model.parameters()) if world > 1 else None
-opt = torch.optim.Adam(model.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15)
+if os.environ.get("TAIL", "torch") == "fused":     # the one-sweep tail (radnerf_b200.optim): deterministic, replicas stay identical
+    from radnerf_b200.optim import FusedAdam
+    opt = FusedAdam(model.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15, zero_grads=True)
+else:
+    opt = torch.optim.Adam(model.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15)
 scaler = torch.amp.GradScaler("cuda")
 batches = [syn.batch_to(syn.training_batch(512, 512, n_rays, frame_index=i, seed=rank), dev) for i in range(4)]
 
