@@ -210,3 +210,46 @@ def test_pack_inputs_layout_matches_the_graph_input_block():
     assert p.shape == (24 + 8 * 44 * 16,)
     assert np.array_equal(p[:16], pose.reshape(-1)) and np.array_equal(p[16:22], np.arange(6) + 50) and p[22] == 0.25 and p[23] == 0
     assert np.array_equal(p[24:], auds.reshape(-1))
+
+
+def test_config1_case(oracle):
+    """BASELINE configs[0] (the reference's CPU-runnable case: march -> GridEncoder fwd+bwd -> composite_rays_train fwd+bwd) at a
+    small size on the CPU restatement: the pipeline is self-consistent (exact packing of the marcher's output, weights in
+    [0,1], gradient sums) and independent of the marcher's slot order (tools/config1.py compares GPU and CPU runs that way)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("config1", os.path.join(ROOT, "tools", "config1.py"))
+    c1 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(c1)
+    c = c1.inputs(4096)
+    res, timing = c1.run_cpu(c, reps=1)
+    m, rays = timing["samples"], res["rays"]
+    assert 0 < m <= 4096 * c1.MAX_STEPS and timing["cores"] >= 1
+    assert int(res["counter"][0]) == m == int(rays[:, 2].sum()) and int(res["counter"][1]) == 4096
+    order = np.argsort(rays[:, 1], kind="stable")                       # offsets tile [0, m) exactly
+    assert np.array_equal(np.cumsum(rays[order, 2]) - rays[order, 2], rays[order, 1])
+    assert res["weights_sum"].min() >= 0 and res["weights_sum"].max() <= 1 + 1e-6
+    assert res["feat"].shape == (m, 32) and np.isfinite(res["g_table"]).all()
+    # the table gradient distributes exactly the incoming gradient: per level, sum over rows == sum over samples (weights sum to 1)
+    s = c1.sample_inputs(c, rays, m)
+    offs = c["offsets"]
+    for lvl in (0, 7, 15):
+        want = s["d_feat"][:, 2 * lvl:2 * lvl + 2].astype(np.float64).sum(0)
+        got = res["g_table"][offs[lvl]:offs[lvl + 1]].sum(0)
+        assert np.abs(got - want).max() <= 1e-6 * max(1.0, np.abs(want).max())
+    # a run whose slots are permuted ray by ray compares equal in canonical order
+    perm = np.random.default_rng(3).permutation(4096)
+    shuffled = dict(res)
+    new_rays, pieces, off = np.empty_like(rays), {k: [] for k in ("xyzs", "dirs", "deltas", "feat", "g_sigmas", "g_rgbs", "g_ambient")}, 0
+    for j, i in enumerate(perm):
+        rid, o, k = rays[i]
+        new_rays[j] = (rid, off, k)
+        for key in pieces:
+            pieces[key].append(res[key][o:o + k])
+        off += k
+    shuffled["rays"] = new_rays
+    for key in pieces:
+        shuffled[key] = np.concatenate(pieces[key])
+    for key in ("weights_sum", "ambient_sum", "depth", "image"):
+        shuffled[key] = res[key][perm]
+    e = c1.compare(shuffled, res)
+    assert all(v is True or v == 0.0 for v in e.values()), e
