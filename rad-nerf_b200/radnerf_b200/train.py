@@ -117,6 +117,35 @@ def train_step(model, batch, optimizer, scaler=None, sync=None, lambda_amb=0.1, 
     return loss.detach()
 
 
+def update_extra_state_replicated(model, group=None, share_counters=True):
+    """`model.update_extra_state()` on every data-parallel rank such that the replicas stay bit-identical (SURVEY 8(e), rows
+    "Occupancy update" and "mean_count").  The update draws a random audio window / pose (Python `random`) and jitters the
+    query points inside their cells (`torch.rand_like`, nerf/renderer.py:383-501): rank 0 broadcasts one seed, every rank
+    runs the update under it (its own RNG streams -- which feed the per-rank ray sampling -- are restored afterwards), and
+    with identical weights, grids and draws all ranks build the same density grid and bitfield without exchanging them.
+    share_counters: the (samples, rays) counters of the last <= 16 steps are max-reduced first, so `mean_count`, which sizes
+    the marcher's buffers and decides which rays are dropped on overflow, is the same everywhere (and safe for the rank that
+    emitted the most samples)."""
+    import random
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world <= 1:
+        return model.update_extra_state()
+    dev = model.step_counter.device
+    import os
+    seed = torch.tensor([int.from_bytes(os.urandom(4), "little") & 0x7FFFFFFF], dtype=torch.int64, device=dev)   # no RNG stream consumed
+    dist.broadcast(seed, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if share_counters:
+        dist.all_reduce(model.step_counter, op=dist.ReduceOp.MAX, group=group)
+    py_state = random.getstate()
+    with torch.random.fork_rng(devices=[dev] if dev.type == "cuda" else []):
+        torch.manual_seed(int(seed.item()))
+        random.seed(int(seed.item()))
+        try:
+            return model.update_extra_state()
+        finally:
+            random.setstate(py_state)
+
+
 class GraphedTrainStep:
     """`train_step` replayed as ONE CUDA graph per step (single GPU, FusedAdam tail, fp16 autocast).
 

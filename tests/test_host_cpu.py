@@ -103,6 +103,55 @@ def test_gradsync_two_ranks_gloo_equals_mean_of_local_grads():
     assert out[0][1] == (1024 + 6 + 3) * 4   # bytes exchanged per step: the table + the flat bucket (lin.weight, lin.bias)
 
 
+class _OccupancyStub:
+    """stands in for NeRFNetwork: an update that consumes the RNG streams update_extra_state consumes and derives its grid from
+    the draws and the step counters"""
+
+    def __init__(self, rank):
+        self.step_counter = torch.zeros(16, 2, dtype=torch.int32)
+        self.step_counter[:4, 0] = torch.tensor([100, 120, 90, 110]) * (rank + 1)     # ranks emitted different sample counts
+        self.step_counter[:4, 1] = 64
+        self.grid = None
+
+    def update_extra_state(self):
+        import random
+        k = random.randint(0, 599)
+        self.grid = torch.rand(32) + k
+        self.mean_count = int(self.step_counter[:4, 0].sum().item() / 4)
+        return k
+
+
+def _occupancy_worker(rank, world, port, out):
+    import random
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.join(ROOT, "rad-nerf_b200"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from radnerf_b200.train import update_extra_state_replicated
+    torch.manual_seed(1000 + rank)       # every rank has its own RNG streams (its own rays) ...
+    random.seed(2000 + rank)
+    m = _OccupancyStub(rank)
+    before = (torch.rand(3), random.random())
+    torch.manual_seed(1000 + rank)
+    random.seed(2000 + rank)
+    k = update_extra_state_replicated(m)
+    after = (torch.rand(3), random.random())      # ... which the replicated update must leave where they were
+    out[rank] = (k, m.grid, m.mean_count, m.step_counter.clone(), torch.equal(before[0], after[0]) and before[1] == after[1])
+    dist.destroy_process_group()
+
+
+def test_replicated_occupancy_update_two_ranks_gloo():
+    """SURVEY 8(e) "Occupancy update" / "mean_count": same draws and the same (max-reduced) counters on every rank, per-rank
+    RNG streams untouched"""
+    world = 2
+    out = mp.Manager().dict()
+    port = 29500 + (os.getpid() + 131) % 1000
+    mp.spawn(_occupancy_worker, args=(world, port, out), nprocs=world, join=True)
+    (k0, g0, mc0, sc0, kept0), (k1, g1, mc1, sc1, kept1) = out[0], out[1]
+    assert k0 == k1 and torch.equal(g0, g1)                     # identical random draws -> identical grids
+    assert mc0 == mc1 == (200 + 240 + 180 + 220) // 4           # counters max-reduced: the busier rank's counts
+    assert torch.equal(sc0, sc1) and kept0 and kept1
+
+
 def test_sharder_rejects_unbalanced_split():
     sys.path.insert(0, os.path.join(ROOT, "rad-nerf_b200"))
     from radnerf_b200.sharding import FrameSharder
