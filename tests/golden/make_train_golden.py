@@ -4,11 +4,14 @@ produced by the REFERENCE's own classes on the CPU of this container:
     NeRFNetwork (nerf/network.py) . train()  ->  NeRFRenderer.run_cuda, training branch (nerf/renderer.py:207-236)
     ->  Trainer.train_step (nerf/utils.py:718-808, called unbound on a bare object)  ->  loss.backward()
 
+once for the head phase and once for the torso phase (`--torso`: the loss is taken on `torso_color` against `bg_torso_color`, only the
+torso branch -- deformation MLP, 2-D torso grid, torso MLP, torso individual codes -- receives gradients; nerf/utils.py:730, 744, 787).
+
 `raymarching` / `encoding` / `activation` are bound to the oracle's CPU operators with autograd (oracle/cpu_backend.py,
 CPUOps(train=True); the kernels underneath are pinned to the reference's CUDA kernels by tests/test_oracle_golden.py), weights
 come from tests/network_case.fill_parameters, the batch / marcher noise / lambda schedule from tests/train_case.py; fp32.
 
-    python tests/golden/make_train_golden.py      ->  tests/golden/train_step.npz   (needs /root/reference)
+    python tests/golden/make_train_golden.py      ->  tests/golden/train_step.npz, train_step_torso.npz   (needs /root/reference)
 """
 import os
 import sys
@@ -55,32 +58,34 @@ def main():
     from nerf.utils import Trainer
     from radnerf_b200.model import Options
 
-    o = Options(torso=False, smooth_lips=False, fp16=False, exp_eye=True)
-    opt = types.SimpleNamespace(**{**vars(o), "test_train": False, "color_space": "srgb", "patch_size": 1, "finetune_lips": False,
-                                   "iters": tc.ITERS, "lambda_amb": tc.LAMBDA_AMB})
-    net = NeRFNetwork(opt).train()
-    fill_parameters(net)
     scales = np.load(os.path.join(HERE, "grid_g3_f32.npz"))["scales"]
-    for e in (net.encoder, net.encoder_ambient):
-        e.device_scales = scales
-    tc.install_head_occupancy(net)
-    cpu_backend.TRAIN_NOISE = tc.noise()
-    me = types.SimpleNamespace(opt=opt, model=net, criterion=torch.nn.MSELoss(reduction="none"), global_step=tc.GLOBAL_STEP,
-                               flip_finetune_lips=False)
-    b = tc.batch()
-    pred, truth, loss = Trainer.train_step(me, b)
-    loss.backward()
-    counter = net.step_counter[0].numpy().copy()
-    grads = {n: p.grad.numpy() for n, p in net.named_parameters() if p.grad is not None}
-    res = tc.summarise(grads)
-    res["loss"] = np.float64(loss.item())
-    res["pred_rgb"] = pred.detach().numpy().reshape(-1, 3)
-    res["counter"] = counter
-    res["grad_names"] = np.array(sorted(grads))
-    np.savez_compressed(os.path.join(HERE, "train_step.npz"), **res)
-    print("loss", float(loss), "counter", counter.tolist(), "tensors with a gradient:", len(grads))
-    for n in ("encoder.embeddings", "encoder_ambient.embeddings"):
-        print(n, "norm", float(res[n + "/norm"]), "nonzero rows", int(res[n + "/nonzero_rows"]))
+    for phase in ("head", "torso"):
+        o = Options(torso=(phase == "torso"), smooth_lips=False, fp16=False, exp_eye=True)
+        opt = types.SimpleNamespace(**{**vars(o), "test_train": False, "color_space": "srgb", "patch_size": 1, "finetune_lips": False,
+                                       "iters": tc.ITERS, "lambda_amb": tc.LAMBDA_AMB})
+        net = NeRFNetwork(opt).train()
+        fill_parameters(net)
+        for e in ([net.encoder, net.encoder_ambient] + ([net.torso_encoder] if phase == "torso" else [])):
+            e.device_scales = scales
+        tc.install_occupancy(net, torso=(phase == "torso"))
+        cpu_backend.TRAIN_NOISE = tc.noise()
+        me = types.SimpleNamespace(opt=opt, model=net, criterion=torch.nn.MSELoss(reduction="none"), global_step=tc.GLOBAL_STEP,
+                                   flip_finetune_lips=False)
+        b = tc.batch()
+        pred, truth, loss = Trainer.train_step(me, b)
+        loss.backward()
+        counter = net.step_counter[0].numpy().copy()
+        grads = {n: p.grad.numpy() for n, p in net.named_parameters() if p.grad is not None}
+        res = tc.summarise(grads)
+        res["loss"] = np.float64(loss.item())
+        res["pred_rgb"] = pred.detach().numpy().reshape(-1, 3)
+        res["counter"] = counter
+        res["grad_names"] = np.array(sorted(grads))
+        np.savez_compressed(os.path.join(HERE, "train_step.npz" if phase == "head" else "train_step_torso.npz"), **res)
+        print(phase, "loss", float(loss.detach()), "counter", counter.tolist(), "tensors with a gradient:", len(grads))
+        for n in tc.TABLES:
+            if n + "/norm" in res:
+                print("  ", n, "norm", float(res[n + "/norm"]), "nonzero rows", int(res[n + "/nonzero_rows"]))
 
 
 if __name__ == "__main__":

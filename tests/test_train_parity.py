@@ -15,35 +15,39 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "rad-nerf_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-GOLD = os.path.join(ROOT, "tests", "golden", "train_step.npz")
-TABLES = ("encoder.embeddings", "encoder_ambient.embeddings")
+GOLDS = {"head": os.path.join(ROOT, "tests", "golden", "train_step.npz"), "torso": os.path.join(ROOT, "tests", "golden", "train_step_torso.npz")}
+TABLES = ("encoder.embeddings", "encoder_ambient.embeddings", "torso_encoder.embeddings")
 
 
-def _step(device, ops=None):
+def _step(device, ops=None, phase="head"):
     import train_case as tc
     from network_case import fill_parameters
     from radnerf_b200.model import NeRFNetwork, Options
-    from radnerf_b200.train import head_loss
-    net = NeRFNetwork(Options(torso=False, smooth_lips=False, fp16=False, exp_eye=True), ops=ops).to(device)
+    from radnerf_b200.train import head_loss, torso_loss
+    torso = phase == "torso"
+    net = NeRFNetwork(Options(torso=torso, smooth_lips=False, fp16=False, exp_eye=True), ops=ops).to(device)
     fill_parameters(net)
     if ops is not None:   # the CPU port: the device's level scales, as in the golden run
         scales = np.load(os.path.join(ROOT, "tests", "golden", "grid_g3_f32.npz"))["scales"]
-        for e in (net.encoder, net.encoder_ambient):
+        for e in ([net.encoder, net.encoder_ambient] + ([net.torso_encoder] if torso else [])):
             e.device_scales = scales
-    tc.install_head_occupancy(net)
+    tc.install_occupancy(net, torso=torso)
     net.train()
     b = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in tc.batch().items()}
     out = net.render(b["rays_o"], b["rays_d"], b["auds"], b["bg_coords"], b["poses"], eye=b["eye"], index=b["index"],
                      bg_color=b["bg_color"], perturb=True, force_all_rays=False, **net.opt.render_kwargs())
-    loss = head_loss(out, b["rgb"], b["face_mask"], tc.lambda_amb())       # nerf/utils.py:749, 783-806
+    if torso:
+        loss, pred = torso_loss(out, b["bg_torso_color"]), out["torso_color"]      # nerf/utils.py:730, 744-749, 787-791
+    else:
+        loss, pred = head_loss(out, b["rgb"], b["face_mask"], tc.lambda_amb()), out["image"]   # nerf/utils.py:749, 783-806
     loss.backward()
     grads = {n: p.grad.detach().float().cpu().numpy() for n, p in net.named_parameters() if p.grad is not None}
-    return float(loss), out["image"].detach().float().cpu().numpy().reshape(-1, 3), net.step_counter[0].cpu().numpy(), grads
+    return float(loss.detach()), pred.detach().float().cpu().numpy().reshape(-1, 3), net.step_counter[0].cpu().numpy(), grads
 
 
-def _errors(loss, image, counter, grads):
+def _errors(loss, image, counter, grads, phase="head"):
     """every deviation from the golden step, relative to the scale of its tensor"""
-    g = np.load(GOLD)
+    g = np.load(GOLDS[phase])
     e = {"names_equal": sorted(grads) == list(g["grad_names"]), "counter_equal": bool(np.array_equal(counter, g["counter"])),
          "loss": abs(loss - float(g["loss"])), "image": float(np.abs(image - g["pred_rgb"]).max()), "grad": {}, "table": {}}
     for name, got in grads.items():
@@ -73,15 +77,19 @@ def _check(e, tol, loss_tol, image_tol, rows_tol):
         assert t["norm"] <= tol and t["colsum"] <= 50 * tol and t["nonzero_rows"] <= rows_tol, (name, t)
 
 
-def test_training_step_cpu_port_matches_the_reference_classes():
+@pytest.mark.parametrize("phase", ["head", "torso"])
+def test_training_step_cpu_port_matches_the_reference_classes(phase):
+    """head phase: 35 tensors receive a gradient (tables, MLPs, audio nets, individual codes); torso phase (`--torso`): the 8
+    tensors of the torso branch (2-D torso grid through its input gradient, deformation MLP, torso MLP, torso codes)"""
     from oracle import cpu_backend
     import train_case as tc
     cpu_backend.TRAIN_NOISE = tc.noise()
     try:
-        loss, image, counter, grads = _step("cpu", cpu_backend.CPUOps(train=True))
+        loss, image, counter, grads = _step("cpu", cpu_backend.CPUOps(train=True), phase)
     finally:
         cpu_backend.TRAIN_NOISE = None
-    _check(_errors(loss, image, counter, grads), tol=1e-6, loss_tol=1e-7, image_tol=1e-6, rows_tol=0.0)
+    assert len(grads) == (35 if phase == "head" else 8)
+    _check(_errors(loss, image, counter, grads, phase), tol=1e-6, loss_tol=1e-7, image_tol=1e-6, rows_tol=0.0)
 
 
 @pytest.mark.gpu

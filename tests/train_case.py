@@ -17,13 +17,24 @@ def lambda_amb():
     return min(GLOBAL_STEP / ITERS, 1.0) * LAMBDA_AMB
 
 
-def install_head_occupancy(net):
+TABLES = ("encoder.embeddings", "encoder_ambient.embeddings", "torso_encoder.embeddings")
+
+
+def install_occupancy(net, torso=False):
     from radnerf_b200 import synthetic as syn
     grid = syn.head_density_grid(128, semi_axes=(0.34, 0.24, 0.37))
     with torch.no_grad():
         net.density_grid.copy_(torch.from_numpy(grid).to(net.density_grid.device))
         net.mean_density = float(np.clip(grid, 0, None).mean())
         net.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, min(net.mean_density, net.density_thresh))).to(net.density_bitfield.device))
+        if torso:
+            tg = syn.torso_density_grid(128)
+            net.density_grid_torso.copy_(torch.from_numpy(tg).to(net.density_grid_torso.device))
+            net.mean_density_torso = float(tg.mean())
+
+
+def install_head_occupancy(net):
+    install_occupancy(net, torso=False)
 
 
 def batch():
@@ -31,6 +42,7 @@ def batch():
     from radnerf_b200 import synthetic as syn
     b = syn.batch_to(syn.training_batch(HW, HW, N_RAYS, frame_index=FRAME), "cpu")
     b["images"] = b["rgb"]
+    b["bg_torso_color"] = b["rgb"]        # the torso phase's target (nerf/utils.py:730): same synthetic colours
     return b
 
 
@@ -39,7 +51,7 @@ def noise():
     return np.random.default_rng(77).random(N_RAYS, dtype=np.float32)
 
 
-def summarise(named_grads, tables=("encoder.embeddings", "encoder_ambient.embeddings")):
+def summarise(named_grads, tables=TABLES):
     """what the fixture keeps of a set of gradients: small tensors whole; a table as its level-free summary -- the TOP_ROWS rows
     with the largest gradient (indices + values), the column sums and the L2 norm"""
     out = {}
