@@ -19,3 +19,14 @@ def case_inputs():
     from radnerf_b200 import synthetic as syn
     poses = np.stack([syn.orbit_pose(yaw_deg=y, pitch_deg=2.0) for y in (-10.0, 0.0, 10.0)]).astype(np.float32)
     return dict(poses=poses, intrinsics=np.asarray(syn.intrinsics_for(450, 450), np.float32))
+
+
+def torso_case():
+    """state the torso-phase update needs (main.py:210-212 hands the model the dataset's audio features, eye areas and poses):
+    a bank of audio windows, 16 orbit poses, a previous 2-D alpha grid, and the seed of Python's `random`"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rad-nerf_b200"))
+    from radnerf_b200 import synthetic as syn
+    poses = np.stack([syn.orbit_pose(yaw_deg=float(y), pitch_deg=2.0) for y in np.linspace(-10, 10, 16)]).astype(np.float32)
+    return dict(aud_features=torch.from_numpy(syn.audio_feature_bank(64, 44, 16, seed=3)), eye_area=torch.full((64, 1), 0.25),
+                poses=torch.from_numpy(poses), grid0=torch.from_numpy(syn.torso_density_grid(128)) * 0.5, seed=5)

@@ -71,3 +71,41 @@ def test_occupancy_maintenance_cpu_port_matches_the_reference_code():
 @pytest.mark.gpu
 def test_occupancy_maintenance_cuda_matches_the_reference_code():
     _check(*_run("cuda"), exact=False)
+
+
+def test_torso_occupancy_update_cpu_port_matches_the_reference_code():
+    """the TORSO branch of update_extra_state (nerf/renderer.py:455-501) with the real torso network: golden from the reference's
+    own NeRFNetwork(torso=True) on the CPU (tests/golden/make_torso_occupancy_golden.py); our mirror queries all 128^2 cells in
+    one vectorised pass instead of the reference's chunk loop -- same grid (<= 1e-6), same mean density, same mean_count, and the
+    head's density grid is left alone while the torso trains"""
+    import random
+    from network_case import fill_parameters
+    from occupancy_case import torso_case
+    from oracle.cpu_backend import CPUOps
+    from radnerf_b200.model import NeRFNetwork, Options
+    g = np.load(os.path.join(ROOT, "tests", "golden", "occupancy_torso.npz"))
+    m = NeRFNetwork(Options(torso=True, smooth_lips=False, fp16=False, exp_eye=True), ops=CPUOps())
+    fill_parameters(m)
+    scales = np.load(os.path.join(ROOT, "tests", "golden", "grid_g3_f32.npz"))["scales"]
+    for e in (m.encoder, m.encoder_ambient, m.torso_encoder):
+        e.device_scales = scales
+    c = torso_case()
+    m.aud_features, m.eye_area, m.poses = c["aud_features"], c["eye_area"], c["poses"]
+    m.density_grid_torso.copy_(c["grid0"])
+    head_before = m.density_grid.clone()
+    m.local_step = 2
+    m.step_counter[:2, 0] = torch.tensor([700, 901], dtype=torch.int32)
+    orig = torch.rand_like
+    torch.rand_like = lambda t, **kw: torch.full_like(t, 0.5)
+    random.seed(c["seed"])
+    try:
+        m.update_extra_state()
+        g1, md1, mc = m.density_grid_torso.clone(), m.mean_density_torso, m.mean_count
+        m.update_extra_state()
+    finally:
+        torch.rand_like = orig
+    assert np.abs(g1.numpy() - g["grid_after_1"]).max() <= 1e-6
+    assert np.abs(m.density_grid_torso.numpy() - g["grid_after_2"]).max() <= 1e-6
+    assert abs(md1 - float(g["mean_density_1"])) <= 1e-6 and abs(m.mean_density_torso - float(g["mean_density_2"])) <= 1e-6
+    assert mc == int(g["mean_count"]) == 800 and m.local_step == 0
+    assert torch.equal(m.density_grid, head_before)
