@@ -4,6 +4,10 @@
     ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \\
         --log-file gpurun_out/train_launches.csv python tools/train_profile.py
     python tools/launch_summary.py gpurun_out/train_launches.csv profiles/rNN_launches_train_step_summary.txt "<note>"
+    # one kernel in depth, e.g. the table backward (3-D: L2-atomic bound at 6 % of HBM peak in round 1):
+    ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:grid_backward \
+        -o gpurun_out/prof_grid_backward_rNN python tools/train_profile.py
+    python tools/ncu_summary.py gpurun_out/prof_grid_backward_rNN.ncu-rep profiles/rNN_grid_backward_ncu_full.json
 
 Setup as tools/train_bench.py (BASELINE configs[3]: 2^16 rays, fp16 autocast, FusedAdam tail): 16 cold steps, the first
 occupancy update, 4 steady steps, then the bracketed step."""
