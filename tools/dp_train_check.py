@@ -71,8 +71,18 @@ if world > 1:
                 print(f"[rank {rank}] grad mismatch {n}: {err:.3e} vs scale {ref:.3e}")
     model.zero_grad(set_to_none=True)
 
-for i in range(3):
+# steady state as in a real run (tools/train_bench.py): 16 steps with unknown mean_count, the first occupancy update -- run so
+# that the replicas stay identical (same seed on every rank, max-reduced counters) -- then the timed steps
+from radnerf_b200.train import update_extra_state_replicated
+model.aud_features = torch.from_numpy(syn.audio_feature_bank(600, 44, 16, seed=0))
+model.eye_area = torch.full((600, 1), 0.25)
+for i in range(16 if os.environ.get("REGIME", "steady") == "steady" else 3):
     train_step(model, batches[i % 4], opt, scaler, sync)
+if os.environ.get("REGIME", "steady") == "steady":
+    with torch.autocast("cuda", dtype=torch.float16):
+        update_extra_state_replicated(model)
+    for i in range(4):
+        train_step(model, batches[i % 4], opt, scaler, sync)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
@@ -95,7 +105,7 @@ if world > 1:
             same = False
             if rank == 0: print("replicas diverged in", n)
 if rank == 0:
-    print(json.dumps({"world": world, "rays_per_rank": n_rays, "ms_per_step": float(ms.item()),
+    print(json.dumps({"world": world, "rays_per_rank": n_rays, "regime": os.environ.get("REGIME", "steady"), "mean_count": int(model.mean_count), "ms_per_step": float(ms.item()),
                       "rays_per_s_total": world * n_rays / (float(ms.item()) / 1e3), "loss": float(loss),
                       "allreduce_bytes_per_step": None if sync is None else sync.bytes_last,
                       "synced_grad_equals_mean_of_local": ok_grad, "replicas_identical_after_training": same}))
