@@ -154,3 +154,28 @@ def test_streamed_frames_from_the_device_ring_equal_frames_from_host_windows():
     for i, (a, b) in enumerate(zip(*images)):
         assert torch.equal(a, b), i
     assert not torch.equal(images[1][3], images[1][20])
+
+
+def test_window_book_random_schedules_against_the_oracle_ring():
+    """property check over random ring geometries and write/read schedules (ring sizes from one window up, writes of ragged
+    lengths at arbitrary times): host bookkeeping + the kernel's contract == the restated reference, window for window"""
+    from oracle.feature_ring import Ring
+    from radnerf_b200.audio_ring import WindowBook
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        slots, context, dim = int(rng.integers(1, 6)), int(rng.integers(4, 40)), int(rng.integers(1, 9))
+        if slots * context < 16:
+            slots = -(-16 // context)
+        size = slots * context
+        ref, book = Ring(slots, context, dim), WindowBook(size)
+        queue, snaps, slot = np.zeros((size, dim), np.float32), np.zeros((8, 16, dim), np.float32), 0
+        for step in range(int(rng.integers(20, 120))):
+            if rng.random() < 0.3:
+                feats = rng.standard_normal((int(rng.integers(1, context + 1)), dim)).astype(np.float32)
+                ref.write(feats)
+                queue[slot * context: slot * context + feats.shape[0]] = feats
+                slot = (slot + 1) % slots
+            else:
+                start, snapshot, fresh = book.advance()
+                got = _emulated_kernel(queue, snaps, start, snapshot, fresh)
+                assert np.array_equal(got, ref.next_window()), (trial, step, slots, context)

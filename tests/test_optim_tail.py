@@ -238,3 +238,24 @@ def test_param_ema_matches_the_oracle_and_restores(oracle):
     assert all(torch.equal(p, s) for p, s in zip(params, ema.shadow_params))
     ema.restore()
     assert all(torch.equal(p, l) for p, l in zip(params, live))
+
+
+def test_every_chunk_finds_its_tensor():
+    """the kernel's per-CTA binary search over `first_chunk` (csrc/optim_tail.cu find_tensor), restated: for random tensor sizes
+    including empty tensors, chunk c belongs to the tensor whose chunk range contains it"""
+    from radnerf_b200 import optim
+    rng = np.random.default_rng(9)
+    for _ in range(200):
+        sizes = [int(s) for s in rng.choice([0, 1, 5, 4095, 4096, 4097, 10000, 70001], size=int(rng.integers(1, 12)))]
+        first, total = optim.chunk_layout(sizes)
+        owner = []
+        for t, n in enumerate(sizes):
+            owner += [t] * ((n + optim.CHUNK - 1) // optim.CHUNK)
+        assert len(owner) == total
+        for c in range(total):
+            lo, hi = 0, len(sizes)                      # last tensor with first_chunk <= c
+            while hi - lo > 1:
+                mid = (lo + hi) >> 1
+                lo, hi = (mid, hi) if first[mid] <= c else (lo, mid)
+            assert lo == owner[c], (sizes, c)
+            assert 0 <= (c - first[lo]) * optim.CHUNK < sizes[lo]
