@@ -186,6 +186,11 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
+    if not args.no_train:
+        try:
+            line["train"] = cpu_training_rate()
+        except Exception as e:  # noqa: BLE001
+            line["train"] = {"unavailable": repr(e)[:200]}
     # context, next to the CPU number this arm is about: the reference's OWN CUDA extensions (oracle/_ref, built from
     # /root/reference by oracle/build_ref.py) driven in the reference's op order on this box's GPU, if there is one
     if not args.no_ref_cuda:
@@ -444,6 +449,38 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_training_rate(n_rays=65536, steps=2, threads=None):
+    """BASELINE configs[3] on the host cores: one head training step of the CPU port (oracle C kernels under autograd +
+    torch-CPU layers + torch.optim.Adam, fp32; the reference has no CPU implementation of its own).  A bounded sample: one
+    warm-up step and `steps` timed steps of the full 2^16-ray batch (~1-2 s each), cold regime only (mean_count unknown)."""
+    import torch
+    from oracle import cpu_backend
+    from oracle import oracle as O
+    from radnerf_b200 import synthetic as syn
+    from radnerf_b200.model import NeRFNetwork, Options
+    from radnerf_b200.train import train_step
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    O.set_num_threads(threads)
+    torch.manual_seed(0)
+    m = NeRFNetwork(Options(torso=False, fp16=False, exp_eye=True), ops=cpu_backend.CPUOps(train=True))
+    grid = syn.head_density_grid(128, semi_axes=(0.34, 0.24, 0.37))
+    m.density_grid.copy_(torch.from_numpy(grid))
+    m.mean_density = float(np.clip(grid, 0, None).mean())
+    m.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, min(m.mean_density, m.density_thresh))))
+    b = syn.batch_to(syn.training_batch(512, 512, n_rays, frame_index=0), "cpu")
+    opt = torch.optim.Adam(m.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15)
+    train_step(m, b, opt, None, None)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = train_step(m, b, opt, None, None)
+    dt = (time.perf_counter() - t0) / steps
+    samples = float(m.step_counter[1:1 + steps, 0].float().mean())
+    return {"workload": "RAD-NeRF head training step (BASELINE configs[3]): %d rays/batch on the CPU port, fp32, torch.optim.Adam" % n_rays,
+            "ms_per_step": dt * 1e3, "rays_per_s": n_rays / dt, "samples_per_step": samples, "msamples_per_s": samples / dt / 1e6,
+            "cores": threads, "kind": "port", "steps": steps, "loss": float(loss)}
 
 
 def training_rate(dev, n_rays=65536, steps=48, ops=None, tail="fused", graphed=False):
