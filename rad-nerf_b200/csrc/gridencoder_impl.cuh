@@ -467,22 +467,24 @@ grid_backward_shared_cell_kernel(const T* __restrict__ grad, const float* __rest
             const LevelMeta m = meta[l];
             G* __restrict__ gt = grad_table + (size_t)m.offset * C;
             Cell<D> cell = {};
-            uint32_t key = FULL;                            // never a real cell: coordinates stay below 2^16
+            uint32_t key = FULL;                            // never a real cell: packed coordinates stay below 2^16 each
+            const bool packable = m.resolution < 65535u;    // warp-uniform; a wider level (not a RAD-NeRF geometry) keeps per-lane atomics
             if (valid) {
                 cell = locate<D>(x, m, align_corners != 0, interp);
-                key = cell.pg[0] | (cell.pg[1] << 16);
+                if (packable) key = cell.pg[0] | (cell.pg[1] << 16);
             }
+            const bool groupable = valid && packable;
             const uint32_t peers = __match_any_sync(FULL, key);
-            const bool leader = valid && lane == (uint32_t)(__ffs(peers) - 1);
+            const bool leader = groupable && lane == (uint32_t)(__ffs(peers) - 1);
             uint32_t leaders = __ballot_sync(FULL, leader);
-            const uint32_t n_valid = __popc(__ballot_sync(FULL, valid));
+            const uint32_t n_valid = __popc(__ballot_sync(FULL, groupable));
             const uint32_t n_groups = __popc(leaders);
             if (n_groups <= kMaxGroups && n_groups < n_valid) {     // warp-uniform: few cells, at least one shared
                 while (leaders) {
                     const int src = __ffs(leaders) - 1;
                     leaders &= leaders - 1;
                     const uint32_t group_key = __shfl_sync(FULL, key, src);   // outside the `&&`: every lane must execute the shuffle
-                    const bool mine = valid && key == group_key;
+                    const bool mine = groupable && key == group_key;
                     float v[4][C];
 #pragma unroll
                     for (uint32_t k = 0; k < 4; ++k) {
