@@ -354,6 +354,19 @@ void rn_debug_set_while_node(int on);
 /* one 128 x N x K fp16 GEMM tile through the hand-written tcgen05/TMEM path (out = A @ W^T, fp32 accumulate);
  * A [128,K] fp16 row-major, W [N,K] fp16 row-major.  Validates descriptors/layouts in isolation. */
 int rn_selftest_umma(const void* A, const void* W, float* out, uint32_t K, uint32_t N, void* stream);
+/* the weight-gradient contraction of the fused training step: out[m,n] = passes * sum_s X[s,m] * Y[s,n] with both operands read
+ * MN-major from interleaved [128 x K] tiles (samples = the MMA's K dimension); rows m >= Kx of out [128,Ky] are undefined. */
+int rn_selftest_umma_mn(const void* X, const void* Y, float* out, uint32_t Kx, uint32_t Ky, uint32_t passes, void* stream);
+
+/* table-gradient scatter of a 3-D, 2-feature, linearly interpolated grid (replaces kernel_grid_backward,
+ * gridencoder.cu:247-339, for the head's spatial encoder): grad [B, L*2] (RN_LAYOUT_BLC) of `dtype`, inputs [B,3] in [0,1],
+ * grad_table fp32 [rows,2] accumulated INTO.  variant: bit0 merge the two z-corners of levels that never index z + pair the
+ * x-corners into 16-byte atomics, bit1 segmented warp reduction of consecutive samples in one cell on levels < agg_levels,
+ * bit2 accumulate the first priv_levels (dense) levels, priv_rows rows in total, in shared memory.  level_mask bit l = do level l.
+ * rn_grid_encode_backward dispatches here with the production settings. */
+int rn_grid_backward3(const void* grad, const float* inputs, const int32_t* offsets, float* grad_table, uint32_t B, uint32_t L,
+                      float S, uint32_t H, uint32_t gridtype, uint32_t dtype, uint32_t variant, uint32_t level_mask,
+                      uint32_t agg_levels, uint32_t priv_levels, uint32_t priv_rows, void* stream);
 
 #ifdef __cplusplus
 }

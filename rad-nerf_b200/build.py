@@ -36,7 +36,8 @@ def needs_build():
 
 def compile_one(src, verbose):
     obj = os.path.join(OBJ, src[:-3] + ".o")
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu")] + [os.path.join(CSRC, src)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu")] + [os.path.join(CSRC, src),
+                                                                                         os.path.join(HERE, "..", "include", "radnerf_b200.h")]
     if os.path.exists(obj) and all(os.path.getmtime(d) < os.path.getmtime(obj) for d in deps):
         return obj
     cmd = [NVCC] + COMMON + EXTRA.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]

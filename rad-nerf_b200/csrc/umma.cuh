@@ -66,6 +66,36 @@ __device__ __forceinline__ void gemm_issue(uint32_t tmem_d, uint32_t a_smem, uin
     }
 }
 
+// ---- MN-major ("transposed") operands ---------------------------------------------------------------------------------
+// The SAME interleaved [rows x Kf] tile read with rows as the MMA's K dimension and the Kf features as its M (or N) dimension:
+// a core matrix is then 8 K-rows x 16 bytes of 8 consecutive M/N elements, which is exactly how the tile already sits in shared
+// memory.  cute's canonical form (mma_traits_sm100.hpp, make_umma_desc<Major::MN>, INTERLEAVE, units of 16 bytes):
+//      ((1,n),(8,k)) : ((X,SBO),(1,LBO))   ->   SBO = stride between core matrices along M/N = 128 bytes,
+//                                               LBO = stride between 8-row groups along K   = 16 * Kf bytes
+// One tcgen05.mma consumes K = 16 rows = two 8-row groups; k-step s starts at base + s * 2 * LBO.
+// This is how the weight gradient dW = dZ^T A runs on tensor cores without transposing anything: samples are K.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t Kf) {
+    const uint32_t lbo = 16u * Kf;
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(LBO_BYTES >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// D[128 x N] (+)= X^T Y over `rows` tile rows (a multiple of 16): X = interleaved [rows x Kx] tile whose feature columns
+// [mx0, mx0 + 128) become D's rows (columns past Kx read whatever follows in shared memory: those D rows are garbage and must be
+// ignored), Y = interleaved [rows x Ky] tile whose columns [ny0, ny0 + N) become D's columns.
+__device__ __forceinline__ void gemm_issue_mn(uint32_t tmem_d, uint32_t x_smem, uint32_t Kx, uint32_t mx0, uint32_t y_smem, uint32_t Ky,
+                                              uint32_t ny0, uint32_t N, uint32_t rows, bool accumulate) {
+    const uint32_t idesc = make_idesc_f16(128, N) | (1u << 15) | (1u << 16);   // A and B both MN-major
+    for (uint32_t s = 0; s < rows; s += 16) {
+        const uint64_t da = make_desc_mn(x_smem + (mx0 >> 3) * LBO_BYTES + (s >> 3) * 16u * Kx, Kx);
+        const uint64_t db = make_desc_mn(y_smem + (ny0 >> 3) * LBO_BYTES + (s >> 3) * 16u * Ky, Ky);
+        mma_f16_ss(tmem_d, da, db, idesc, (accumulate || s > 0) ? 1u : 0u);
+    }
+}
+
 __device__ __forceinline__ void commit(uint64_t* mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
 }

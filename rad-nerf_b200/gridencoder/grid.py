@@ -50,8 +50,7 @@ class GridEncodeFn(torch.autograd.Function):
     def forward(ctx, x, table, offsets, per_level_scale, base_resolution, want_input_grad=False, gridtype=0, align_corners=False,
                 interpolation=0):
         abi.require_cuda(x, table, offsets)
-        if x.dtype != torch.float32:
-            raise RuntimeError("GridEncoder: inputs must be float32 (coordinates are never reduced in precision)")
+        x = x.float()   # coordinates are evaluated in fp32 whatever arrives (the reference's grid.py:35 `inputs.float()` under autocast)
         param_dtype = table.dtype
         if torch.is_autocast_enabled() and table.shape[1] % 2 == 0:   # the reference's own autocast rule (grid.py:41-44)
             table = table.half()

@@ -39,6 +39,8 @@ _PROTOS = {
     "rn_scatter_rows_to_peers": [_vp, _vp, _u32, _u32, _vp, _u32, _vp],
     "rn_image_to_uint8": [_vp, _vp, C.c_uint64, _vp],
     "rn_selftest_umma": [_vp, _vp, _vp, _u32, _u32, _vp],
+    "rn_selftest_umma_mn": [_vp, _vp, _vp, _u32, _u32, _u32, _vp],
+    "rn_grid_backward3": [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp],
 }
 
 _lib = None
@@ -98,7 +100,21 @@ def call(name, *args):
     """Invoke ABI function `name` on torch's current stream: tensors become device pointers (None -> NULL), scalars pass
     through, the stream is appended, a non-zero return code raises RuntimeError with the library's message."""
     fn = getattr(lib(), name)
-    check(fn(*[ptr(a) if (a is None or torch.is_tensor(a)) else a for a in args], cur_stream()), name)
+    dev = None
+    for a in args:   # every tensor argument lives on ONE device; the launch goes to that device's current stream
+        if torch.is_tensor(a):
+            if not a.is_cuda:
+                raise RuntimeError("radnerf_b200.%s: expected CUDA tensors (this library has no CPU path)" % name)
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise RuntimeError("radnerf_b200.%s: tensor arguments on different devices (%s, %s)" % (name, dev, a.device))
+    argv = [ptr(a) if (a is None or torch.is_tensor(a)) else a for a in args]
+    if dev is None or dev.index == torch.cuda.current_device():
+        check(fn(*argv, cur_stream()), name)
+    else:
+        with torch.cuda.device(dev):
+            check(fn(*argv, cur_stream()), name)
 
 
 def rows(t, width=None, dtype=torch.float32):

@@ -179,6 +179,11 @@ class FusedAdam(torch.optim.Optimizer):
                                              abi.ptr(_scalar_f32(scale, device)), abi.ptr(_scalar_f32(found, device)), flags,
                                              abi.cur_stream()), "rn_adam_step")
         self._grads_are_zero = self.zero_grads
+        # the kernel updated parameters, moments (and zeroed gradients) through raw pointers: advance the version counters so
+        # that consumers caching derived data per (pointer, version) -- radnerf_b200.frame.FusedShared's fp16 tables and weight
+        # blobs -- see the step
+        touched = [p for group in self.param_groups for p in group["params"] if p.grad is not None]
+        torch.autograd.graph.increment_version(touched)
         return loss
 
 

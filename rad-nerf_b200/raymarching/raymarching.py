@@ -103,6 +103,11 @@ class PackbitsFn(torch.autograd.Function):
         n_bytes = g.shape[0] * g.shape[1] // 8
         bits = bitfield if bitfield is not None else torch.empty(n_bytes, dtype=torch.uint8, device=g.device)
         abi.call("rn_packbits", g, n_bytes, float(thresh), bits)      # bit i of byte n <-> cell 8n + i
+        if bitfield is not None:
+            # the kernel wrote through the raw pointer: tell autograd (and everything that caches on `_version`, e.g. the fused
+            # renderer's occupied-cell box) that the caller's tensor changed
+            ctx.mark_dirty(bitfield)
+            torch.autograd.graph.increment_version(bitfield)
         return bits
 
 

@@ -1,0 +1,87 @@
+"""Round-2 kernels in isolation: the MN-major tcgen05 contraction (weight gradients) and the restructured 3-D table backward."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("Kx,Ky,passes", [(16, 16, 1), (32, 64, 1), (64, 64, 1), (64, 16, 1), (80, 64, 1), (64, 80, 3), (128, 128, 2), (32, 48, 5)])
+def test_tcgen05_mn_major_contraction_matches_torch_fp32(Kx, Ky, passes):
+    """out[m, n] = passes * sum_s X[s, m] Y[s, n]: both operands are the SAME interleaved tiles the forward writes, read MN-major
+    (samples = the MMA's K dimension), accumulated over `passes` issues in TMEM -- vs a plain PyTorch fp32 matmul."""
+    from radnerf_b200 import abi as L
+    g = torch.Generator(device="cpu").manual_seed(Kx * 1000 + Ky)
+    X = torch.randn(128, Kx, generator=g).half().to(DEV)
+    Y = torch.randn(128, Ky, generator=g).half().to(DEV)
+    out = torch.full((128, Ky), float("nan"), device=DEV)
+    L.check(L.lib().rn_selftest_umma_mn(L.ptr(X), L.ptr(Y), L.ptr(out), Kx, Ky, passes, L.cur_stream()))
+    torch.cuda.synchronize()
+    ref = passes * (X.float().t() @ Y.float())
+    got = out[:Kx]
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()) * passes
+
+
+def _bwd3_case(B, seed, clustered):
+    from gridencoder import GridEncoder
+    enc = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=16, desired_resolution=2048,
+                      gridtype='tiled').to(DEV)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    if clustered:   # rays: runs of 16 consecutive samples 0.0135 apart (in [0,1] units), like march_rays_train's packing
+        o = torch.rand(B // 16, 1, 3, generator=g) * 0.3 + 0.3
+        d = torch.nn.functional.normalize(torch.randn(B // 16, 1, 3, generator=g), dim=-1)
+        x = (o + d * torch.arange(16).view(1, 16, 1) * 0.0135).reshape(-1, 3)
+    else:
+        x = torch.rand(B, 3, generator=g)
+    x[::97] = 1.5   # out-of-range samples are skipped
+    grad = (torch.randn(x.shape[0], 32, generator=g) * 0.1).half()
+    return enc, x.to(DEV).contiguous(), grad.to(DEV).contiguous()
+
+
+@pytest.mark.parametrize("clustered", [False, True])
+@pytest.mark.parametrize("variant", [1, 3, 5, 7])
+def test_grid_backward3_variants_match_the_generic_kernel(variant, clustered):
+    from radnerf_b200 import abi
+    enc, x, grad = _bwd3_case(16 * 4000 + 16, 7, clustered)
+    B, rows = x.shape[0], enc.embeddings.shape[0]
+    S, H = float(np.log2(enc.per_level_scale)), int(enc.base_resolution)
+    ref = torch.zeros(rows, 2, device=DEV, dtype=torch.float64)
+    # double-precision restatement of the scatter with torch ops, per level
+    offs = enc.offsets.cpu().numpy()
+    xv = x.double()
+    ok = ((xv >= 0) & (xv <= 1)).all(1)
+    scales = torch.empty(16, device=DEV)
+    abi.call("rn_grid_level_geometry", S, H, 16, scales, None)
+    for l in range(16):
+        sc = float(scales[l].item())
+        res = int(np.ceil(sc)) + 1
+        size = int(offs[l + 1] - offs[l])
+        pos = (x * sc + 0.5)        # fp32, as the kernel
+        pg = pos.floor()
+        fr = (pos - pg).double()
+        pg = pg.long()
+        s1, s2 = res + 1, (res + 1) ** 2
+        use = [True, s1 <= size, s2 <= size]
+        for k in range(8):
+            w = torch.ones(B, device=DEV, dtype=torch.float64)
+            idx = torch.zeros(B, device=DEV, dtype=torch.long)
+            for d, st in enumerate((1, s1, s2)):
+                bit = (k >> d) & 1
+                w = w * (fr[:, d] if bit else 1 - fr[:, d])
+                if use[d] and all(use[:d + 1]):
+                    idx = idx + (pg[:, d] + bit) * st
+            idx = idx % size + int(offs[l])
+            contrib = (w[:, None] * grad[:, 2 * l:2 * l + 2].double())[ok]
+            ref.index_add_(0, idx[ok], contrib)
+    out = torch.zeros(rows, 2, device=DEV)
+    sizes = offs[1:] - offs[:-1]
+    abi.check(abi.lib().rn_grid_backward3(abi.ptr(grad), abi.ptr(x), abi.ptr(enc.offsets), abi.ptr(out), B, 16, S, H, 1, 1, variant, 0xffff, 6,
+                                          2, int(sizes[0] + sizes[1]), abi.cur_stream()))
+    gen = torch.zeros(rows, 2, device=DEV)
+    abi.call("rn_grid_encode_backward", grad, x, None, enc.offsets, gen, B, 3, 2, 16, S, H, None, None, 1, 0, 0, 1, 1, 0)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (gen.double() - ref).abs().max().item() <= 1e-5 * scale      # the generic kernel vs the double restatement
+    assert (out.double() - ref).abs().max().item() <= 1e-5 * scale, variant
