@@ -213,6 +213,10 @@ typedef struct rn_conditioning_desc {
     const void* w_def1; const void* w_tor1;                        /* fp16 [64,104] [32,136] or NULL */
     const float* pose6; const float* ind_torso;
     float* torso_consts;         /* out [64+32] */
+    const float* pose44;         /* optional device [16] cam2world: when given, the 6-vector (XYZ Euler angles, translation) of the
+                                    reference's convert_poses (nerf/utils.py:230-237) is computed ON THE DEVICE from it and `pose6`
+                                    is ignored; NULL = use pose6 */
+    float* pose6_out;            /* optional device [6]: receives the 6-vector the kernel used (parity checks) */
 } rn_conditioning_desc;
 
 typedef struct rn_frame_head_desc {
@@ -364,6 +368,8 @@ int rn_selftest_umma_mn(const void* X, const void* Y, float* out, uint32_t Kx, u
  * x-corners into 16-byte atomics, bit1 segmented warp reduction of consecutive samples in one cell on levels < agg_levels,
  * bit2 accumulate the first priv_levels (dense) levels, priv_rows rows in total, in shared memory.  level_mask bit l = do level l.
  * rn_grid_encode_backward dispatches here with the production settings. */
+#define RN_BWD3_PRODUCTION 3u   /* z-merge + x-pair + segmented warp aggregation (profiles/r02_bwd3_variants_*.json) */
+#define RN_BWD3_AGG_LEVELS 6u
 int rn_grid_backward3(const void* grad, const float* inputs, const int32_t* offsets, float* grad_table, uint32_t B, uint32_t L,
                       float S, uint32_t H, uint32_t gridtype, uint32_t dtype, uint32_t variant, uint32_t level_mask,
                       uint32_t agg_levels, uint32_t priv_levels, uint32_t priv_rows, void* stream);

@@ -261,13 +261,32 @@ audio_frame_kernel(const __grid_constant__ AudioParams p, const __grid_constant_
     RN_STAMP(7)
     // ---- hoisted terms of the torso: [freq(pose6) (54) | individual code (8)], zero-padded to 64
     if (p.w_def1) {
+        // the head pose as (XYZ Euler angles, translation): taken from the caller, or derived here from the 4x4 cam2world
+        // (convert_poses -> matrix_to_euler_angles(R, 'XYZ'), nerf/utils.py:113-170, 230-237: for R = Rx(a) Ry(b) Rz(c),
+        //  a = atan2(-R12, R22), b = asin(R02), c = atan2(-R01, R00))
+        __shared__ float s_pose6[6];
+        if (tid < 6) {
+            float v;
+            if (p.pose44) {
+                const float* P = p.pose44;
+                if (tid == 0) v = atan2f(-__ldg(P + 6), __ldg(P + 10));
+                else if (tid == 1) v = asinf(__ldg(P + 2));
+                else if (tid == 2) v = atan2f(-__ldg(P + 1), __ldg(P + 0));
+                else v = __ldg(P + 4 * (tid - 3) + 3);
+            } else {
+                v = __ldg(p.pose6 + tid);
+            }
+            s_pose6[tid] = v;
+            if (p.pose6_out) p.pose6_out[tid] = v;
+        }
+        __syncthreads();
         if (tid < 54) {
             const uint32_t c = tid;
             float v;
-            if (c < 6) v = __ldg(p.pose6 + c);
+            if (c < 6) v = s_pose6[c];
             else {
                 const uint32_t col = c / 6 - 1, d = c % 6, fr = col / 2;
-                v = __sinf(scalbnf(__ldg(p.pose6 + d), (int)fr) + (float)(col % 2) * 1.5707963705062866f);
+                v = __sinf(scalbnf(s_pose6[d], (int)fr) + (float)(col % 2) * 1.5707963705062866f);
             }
             s_vec[c] = __float2half_rn(v);
         } else if (tid < 64) {

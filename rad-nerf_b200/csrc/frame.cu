@@ -27,7 +27,7 @@ extern "C" int rn_frame_conditioning(const rn_conditioning_desc* d, void* stream
     RN_REQUIRE(!d->auds || (d->F >= 1 && d->F <= 8 && d->Cin >= 1 && d->Cin <= 44), "auds must be [F<=8, Cin<=44, 16]");
     RN_REQUIRE(!d->auds || d->att == 0 || d->F == 8, "attention needs the 8-frame window");
     RN_REQUIRE(!d->smooth || d->enc_a_state, "lip smoothing needs a state buffer");
-    RN_REQUIRE(!d->w_def1 || (d->w_tor1 && d->pose6 && d->torso_consts), "incomplete torso conditioning");
+    RN_REQUIRE(!d->w_def1 || (d->w_tor1 && (d->pose6 || d->pose44) && d->torso_consts), "incomplete torso conditioning");
     static_assert(sizeof(AudioParams) == sizeof(rn_conditioning_desc), "descriptor mirrors AudioParams");
     AudioParams p;
     memcpy(&p, d, sizeof(p));

@@ -112,6 +112,8 @@ struct AudioParams {
     const float* pose6;      // device [6]
     const float* ind_torso;  // device [8] or null
     float* torso_consts;     // [64 + 32]
+    const float* pose44;     // device [16] or null: derive the 6-vector on the device (convert_poses, nerf/utils.py:230-237)
+    float* pose6_out;        // device [6] or null
 };
 
 int launch_frame_init(const float* rays_o, const float* rays_d, const float* aabb, const float* occ_aabb /*nullable*/, uint32_t N,

@@ -45,6 +45,10 @@ extern "C" int rn_grid_encode_backward(const void* grad, const float* inputs, co
     if (B == 0) return RN_OK;
     RN_REQUIRE(grad && inputs && offsets && grad_embeddings, "null pointer");
     RN_REQUIRE((dy_dx == nullptr) == (grad_inputs == nullptr), "dy_dx and grad_inputs must be given together");
+    // the head's spatial encoder (3-D, 2 features, linear, fp32 target, no input gradient): restructured scatter, csrc/grid_bwd3.cu
+    if (D == 3 && C == 2 && interp == 0 && !align_corners && grad_layout == RN_LAYOUT_BLC && grad_emb_dtype == RN_F32 && !dy_dx && L <= 32)
+        return rn_grid_backward3(grad, inputs, offsets, (float*)grad_embeddings, B, L, S, H, gridtype, dtype, RN_BWD3_PRODUCTION, 0xffffffffu,
+                                 RN_BWD3_AGG_LEVELS, 0, 0, stream);
     const BwdArgs a{grad, inputs, offsets, grad_embeddings, dy_dx, grad_inputs, B, C, L, S, H, gridtype, align_corners,
                     interp, dtype, grad_layout, grad_emb_dtype, (cudaStream_t)stream};
     const int rc = by_dim(D, a, backward_d<2>, backward_d<3>, backward_d<4>, backward_d<5>);

@@ -31,7 +31,8 @@ class ConditioningDesc(C.Structure):
                 ("att_w", _vp * 5), ("att_b", _vp * 5), ("att_fc_w", _vp), ("att_fc_b", _vp),
                 ("enc_a_state", _vp), ("lambda_", _f32),
                 ("w_amb1", _vp), ("w_sig1", _vp), ("w_col1", _vp), ("eye", _vp), ("ind_code", _vp), ("head_consts", _vp),
-                ("w_def1", _vp), ("w_tor1", _vp), ("pose6", _vp), ("ind_torso", _vp), ("torso_consts", _vp)]
+                ("w_def1", _vp), ("w_tor1", _vp), ("pose6", _vp), ("ind_torso", _vp), ("torso_consts", _vp),
+                ("pose44", _vp), ("pose6_out", _vp)]
 
 
 class FrameHeadDesc(C.Structure):
@@ -251,7 +252,9 @@ def _grid_table(enc, packed):
                      first.data_ptr())
 
 
-def conditioning_desc(model, st, auds, eye_t, pose6):
+def conditioning_desc(model, st, auds, eye_t, pose6, pose44=None):
+    """pose44: device [4,4] cam2world -- the kernel then derives the 6-vector itself (the reference's convert_poses on the
+    device) and writes it back into `pose6` (if given) for inspection"""
     an, at = model.audio_net, getattr(model, "audio_att_net", None)
 
     def H(param):  # cached fp16 copy (cleared by refresh_weights when any parameter changes)
@@ -283,7 +286,11 @@ def conditioning_desc(model, st, auds, eye_t, pose6):
     if model.torso:
         cd.w_def1 = H(model.torso_deform_net.net[0].weight)
         cd.w_tor1 = H(model.torso_net.net[0].weight)
-        cd.pose6, cd.ind_torso, cd.torso_consts = pose6.data_ptr(), model.individual_codes_torso.data_ptr(), st.torso_consts.data_ptr()
+        cd.ind_torso, cd.torso_consts = model.individual_codes_torso.data_ptr(), st.torso_consts.data_ptr()
+        if pose44 is not None:
+            cd.pose44, cd.pose6_out = pose44.data_ptr(), _p(pose6)
+        else:
+            cd.pose6 = pose6.data_ptr()
     return cd
 
 
@@ -314,7 +321,7 @@ def _sync_smoothing_state(model, st):
             st.enc_a_state[64] = 1.0
 
 
-def launch_conditioning(model, lane, auds, eye=None, poses=None):
+def launch_conditioning(model, lane, auds, eye=None, poses=None, pose44=None):
     """The conditioning kernel of ONE frame on the current stream, writing lane `lane`'s hoisted-term vectors and advancing
     the shared lip-smoothing state.  Callers that keep several frames in flight (radnerf_b200.stream.FramePipeline) run these
     in frame order on one stream and render the frame with render_frame(..., lane=lane, external_cond=True)."""
@@ -323,16 +330,20 @@ def launch_conditioning(model, lane, auds, eye=None, poses=None):
     _sync_smoothing_state(model, st)
     auds_t = None if auds is None else auds.contiguous().float()
     eye_t = None if eye is None else eye.reshape(-1).float().contiguous()
-    pose6 = poses.reshape(-1).float().contiguous() if model.torso else None
-    st._keep = (auds_t, eye_t, pose6)   # alive until the kernel has run
+    pose6 = poses.reshape(-1).float().contiguous() if (model.torso and poses is not None) else None
+    if model.torso and pose44 is not None:
+        pose44 = pose44.reshape(-1).float().contiguous()   # device-side convert_poses; `pose6` (if any) receives the result
+    else:
+        pose44 = None
+    st._keep = (auds_t, eye_t, pose6, pose44)   # alive until the kernel has run
     # callers that stream frames pass the same (static) buffers every time: build the descriptor once per set of pointers
     key = (None if auds_t is None else (auds_t.data_ptr(), tuple(auds_t.shape)), None if eye_t is None else eye_t.data_ptr(),
-           None if pose6 is None else pose6.data_ptr(), st.shared.generation)
+           None if pose6 is None else pose6.data_ptr(), None if pose44 is None else pose44.data_ptr(), st.shared.generation)
     cache = st.__dict__.setdefault("_cd_cache", {})
     cd = cache.get(key)
     if cd is None:
         cache.clear()
-        cd = cache[key] = conditioning_desc(model, st, auds_t, eye_t, pose6)
+        cd = cache[key] = conditioning_desc(model, st, auds_t, eye_t, pose6, pose44)
     abi.check(abi.lib().rn_frame_conditioning(C.byref(cd), abi.cur_stream()))
     if model.smooth_lips and auds is not None:
         model.enc_a = st.enc_a_state[:64].view(1, 64)

@@ -85,7 +85,7 @@ class FramePipeline:
     def next_lane(self):
         return self.n % self.lanes
 
-    def submit(self, rays_o, rays_d, auds, bg_coords, poses, eye=None, post=None, ready_on=None, static_inputs=False, **kw):
+    def submit(self, rays_o, rays_d, auds, bg_coords, poses, eye=None, post=None, ready_on=None, static_inputs=False, pose44=None, **kw):
         """Enqueue one frame.  The inputs are device tensors that are ready on stream `ready_on` (default: the current
         stream) and stay untouched until the frame has run.  post(out, lane), if given, runs on the lane's stream right
         after the frame (gather, staging, ...).  static_inputs=True: the tensors ARE the input buffers of the lane's captured
@@ -100,7 +100,7 @@ class FramePipeline:
         self.cond_stream.wait_stream(src)
         self.cond_stream.wait_event(self.ev_done[k])   # lane k's previous frame no longer reads its hoisted-term vectors
         with torch.cuda.stream(self.cond_stream):
-            _frame.launch_conditioning(self.model, k, auds, eye, poses)
+            _frame.launch_conditioning(self.model, k, auds, eye, poses, pose44=pose44)
             self.ev_cond[k].record(self.cond_stream)
         if src is not ls:
             ls.wait_stream(src)
@@ -124,13 +124,16 @@ class FramePipeline:
 
 class FrameStreamer:
     def __init__(self, model, H, W, intrinsics, bg_coords, auds_shape, use_eye=True, sharder=None, deliver=True, depth=2,
-                 output="float32", **render_kw):
+                 output="float32", device_pose6=True, **render_kw):
         """bg_coords: [H*W, 2] on the device (this rank's rows if `sharder` splits the frame); auds_shape: e.g. (8, 44, 16);
         deliver=False skips the device->host stage (ranks other than the one that consumes the frames); depth = frames in
         flight (= lanes of the FramePipeline underneath); output="uint8" converts on the device -- the reference's
         `(pred * 255).astype(np.uint8)` -- and copies a quarter of the bytes to the host."""
         assert output in ("float32", "uint8") and (output == "float32" or (H * W * 3) % 16 == 0)
         self.u8 = output == "uint8"
+        # device_pose6: the torso's 6-vector pose (the reference's convert_poses, nerf/utils.py:230-237) is derived from the 4x4
+        # pose inside the conditioning kernel; the [16:22] slot of the input block is then an OUTPUT (host values are ignored)
+        self.device_pose6 = bool(device_pose6)
         self.model, self.kw, self.depth, self.deliver = model, render_kw, depth, deliver
         self.dev = bg_coords.device
         self.sharder = sharder if sharder is not None else FrameSharder(H, W, 1, 0, self.dev)
@@ -216,7 +219,8 @@ class FrameStreamer:
             flat = packed.to(self.dev, non_blocking=True)
             ro, rd = self.raygen(flat[:16].view(4, 4))
             auds, pose6, eye = self._views(flat)
-            self.pipe.submit(ro[None], rd[None], auds, self.bg[None], pose6, eye=eye, post=self._post, **kw)
+            self.pipe.submit(ro[None], rd[None], auds, self.bg[None], pose6, eye=eye, post=self._post,
+                             pose44=flat[:16] if self.device_pose6 else None, **kw)
             self.static[k] = _frame.lane_state(self.model, k).last_static
             if self.static[k] is not None and k == 0:
                 self.bg = self.static[0]["bg_coords"]   # same values, already in place for lane 0: no per-frame copy there
@@ -227,7 +231,7 @@ class FrameStreamer:
                 self.raygen(st["pose"], out=(st["rays_o"], st["rays_d"]))        # rays straight into the graph's inputs
             auds, pose6, eye = self._views(st["flat"])
             self.pipe.submit(st["rays_o"][None], st["rays_d"][None], auds, st["bg_coords"][None], pose6, eye=eye, post=self._post,
-                             ready_on=ls, static_inputs=True, **kw)
+                             ready_on=ls, static_inputs=True, pose44=st["pose"] if self.device_pose6 else None, **kw)
         self.pending.append((k, False))
         self._arm_fast(k)
 
@@ -251,7 +255,8 @@ class FrameStreamer:
             ev.append(e.value)
         auds, pose6, eye = self._views(static["flat"])
         cd = _frame.conditioning_desc(self.model, st, auds.contiguous(), None if eye is None else eye.contiguous(),
-                                      pose6.contiguous() if self.model.torso else None)
+                                      pose6.contiguous() if self.model.torso else None,
+                                      static["pose"].reshape(-1) if (self.model.torso and self.device_pose6) else None)
         s = LaneSubmit()
         s.lane_stream, s.cond_stream, s.copy_stream = self.pipe.streams[k].cuda_stream, self.pipe.cond_stream.cuda_stream, self.copy_stream.cuda_stream
         s.ev_in, s.ev_cond, s.ev_done, s.ev_staged, s.ev_delivered = ev

@@ -58,7 +58,7 @@ def test_grid_backward3_variants_match_the_generic_kernel(variant, clustered):
         sc = float(scales[l].item())
         res = int(np.ceil(sc)) + 1
         size = int(offs[l + 1] - offs[l])
-        pos = (x * sc + 0.5)        # fp32, as the kernel
+        pos = (x.double() * sc + 0.5).float()        # one rounding, as the kernel's fmaf
         pg = pos.floor()
         fr = (pos - pg).double()
         pg = pg.long()

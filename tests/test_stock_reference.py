@@ -25,6 +25,9 @@ CONFIGS = {
     "configs1_head_450": dict(hw=450, torso=False, asr_model="cpierse/wav2vec2-large-xlsr-53-esperanto", dim=44),
     "configs2_head_torso_512": dict(hw=512, torso=True, asr_model="cpierse/wav2vec2-large-xlsr-53-esperanto", dim=44),
     "configs4_deepspeech_1024": dict(hw=1024, torso=True, asr_model="deepspeech", dim=29),
+    # the same 512x512 scene with an OPAQUE head (log-density row of the sigma net made positive): rays terminate early, the
+    # alive list shrinks from iteration to iteration (n_step > 1), depth is non-trivial -- the regime of a trained model
+    "configs2_opaque_512": dict(hw=512, torso=True, asr_model="cpierse/wav2vec2-large-xlsr-53-esperanto", dim=44, opaque=6.0),
 }
 _report = {}
 
@@ -49,6 +52,10 @@ def _pair(cfg, fp16):
         with torch.no_grad():
             for enc in encs:
                 enc.embeddings.copy_((torch.rand(enc.embeddings.shape, generator=g) * 2 - 1).to(DEV))
+        if cfg.get("opaque"):
+            with torch.no_grad():
+                w = net.sigma_net.net[2].weight
+                w[0] = w[0].abs() * cfg["opaque"]
         if cfg["torso"]:
             install_occupancy(net)
         else:

@@ -21,7 +21,7 @@ from radnerf_b200 import abi, synthetic as syn
 from radnerf_b200.model import NeRFNetwork, Options
 
 
-def training_samples(dev, n_rays=65536):
+def training_samples(dev, n_rays=65536, dense=False):
     import raymarching as rm
     torch.manual_seed(0)
     m = NeRFNetwork(Options(torso=False, fp16=True, exp_eye=True))
@@ -30,6 +30,12 @@ def training_samples(dev, n_rays=65536):
     m.mean_density = float(np.clip(grid, 0, None).mean())
     m.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, min(m.mean_density, m.density_thresh))))
     m = m.to(dev)
+    if dense:   # what the bench's steady-state training step sees: the occupancy grid after update_extra_state on a random-init
+        # network (sigma ~ 1 everywhere, threshold = the mean): about half of ALL cells occupied, ~0.7 M samples per batch
+        m.aud_features = torch.from_numpy(syn.audio_feature_bank(600, 44, 16, seed=0))
+        m.eye_area = torch.full((600, 1), 0.25)
+        with torch.autocast("cuda", dtype=torch.float16):
+            m.update_extra_state()
     b = syn.batch_to(syn.training_batch(512, 512, n_rays, frame_index=0), dev)
     ro, rd = b["rays_o"][0].contiguous(), b["rays_d"][0].contiguous()
     nears, fars = rm.near_far_from_aabb(ro, rd, m.aabb_train, m.min_near)
@@ -42,7 +48,8 @@ def training_samples(dev, n_rays=65536):
 
 def main():
     dev = torch.device("cuda", 0)
-    m, xyz = training_samples(dev)
+    dense = os.environ.get("DENSE", "0") == "1"
+    m, xyz = training_samples(dev, dense=dense)
     enc = m.encoder
     B = xyz.shape[0]
     x01 = ((xyz + m.bound) / (2 * m.bound)).contiguous()
@@ -54,8 +61,9 @@ def main():
     lib = abi.lib()
     sizes = (offsets[1:] - offsets[:-1]).cpu().numpy()
 
-    def generic(out):
-        abi.call("rn_grid_encode_backward", grad16, x01, None, offsets, out, B, 3, 2, L, S, H, None, None, 1, 0, 0, 1, 1, 0)
+    def generic(out):   # the round-1 structure: one v2 atomic per corner (variant 0 of the same entry point)
+        abi.check(lib.rn_grid_backward3(abi.ptr(grad16), abi.ptr(x01), abi.ptr(offsets), abi.ptr(out), B, L, S, H, 1, 1, 0, 0xffff, 0, 0, 0,
+                                        abi.cur_stream()))
 
     # privatisable: leading dense levels (row count == (res+1)^3 rounded) that fit in 150 KB
     priv_levels, priv_rows = 0, 0
@@ -86,7 +94,7 @@ def main():
     generic(ref)
     torch.cuda.synchronize()
     scale = ref.abs().max().item()
-    report = {"samples": B, "rows": rows, "priv_levels": priv_levels, "priv_rows": priv_rows, "ref_absmax": scale, "variants": {}}
+    report = {"distribution": "dense occupancy after update_extra_state (bench steady state)" if dense else "head-shaped occupancy", "samples": B, "rows": rows, "priv_levels": priv_levels, "priv_rows": priv_rows, "ref_absmax": scale, "variants": {}}
 
     def timeit(fn, reps=20):
         out = torch.zeros(rows, 2, device=dev)
@@ -102,6 +110,11 @@ def main():
         return e0.elapsed_time(e1) / reps
 
     report["generic_ms"] = timeit(generic)
+
+    def production(out):
+        abi.call("rn_grid_encode_backward", grad16, x01, None, offsets, out, B, 3, 2, L, S, H, None, None, 1, 0, 0, 1, 1, 0)
+    report["production_ms"] = timeit(production)
+    report["production_gbs_algorithmic"] = B * 1100 / report["production_ms"] / 1e6
     names = {0: "plain (8 x v2 per level)", 1: "z-merge + x-pair v4", 3: "z-merge + x-pair + segmented warp aggregation",
              5: "z-merge + x-pair + smem privatisation", 7: "all three"}
     for v, name in names.items():

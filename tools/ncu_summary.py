@@ -27,6 +27,15 @@ want = {
     "stall_not_selected": "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "stall_barrier": "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "stall_no_instruction": "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "stall_lg_throttle": "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "stall_mio_throttle": "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "l2_red_sectors": "lts__t_sectors_srcunit_tex_op_red.sum",
+    "l2_red_pct_of_peak_avg_slice": "lts__t_sectors_srcunit_tex_op_red.avg.pct_of_peak_sustained_elapsed",
+    "l2_throughput_pct_avg_slice": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l2_throughput_pct_max_slice": "lts__throughput.max.pct_of_peak_sustained_elapsed",
+    "l2_throughput_pct_min_slice": "lts__throughput.min.pct_of_peak_sustained_elapsed",
+    "l1_red_requests": "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum",
+    "l2_sectors": "lts__t_sectors.sum",
 }
 scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}
 launches = []
