@@ -355,6 +355,46 @@ void rn_debug_set_while_node(int on);
 
 /* ------------------------------------------------------------------ diagnostics ---------------------- */
 
+/* ------------------------------------------------------------------ fused training step of the head network ------------
+ * Replaces, for one batch of march_rays_train samples, NeRFNetwork.forward (nerf/network.py:222-283: two grid encoders, SH, the
+ * ambient / sigma / colour MLPs, trunc_exp, sigmoid) and its backward (autograd through the same, nerf/utils.py:1168-1171) --
+ * in the reference ~16 cuBLAS GEMMs and ~300 elementwise / cat / repeat / cast launches per step -- by one forward kernel and two
+ * backward kernels on tcgen05 (csrc/head_train_fwd.cu, head_train_bwd.cu) plus the grid scatter kernels.
+ * All buffers are caller-allocated; sizes come from the rn_head_train_*_bytes queries. */
+typedef struct rn_head_train_desc {
+    uint32_t M;                  /* sample rows of xyzs / dirs (the tail of the last 128-row tile is padded internally) */
+    uint32_t reserved;
+    float bound; float reserved1;
+    const float* xyzs; const float* dirs;            /* [M,3] fp32: positions in [-bound, bound], unit directions */
+    rn_grid_table grid3d, grid2d;                    /* packed fp16 tables (rn_pack_grid_table) of encoder / encoder_ambient */
+    const void* fwd_blob;                            /* rn_head_blob_bytes() of interleaved fp16 weights (rn_pack_head_blobs) */
+    const void* bwd_blob;                            /* rn_head_train_bwd_blob_bytes(): transposed weights for the data gradients */
+    const float* consts;                             /* [3*64] hoisted first-layer terms: W_a1[:,32:96] enc_a, W_s1[:,64] eye, W_c1[:,80:84] ind */
+    float* sigma; float* rgb; float* ambient;        /* forward outputs [M], [M,3], [M,2] fp32 (rgb, sigma rounded as the fp16 autocast path) */
+    float* sigma_pre;                                /* [M] log-density (input of trunc_exp), kept for its backward */
+    void* acts;                                      /* rn_head_train_acts_bytes(M): saved layer inputs, 928 B/sample */
+    void* dy_dx2;                                    /* [M, 16*2*2] fp16: d(enc_w)/d(ambient coordinate in [0,1]), gridencoder.cu:200-243 */
+    const float* d_sigma; const float* d_rgb; const float* d_ambient;   /* backward inputs [M], [M,3], [M,2] fp32 */
+    float* d_table3; float* d_table2;                /* fp32 [rows,2] table gradients, accumulated INTO (caller pre-zeroes) */
+    float* d_weights;                                /* [rn_head_train_dw_floats()] fp32, overwritten: nn.Linear-shaped gradients of the
+                                                        encoder-fed weight columns + the three column sums that carry the hoisted
+                                                        columns (layout: csrc/head_train.cuh G_*) */
+    void* workspace; uint64_t workspace_bytes;       /* rn_head_train_workspace_bytes(M) */
+} rn_head_train_desc;
+uint64_t rn_head_train_acts_bytes(uint32_t M);
+uint64_t rn_head_train_workspace_bytes(uint32_t M);
+uint32_t rn_head_train_bwd_blob_bytes(void);
+uint32_t rn_head_train_dw_floats(void);
+int rn_head_train_forward(const rn_head_train_desc* d, void* stream);
+int rn_head_train_backward(const rn_head_train_desc* d, void* stream);
+/* fp32 GridEncoder table [rows,2] -> the packed fp16 copy the fused kernels gather from: row r of level l (first row
+ * packed_first[l]) = (features of row r, features of row (r + 1) mod size_l); radnerf_b200/frame.py pack_table in one launch. */
+int rn_pack_grid_table(const float* embeddings, const int32_t* offsets, const int32_t* packed_first, uint32_t L, void* out, void* stream);
+/* the eight bias-free Linear weights of the head (fp32, nn.Linear [out,in]: ambient 64x96, 64x64, 2x64; sigma 64x65, 64x64, 65x64;
+ * colour 64x84, 3x64) -> the interleaved fp16 operand blobs of the forward (rn_head_blob_bytes) and, if bwd_blob != NULL, of the
+ * backward (rn_head_train_bwd_blob_bytes) in one launch. */
+int rn_pack_head_blobs(const float* const* weights8, void* fwd_blob, void* bwd_blob, void* stream);
+
 /* one 128 x N x K fp16 GEMM tile through the hand-written tcgen05/TMEM path (out = A @ W^T, fp32 accumulate);
  * A [128,K] fp16 row-major, W [N,K] fp16 row-major.  Validates descriptors/layouts in isolation. */
 int rn_selftest_umma(const void* A, const void* W, float* out, uint32_t K, uint32_t N, void* stream);

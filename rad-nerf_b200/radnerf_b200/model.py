@@ -351,7 +351,11 @@ class NeRFNetwork(nn.Module):
             xyzs, dirs, deltas, rays = rm.march_rays_train(rays_o, rays_d, self.bound, self.density_bitfield, self.cascade,
                                                            self.grid_size, nears, fars, counter, self.mean_count, perturb, 128,
                                                            force_all_rays, dt_gamma, max_steps)
-            sigmas, rgbs, ambient = self(xyzs, dirs, enc_a, ind_code, eye)
+            if self._use_fused_train(enc_a, ind_code, eye):
+                from . import fused_train    # ONE forward kernel (+ 2 backward kernels) instead of 8 GEMMs + ~150 elementwise launches
+                sigmas, rgbs, ambient = fused_train.head_forward(self, xyzs, dirs, enc_a, ind_code, eye)
+            else:
+                sigmas, rgbs, ambient = self(xyzs, dirs, enc_a, ind_code, eye)
             sigmas = self.density_scale * sigmas
             weights_sum, ambient_sum, depth, image = rm.composite_rays_train(sigmas, rgbs, ambient.abs().sum(-1), deltas, rays)
             results['weights_sum'] = weights_sum
@@ -407,6 +411,18 @@ class NeRFNetwork(nn.Module):
         results['depth'] = depth.view(*prefix)
         results['image'] = image
         return results
+
+    # fused_train: "auto" (default) = use the fused training kernels of radnerf_b200.fused_train whenever the step is the one they
+    # implement (CUDA, fp16 autocast, the stock head architecture, this repo's operators); False = always op by op (the parity yardstick)
+    fused_train = "auto"
+
+    def _use_fused_train(self, enc_a, ind_code, eye):
+        if not self.fused_train or not isinstance(self.ops, DefaultOps) or self.density_bitfield.device.type != "cuda":
+            return False
+        if enc_a is None or ind_code is None or eye is None or not torch.is_autocast_enabled():
+            return False
+        from . import fused_train
+        return fused_train.supported(self)
 
     def render(self, rays_o, rays_d, auds, bg_coords, poses, staged=False, max_ray_batch=4096, path="ops", **kwargs):
         """entry point with the reference's contract (renderer.py:504-537); cuda_ray never stages.
@@ -473,7 +489,11 @@ class NeRFNetwork(nn.Module):
             for c0 in range(0, centres.shape[0], chunk):
                 pts = centres[c0:c0 + chunk] * scale
                 pts += (torch.rand_like(pts) * 2 - 1) * half_cell
-                sigma = self.density(pts, enc_a, eye)['sigma'].reshape(-1).detach()
+                if self._use_fused_train(enc_a, 0, eye):
+                    from . import fused_train
+                    sigma = fused_train.density(self, pts, enc_a, eye)     # sigma-only pass of the fused forward kernel
+                else:
+                    sigma = self.density(pts, enc_a, eye)['sigma'].reshape(-1).detach()
                 fresh[cas, c0:c0 + chunk] = sigma.to(fresh.dtype) * self.density_scale
         return fresh
 
