@@ -231,9 +231,10 @@ def density(model, xyzs, enc_a, eye):
     tr = trainer(model)
     xyzs = xyzs.float().contiguous()
     M = xyzs.shape[0]
-    tr.refresh(model)
     ind = model.individual_codes[0] if getattr(model, "individual_codes", None) is not None else torch.zeros(4, device=xyzs.device)
-    _hoisted(model, enc_a, ind, eye, tr.consts)
+    with torch.autocast("cuda", enabled=False):     # the hoisted first-layer terms are fp32 products, as in head_forward
+        tr.refresh(model)
+        _hoisted(model, enc_a.float(), ind.float(), eye.float(), tr.consts)
     sigma = torch.empty(M, device=xyzs.device)
     d = tr.desc(model, xyzs, None, M)
     d.sigma = sigma.data_ptr()

@@ -40,6 +40,8 @@ def make():
     m.aud_features = torch.from_numpy(syn.audio_feature_bank(600, 44, 16, seed=0))
     m.eye_area = torch.full((600, 1), 0.25)
     m.poses = torch.from_numpy(np.stack([syn.orbit_pose(yaw_deg=float(y), pitch_deg=2.0) for y in np.linspace(-10, 10, 16)]))
+    if os.environ.get("RADNERF_FUSED_TRAIN", "1") == "0":      # op-by-op network (cuBLAS + elementwise launches): the round-1 step
+        m.fused_train = False
     return m
 
 
@@ -94,7 +96,7 @@ def run(kind, regime):
         replay_ms = r0.elapsed_time(r1) / 12
     extra = {} if graphed is None else {"captures": graphed.captures, "replays": graphed.replays, "fallback_reason": graphed.fallback_reason,
                                              "capture_ms": graphed.capture_ms, "replay_only_ms_per_step": replay_ms}
-    return {**extra, "optimizer": kind, "regime": regime, "ms_per_step": ms, "host_ms_per_step": (time.perf_counter() - t0) * 1e3 / steps,
+    return {**extra, "optimizer": kind, "regime": regime, "network": "fused kernels" if model.fused_train else "op by op", "ms_per_step": ms, "host_ms_per_step": (time.perf_counter() - t0) * 1e3 / steps,
             "rays_per_s": n_rays / ms * 1e3, "samples_per_step": samples, "msamples_per_s": samples / ms / 1e3,
             "loss": float(loss), "mean_count": int(model.mean_count), "steps": steps}, model, opt, scaler
 
