@@ -12,7 +12,11 @@ Prints ONE JSON line (rank 0).  `value` = frames/s with the frame's inputs (rays
 `e2e` = frames/s through the public API with HOST inputs (pose, intrinsics, audio window, eye) copied in and the fp32
 image copied out every frame; `roofline` = the dominant kernel against the measured B200 peak; `cpu_baseline` = the
 oracle port on the host cores.  `--impl reference` times the CPU port alone (the reference has no CPU implementation
-of this path -- its extensions are CUDA-only -- so oracle/ is the CPU arm, kind "port").
+of this path -- its extensions are CUDA-only -- so oracle/ is the CPU arm, kind "port"), and reports next to it the STOCK reference
+classes on the reference's own CUDA extensions (baseline/stock_bench.py).
+
+Timing: the driver's `--steps K` window is repeated R >= 15 times (each repeat: K frames, drained, bracketed by CUDA events and a
+barrier; max over ranks per repeat); `ms_per_step` / `value` come from the MEDIAN window, `repeats` and the spread are in the line.
 """
 import argparse
 import json
@@ -41,7 +45,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--path", default=os.environ.get("RADNERF_PATH", "auto"), choices=["auto", "fused", "ops"])
+    ap.add_argument("--path", default=os.environ.get("RADNERF_PATH", "fused"), choices=["fused", "ops"])
+    ap.add_argument("--repeats", type=int, default=0, help="timed windows of --steps frames (0 = at least 15, enough to cover ~1 s)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE configs[0], [1], [4] legs")
     ap.add_argument("--hw", type=int, default=HW)
     ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU (fused path; 1 = strictly one frame at a time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -137,8 +143,9 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_frame_rate(hw, frames_to_time=1, threads=None):
-    """the oracle port (C kernels + torch-CPU MLPs) rendering whole frames on the host cores"""
+def cpu_frame_rate(hw, frames_to_time=1, warmup=1, threads=None, budget_s=None):
+    """the oracle port (C kernels + torch-CPU MLPs) rendering whole frames on the host cores.  -> (frames/s from the MEAN frame time,
+    threads, sample slots per frame, frames really timed)"""
     import torch
     from oracle.cpu_backend import CPUOps
     from oracle import oracle as O
@@ -150,8 +157,9 @@ def cpu_frame_rate(hw, frames_to_time=1, threads=None):
     frames, intr, bg = make_frames(hw, 4)
     bg_t = torch.from_numpy(bg)[None]
     times = []
+    t_start = time.perf_counter()
     with torch.no_grad():
-        for i in range(frames_to_time + 1):
+        for i in range(warmup + frames_to_time):
             f = frames[i % len(frames)]
             ro, rd = syn.get_rays(f["pose"], intr, hw, hw)
             t0 = time.perf_counter()
@@ -159,9 +167,13 @@ def cpu_frame_rate(hw, frames_to_time=1, threads=None):
                                torch.from_numpy(f["pose6"]), eye=torch.from_numpy(f["eye"]), index=0, bg_color=None,
                                perturb=False, **model.opt.render_kwargs())
             float(out["image"].sum())
-            times.append(time.perf_counter() - t0)
-    t = min(times[1:]) if len(times) > 1 else times[0]
-    return 1.0 / t, threads, sum(s[2] for s in model.last_frame_stats)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+            # bounded sample: stop early (never before one timed frame) when the wall-clock budget is used up
+            if budget_s is not None and times and time.perf_counter() - t_start > budget_s:
+                break
+    t = sum(times) / len(times)
+    return 1.0 / t, threads, sum(s[2] for s in model.last_frame_stats), len(times)
 
 
 WORKLOAD = ("RAD-NeRF head+torso inference (BASELINE configs[2]), %dx%d, obama_eo shapes (wav2vec 44-d x16, att=2, exp_eye, "
@@ -173,38 +185,43 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
-    fps, threads, nsamp = cpu_frame_rate(args.hw, frames_to_time=steps)
-    sample = "%d full %dx%d head+torso frame(s) on the CPU port (oracle C kernels + torch-CPU MLPs, fp32), %d sample slots/frame" % (
-        steps, args.hw, args.hw, nsamp)
-    line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    warm = max(1, min(args.warmup, 2))
+    fps, threads, nsamp, timed = cpu_frame_rate(args.hw, frames_to_time=max(1, args.steps), warmup=warm, budget_s=75.0)
+    sample = ("%d full %dx%d head+torso frame(s) after %d warm-up frame(s) on the CPU port (oracle C kernels + torch-CPU MLPs, fp32), mean frame "
+              "time, %d sample slots/frame%s" % (timed, args.hw, args.hw, warm, nsamp,
+                                                 "" if timed == args.steps else "; stopped at the 75 s budget of this arm (%d steps requested)" % args.steps))
+    line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": timed, "steps_requested": args.steps, "warmup": warm,
             "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": WORKLOAD % (args.hw, args.hw), "frame": [args.hw, args.hw], "rays_per_frame": args.hw * args.hw,
                        "note": "the reference's extensions are CUDA-only; its CPU implementation is the oracle port (oracle/), all host threads"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s": time.perf_counter() - t0}
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if not args.no_train:
         try:
             line["train"] = cpu_training_rate()
         except Exception as e:  # noqa: BLE001
             line["train"] = {"unavailable": repr(e)[:200]}
-    # context, next to the CPU number this arm is about: the reference's OWN CUDA extensions (oracle/_ref, built from
-    # /root/reference by oracle/build_ref.py) driven in the reference's op order on this box's GPU, if there is one
+    # context, next to the CPU number this arm is about: the reference's OWN classes (baseline/_ref/reference/nerf, unmodified) on the
+    # reference's OWN CUDA extensions (oracle/_ref, built from /root/reference by oracle/build_ref.py) on this box's GPU, and the same
+    # classes on this repository's drop-in packages.  None of radnerf_b200's model / renderer code is on these paths.
     if not args.no_ref_cuda:
         try:
             import torch
             if torch.cuda.is_available():
-                line["ref_cuda"] = ref_cuda_frame_rate(torch.device("cuda", 0), args.hw, 30)
-                if not args.no_train:
-                    from oracle import ref_backend
-                    line["ref_cuda_train"] = training_rate(torch.device("cuda", 0), ops=ref_backend.RefOps(train=True), tail="torch")
-                    line["ref_cuda_train"]["what"] = ("the same training loop on the reference's CUDA extensions (oracle/_ref) in the "
-                                                      "reference's op order, torch.optim.Adam + GradScaler as main.py / nerf/utils.py run them")
+                import contextlib
+                from baseline import stock_bench
+                dev = torch.device("cuda", 0)
+                with contextlib.redirect_stdout(sys.stderr):      # the reference's wrappers print at import; stdout carries ONE JSON line
+                    line["ref_cuda"] = stock_bench.frame_rate(dev, args.hw, 30, backend="ref")
+                    line["stock_on_dropin"] = stock_bench.frame_rate(dev, args.hw, 30, backend="ours")
+                    if not args.no_train:
+                        line["ref_cuda_train"] = stock_bench.train_rate(dev, backend="ref")
+                        line["stock_on_dropin_train"] = stock_bench.train_rate(dev, backend="ours")
         except Exception as e:  # noqa: BLE001
-            line["ref_cuda"] = {"unavailable": repr(e)[:200]}
+            line["ref_cuda_error"] = repr(e)[:300]
+    line["wall_s"] = time.perf_counter() - t0
     print(json.dumps(line))
 
 
@@ -230,14 +247,9 @@ def run_ours(args):
     frames, intr, bg = make_frames(hw)
     bg_t = torch.from_numpy(bg).to(dev)[None]
     kw = model.opt.render_kwargs()
-
     path = args.path
-    if path == "auto":
-        try:
-            from radnerf_b200 import frame  # noqa: F401
-            path = "fused"
-        except Exception:
-            path = "ops"
+    if path == "fused":
+        from radnerf_b200 import frame  # noqa: F401  (no fallback: a broken fused renderer must fail the bench, not change what it times)
 
     from radnerf_b200.sharding import FrameSharder
     sharder = FrameSharder(hw, hw, world, rank, dev)
@@ -256,6 +268,19 @@ def run_ours(args):
     bg_local = sharder.shard(bg_t[0])[None]
 
     lanes = max(1, args.lanes) if path == "fused" else 1
+
+    def streamer_loop(st, blocks):
+        def render(i):
+            if st.in_flight() == st.depth:
+                st.collect()
+            st.submit(blocks[i % len(blocks)])
+
+        def drain():
+            while st.in_flight():
+                st.collect()
+            st.sync()
+        return render, drain
+
     if path == "fused":
         # `value`: the per-frame input blocks (pose, pose6, eye, audio window) are resident on the device; rays are generated
         # on the device from the pose, `lanes` frames are in flight on separate streams (FramePipeline inside FrameStreamer;
@@ -266,16 +291,7 @@ def run_ours(args):
         packed_dev = [p.to(dev) for p in packed]
         resident = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
                                  deliver=False, depth=lanes, **kw)
-
-        def render_resident(i):
-            if resident.in_flight() == resident.depth:
-                resident.collect()
-            resident.submit(packed_dev[i % len(packed_dev)])
-
-        def drain_resident():
-            while resident.in_flight():
-                resident.collect()
-            resident.sync()
+        render_resident, drain_resident = streamer_loop(resident, packed_dev)
     else:
         def render_resident(i):
             f = dev_frames[i % len(dev_frames)]
@@ -292,15 +308,7 @@ def run_ours(args):
         streamer = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
                                  deliver=(rank == 0), depth=max(2, lanes), **kw)
         h2d_bytes, d2h_bytes = streamer.h2d_bytes, streamer.d2h_bytes
-
-        def render_e2e(i):
-            if streamer.in_flight() == streamer.depth:
-                streamer.collect()      # frame i-2 is on the host
-            streamer.submit(packed[i % len(packed)])
-
-        def drain_e2e():
-            while streamer.in_flight():
-                streamer.collect()
+        render_e2e, drain_e2e = streamer_loop(streamer, packed)
     else:
         pinned = [dict(pose=torch.from_numpy(f["pose"]).pin_memory(), auds=torch.from_numpy(f["auds"]).pin_memory(),
                        pose6=torch.from_numpy(f["pose6"]).pin_memory(), eye=torch.from_numpy(f["eye"]).pin_memory()) for f in frames]
@@ -333,72 +341,93 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, drain=None):
-        model.enc_a = None
+    def timed(fn, steps, warmup, drain=None, mdl=None, repeats=None):
+        """-> dict(ms = median window, windows, launches per window, clocks).  A window = `steps` calls of fn + drain, bracketed by CUDA
+        events and a barrier; per window the MAX over ranks is kept."""
+        mdl = mdl if mdl is not None else model
+        mdl.enc_a = None
+        fused = getattr(mdl, "_fused", None)
+
+        def loop_iters():   # over all frame lanes
+            sts = ([fused] if fused is not None else []) + list(getattr(mdl, "_fused_lanes", {}).values())
+            return sum(s.loop_iterations() for s in sts if s.workspace is not None)
         # the clock sampler (nvidia-smi -lms 100) starts before the warm-up so that it is already reporting when the timed
-        # region -- a few tenths of a second -- runs; warm-up and timed steps are the same load
+        # region runs; warm-up and timed steps are the same load
         with ClockSampler(local) as cs:
             for i in range(warmup):
                 fn(i)
             if drain:
                 drain()
             barrier()
-            l0 = abi.launch_count()
-            fused = getattr(model, "_fused", None)
-
-            def loop_iters():   # over all frame lanes
-                sts = ([fused] if fused is not None else []) + list(getattr(model, "_fused_lanes", {}).values())
-                return sum(s.loop_iterations() for s in sts if s.workspace is not None)
-            it0 = loop_iters()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(steps):
-                fn(warmup + i)
-            if drain:
-                drain()   # every timed frame is on the host before the clock stops
-            e1.record()
-            barrier()
-        ms = e0.elapsed_time(e1)
-        launches = abi.launch_count() - l0
-        if fused is not None and fused.use_graph:
-            # a captured frame was counted as its `capture_unroll` plain iterations plus ONE pass of the WHILE node's body;
-            # replace that one pass by the body's real executions (lower bound when some frame needs < capture_unroll)
-            launches += 3 * (max(0, (loop_iters() - it0) - fused.capture_unroll * steps) - steps)
+            windows, launches, n = [], 0, warmup
+            R = repeats or args.repeats or 15
+            r = 0
+            while r < R:
+                l0, it0 = abi.launch_count(), loop_iters()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(steps):
+                    fn(n + i)
+                if drain:
+                    drain()   # every timed frame is delivered before the clock stops
+                e1.record()
+                barrier()
+                n += steps
+                windows.append(e0.elapsed_time(e1))
+                lw = abi.launch_count() - l0
+                if fused is not None and fused.use_graph:
+                    # a captured frame was counted as its `capture_unroll` plain iterations plus ONE pass of the WHILE node's body;
+                    # replace that one pass by the body's real executions (lower bound when some frame needs < capture_unroll)
+                    lw += 3 * (max(0, (loop_iters() - it0) - fused.capture_unroll * steps) - steps)
+                launches += lw
+                r += 1
+                if r == 3 and not (repeats or args.repeats):
+                    # enough windows to cover ~1 s (so that nvidia-smi's 100 ms sampler sees the timed load), the same count on every rank
+                    want = torch.tensor([min(400, max(15, int(1000.0 / max(1e-3, float(np.median(windows))))))], device=dev)
+                    if world > 1:
+                        dist.all_reduce(want, op=dist.ReduceOp.MAX)
+                    R = int(want.item())
+        w = torch.tensor(windows, device=dev, dtype=torch.float64)
         if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches, cs.summary()
+            dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        w = w.cpu().numpy()
+        return {"ms": float(np.median(w)), "min": float(w.min()), "max": float(w.max()), "repeats": int(len(w)),
+                "launches": launches // max(1, len(w)), "clocks": cs.summary()}
 
     W = max(3, args.warmup)
-    ms, launches, clocks = timed(render_resident, args.steps, W, drain_resident)
-    ms_e2e, _, _ = timed(render_e2e, args.steps, W, drain_e2e)
+    K = args.steps
+    t_res = timed(render_resident, K, W, drain_resident)
+    t_e2e = timed(render_e2e, K, W, drain_e2e)
+    ms, launches, clocks = t_res["ms"], t_res["launches"], t_res["clocks"]
+    ms_e2e = t_e2e["ms"]
     e2e_u8 = None
+    latency = None
     if path == "fused":
         # the same end-to-end loop with the output stage on the device (uint8 frames, what the reference's video writer consumes)
         streamer8 = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
                                   deliver=(rank == 0), depth=max(2, lanes), output="uint8", **kw)
-
-        def render_u8(i):
-            if streamer8.in_flight() == streamer8.depth:
-                streamer8.collect()
-            streamer8.submit(packed[i % len(packed)])
-
-        def drain_u8():
-            while streamer8.in_flight():
-                streamer8.collect()
-        ms_u8, _, _ = timed(render_u8, args.steps, W, drain_u8)
-        e2e_u8 = {"value": args.steps / (ms_u8 / 1e3), "unit": UNIT, "h2d_bytes_per_step": streamer8.h2d_bytes,
-                  "d2h_bytes_per_step": streamer8.d2h_bytes, "what": "as e2e, but frames are converted to uint8 on the device "
+        t_u8 = timed(*((lambda rd: (rd[0], K, W, rd[1]))(streamer_loop(streamer8, packed))))
+        e2e_u8 = {"value": K / (t_u8["ms"] / 1e3), "unit": UNIT, "h2d_bytes_per_step": streamer8.h2d_bytes,
+                  "d2h_bytes_per_step": streamer8.d2h_bytes, "repeats": t_u8["repeats"], "what": "as e2e, but frames are converted to uint8 on the device "
                   "((pred * 255).astype(uint8), the reference's host-side expression) before the copy-out"}
-    fps, fps_e2e = args.steps / (ms / 1e3), args.steps / (ms_e2e / 1e3)
+        # single-frame latency: ONE frame in flight, host block in -> image on the host, next frame only after that
+        one = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
+                            deliver=(rank == 0), depth=1, **kw)
 
-    stats = getattr(model, "last_frame_stats", None)
-    line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
+        def render_one(i):
+            one.submit(packed[i % len(packed)])
+            one.collect()
+        t_lat = timed(render_one, K, W, None, repeats=15)
+        latency = t_lat["ms"] / K
+    fps, fps_e2e = K / (ms / 1e3), K / (ms_e2e / 1e3)
+
+    line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "repeats": t_res["repeats"],
+            "ms_per_step": ms / K, "window_ms": {"median": ms, "min": t_res["min"], "max": t_res["max"]},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic", "impl": "ours",
             "config": {"workload": WORKLOAD % (hw, hw),
                        "frame": [hw, hw], "rays_per_frame": hw * hw, "path": path, "frames_in_flight": lanes,
+                       "timing": "median of %d windows of %d frames each (every window drained and bracketed by CUDA events + a barrier, max over ranks)" % (t_res["repeats"], K),
                        "parallelism": "rays of each frame sharded by interleaved row tiles over %d GPU(s), all-gather of image tiles: %s" % (world, gather_impl),
                        "l2": "every frame regenerates its %.0f MB of rays from the pose and rewrites its %.0f MB workspace; with %d frames in "
                              "flight the streamed working set is %.0f MB (> 126 MB L2 for >= 4 lanes); hash tables (8 MB) and weights are "
@@ -408,47 +437,143 @@ def run_ours(args):
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "api": "radnerf_b200.stream.FrameStreamer (depth-2: the image copy-out of frame i overlaps frame i+1)" if path == "fused"
                            else "model.render per frame, synchronous copy-out",
-                    "ms_per_step": ms_e2e / args.steps}}
+                    "ms_per_step": ms_e2e / K, "repeats": t_e2e["repeats"], "window_ms": {"median": ms_e2e, "min": t_e2e["min"], "max": t_e2e["max"]}}}
     if e2e_u8 is not None:
         line["e2e_uint8"] = e2e_u8
+    if latency is not None:
+        line["latency_ms_1lane"] = latency
+        line["latency_note"] = ("one frame in flight: host input block in -> fp32 image on the host, the next frame submitted only then "
+                                "(streaming / config[4] cares about this, `value` is a %d-frames-in-flight throughput)" % lanes)
 
     # ---- N > 1: the same job in FRAME-parallel mode (whole frames per GPU, no collective), reported next to the ray-sharded
     #      headline: ray sharding cuts latency, but a 512x512 frame cannot scale past its ~0.29 ms dependency chain
     if world > 1 and path == "fused":
         from radnerf_b200.stream import FrameStreamer as _FS
         full = _FS(model, hw, hw, intr, bg_t[0], frames[0]["auds"].shape, use_eye=True, deliver=True, depth=max(2, lanes), **kw)
-        model.enc_a = None
-
-        def render_fp(i):
-            if full.in_flight() == full.depth:
-                full.collect()
-            full.submit(packed[i % len(packed)])
-
-        def drain_fp():
-            while full.in_flight():
-                full.collect()
-        ms_fp, _, _ = timed(render_fp, args.steps, W, drain_fp)
-        line["frame_parallel"] = {"value": world * args.steps / (ms_fp / 1e3), "unit": UNIT, "ms_per_step_per_gpu": ms_fp / args.steps,
+        t_fp = timed(*((lambda rd: (rd[0], K, W, rd[1]))(streamer_loop(full, packed))))
+        line["frame_parallel"] = {"value": world * K / (t_fp["ms"] / 1e3), "unit": UNIT, "ms_per_step_per_gpu": t_fp["ms"] / K, "repeats": t_fp["repeats"],
                                   "what": "every GPU renders WHOLE frames of its own slice of the sequence end to end (host inputs in, fp32 "
                                           "image back on the host; radnerf_b200.stream.render_sequence), no collective; weak scaling"}
         model.enc_a = None
+
+    # ---- the other BASELINE configurations, as extra keys (every rank takes part: the frames are ray-sharded like the headline)
+    if path == "fused" and not args.no_extra_configs:
+        try:
+            line["configs"] = extra_configs(args, dev, world, rank, timed, streamer_loop)
+        except Exception as e:  # noqa: BLE001
+            line["configs"] = {"error": repr(e)[:300]}
+
+    # ---- BASELINE configs[3]: the training step, data-parallel over all ranks (every rank its own 2^16 rays)
+    if not args.no_train:
+        try:
+            line["train"] = training_rate(dev, world=world, rank=rank)
+        except Exception as e:  # noqa: BLE001  (context next to the headline, never the reason the line is missing)
+            line["train"] = {"unavailable": repr(e)[:300]}
 
     if rank == 0:
         from radnerf_b200 import roofline
         line["roofline"], line["kernels"] = roofline.measure(model, dev_frames[0], bg_local, kw, path)
         if world == 1 and not args.no_cpu_baseline:
-            fps_cpu, threads, nsamp = cpu_frame_rate(hw, 1)
+            fps_cpu, threads, nsamp, _ = cpu_frame_rate(hw, 1)
             line["cpu_baseline"] = {"value": fps_cpu, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "1 full %dx%d head+torso frame on the CPU port (oracle C kernels, OpenMP, + torch-CPU "
-                                              "MLPs, fp32), %d sample slots" % (hw, hw, nsamp)}
-        if world == 1 and not args.no_train:
-            try:
-                line["train"] = training_rate(dev)
-            except Exception as e:  # noqa: BLE001  (context next to the headline, never the reason the line is missing)
-                line["train"] = {"unavailable": repr(e)[:200]}
+                                    "sample": "1 full %dx%d head+torso frame (after 1 warm-up frame) on the CPU port (oracle C kernels, OpenMP, + "
+                                              "torch-CPU MLPs, fp32), %d sample slots" % (hw, hw, nsamp)}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def extra_configs(args, dev, world, rank, timed, streamer_loop):
+    """BASELINE configs[1] (head only, 450x450, wav2vec 44-d; one GPU) and configs[4] (DeepSpeech 29-d model with eye / individual codes,
+    1024x1024, audio windows streamed through the device-side FeatureRing; rays sharded over all ranks), end to end through
+    FrameStreamer -- host input block in, fp32 image back on rank 0's host."""
+    import torch
+    from radnerf_b200 import synthetic as syn
+    from radnerf_b200.audio_ring import FeatureRing
+    from radnerf_b200.model import NeRFNetwork, Options
+    from radnerf_b200.posemath import convert_poses
+    from radnerf_b200.sharding import FrameSharder
+    from radnerf_b200.stream import FrameStreamer, pack_inputs
+    out = {}
+    K, W = args.steps, max(3, args.warmup)
+
+    def build(torso, asr_model, hw, dim, share):
+        torch.manual_seed(0)
+        m = NeRFNetwork(Options(torso=torso, smooth_lips=True, fp16=True, exp_eye=True, asr_model=asr_model))
+        grid = syn.head_density_grid(128, semi_axes=(0.34, 0.24, 0.37))
+        m.density_grid.copy_(torch.from_numpy(grid))
+        m.mean_density = float(np.clip(grid, 0, None).mean())
+        m.density_bitfield.copy_(torch.from_numpy(syn.packbits_np(grid, min(m.mean_density, m.density_thresh))))
+        if torso:
+            tg = syn.torso_density_grid(128)
+            m.density_grid_torso.copy_(torch.from_numpy(tg))
+            m.mean_density_torso = float(tg.mean())
+        m = m.eval().to(dev)
+        sh = FrameSharder(hw, hw, world if share else 1, rank if share else 0, dev)
+        if share and world > 1:
+            sh.enable_peer_gather(n_buffers=max(2, args.lanes))
+        bank = syn.audio_feature_bank(600, dim, 16, seed=0)
+        intr = syn.intrinsics_for(hw, hw)
+        bg = torch.from_numpy(syn.get_bg_coords(hw, hw)).to(dev)
+        blocks = []
+        for i in range(16):
+            pose = syn.orbit_pose(yaw_deg=10.0 * np.sin(2 * np.pi * i / 16), pitch_deg=2.0)
+            blocks.append(pack_inputs(pose, syn.audio_window(bank, 8 + i, 2), convert_poses(torch.from_numpy(pose)[None]).numpy(), np.array([[0.25]], np.float32)))
+        st = FrameStreamer(m, hw, hw, intr, sh.shard(bg), (8, dim, 16), use_eye=True, sharder=sh, deliver=(rank == 0), depth=max(2, args.lanes),
+                           **m.opt.render_kwargs())
+        return m, st, blocks, bank
+
+    if world == 1:
+        m, st, blocks, _ = build(False, "cpierse/wav2vec2-large-xlsr-53-esperanto", 450, 44, False)
+        r, d = streamer_loop(st, blocks)
+        t = timed(r, K, W, d, mdl=m)
+        out["configs1_head_only_450"] = {"value": K / (t["ms"] / 1e3), "unit": UNIT, "ms_per_step": t["ms"] / K, "repeats": t["repeats"],
+                                         "workload": "BASELINE configs[1]: head-only inference, obama_eo shapes (wav2vec 44-d x16), 450x450, random-init, end to "
+                                                     "end through FrameStreamer (host block in, fp32 image out), %d frames in flight" % st.depth}
+        del m, st
+    # configs[4]: the ASR feature rows live in a device ring (audio_ring.FeatureRing = the reference's ASR.feat_queue); per frame the host sends
+    # the 24-float head [pose | pose6 | eye] only, two new feature rows are pushed (25 fps video on 50 Hz features) and the frame's
+    # [8, 29, 16] window is gathered on the device straight into the lane's input block
+    m, st, blocks, bank = build(True, "deepspeech", 1024, 29, True)
+    # reference defaults (nerf/asr.py): feat_buffer_size 4, -m 50 -> a context of 50 feature rows lands every 25 video frames
+    ring = FeatureRing(slots=4, context=50, dim=29, device=dev)
+    feats = torch.from_numpy((np.random.default_rng(3).standard_normal((4000, 29)) * 3).astype(np.float32)).to(dev)
+    heads = [b[:24].clone().pin_memory() for b in blocks]
+    state = {"row": 0}
+
+    def push(i):
+        if i % 25 == 0:
+            r0 = state["row"] % (feats.shape[0] - 50)
+            ring.push(feats[r0:r0 + 50])
+            state["row"] += 50
+
+    def render(i):
+        if st.in_flight() == st.depth:
+            st.collect()
+        push(i)
+        st.submit(heads[i % len(heads)], ring=ring)
+
+    def drain():
+        while st.in_flight():
+            st.collect()
+        st.sync()
+    t = timed(render, K, W, drain, mdl=m)
+    one = FrameStreamer(m, 1024, 1024, syn.intrinsics_for(1024, 1024), st.bg, (8, 29, 16), use_eye=True, sharder=st.sharder, deliver=(rank == 0), depth=1,
+                        **m.opt.render_kwargs())
+
+    def render_one(i):
+        push(i)
+        one.submit(heads[i % len(heads)], ring=ring)
+        one.collect()
+    tl = timed(render_one, K, W, None, mdl=m, repeats=15)
+    out["configs4_deepspeech_1024_streaming"] = {
+        "value": K / (t["ms"] / 1e3), "unit": UNIT, "ms_per_step": t["ms"] / K, "repeats": t["repeats"], "frame_latency_ms": tl["ms"] / K,
+        "n_gpus": world, "h2d_bytes_per_step": 96, "d2h_bytes_per_step": st.d2h_bytes,
+        "workload": "BASELINE configs[4]: DeepSpeech-feature (29-d) model with eye / individual codes + torso, 1024x1024 streaming render: audio "
+                    "windows gathered on the device from the FeatureRing, rays sharded over %d GPU(s), fp32 image back on rank 0's host, %d frames in "
+                    "flight; frame_latency_ms = one frame in flight" % (world, st.depth)}
+    return out
 
 
 def cpu_training_rate(n_rays=65536, steps=2, threads=None):
@@ -483,16 +608,19 @@ def cpu_training_rate(n_rays=65536, steps=2, threads=None):
             "cores": threads, "kind": "port", "steps": steps, "loss": float(loss)}
 
 
-def training_rate(dev, n_rays=65536, steps=48, ops=None, tail="fused", graphed=False):
-    """BASELINE configs[3] on one GPU, steady state: head training step on 2^16 rays (march_rays_train -> encoders + MLPs ->
-    composite_rays_train, backward, GradScaler, FusedAdam one-sweep tail), occupancy-grid update every 16 steps inside the
-    timed region (nerf/utils.py:1153-1182).  The first 16 steps (unknown mean_count: worst-case buffers + a host read per
-    step, raymarching.py:213-256) and the first grid update are warm-up, as in any run longer than 16 steps."""
+def training_rate(dev, n_rays=65536, steps=64, ops=None, tail="fused", graphed=True, world=1, rank=0):
+    """BASELINE configs[3], steady state: head training step on 2^16 rays PER GPU (march_rays_train -> fused encoders + MLPs ->
+    composite_rays_train, backward, GradScaler, FusedAdam one-sweep tail), occupancy-grid update every 16 steps inside the timed
+    region (nerf/utils.py:1153-1182); with world > 1 data-parallel: every rank draws its own rays, gradients are averaged with
+    NCCL all-reduces (two hash tables + one flat bucket), the occupancy update is replicated (radnerf_b200.train).  The first 16
+    steps (unknown mean_count: worst-case buffers + a host read per step, raymarching.py:213-256) and the first grid update are
+    warm-up, as in any run longer than 16 steps.  graphed: the step is replayed from CUDA graphs (train.GraphedTrainStep)."""
     import torch
+    import torch.distributed as dist
     from radnerf_b200 import synthetic as syn
     from radnerf_b200.model import NeRFNetwork, Options
     from radnerf_b200.optim import FusedAdam
-    from radnerf_b200.train import GraphedTrainStep, train_step
+    from radnerf_b200.train import GradSync, GraphedTrainStep, train_step, update_extra_state_replicated
     torch.manual_seed(0)
     m = NeRFNetwork(Options(torso=False, fp16=True, exp_eye=True), ops=ops)
     grid = syn.head_density_grid(128, semi_axes=(0.34, 0.24, 0.37))
@@ -502,30 +630,36 @@ def training_rate(dev, n_rays=65536, steps=48, ops=None, tail="fused", graphed=F
     m = m.to(dev)
     m.aud_features = torch.from_numpy(syn.audio_feature_bank(600, 44, 16, seed=0))     # main.py:210-212
     m.eye_area = torch.full((600, 1), 0.25)
-    batches = [syn.batch_to(syn.training_batch(512, 512, n_rays, frame_index=i), dev) for i in range(8)]
+    batches = [syn.batch_to(syn.training_batch(512, 512, n_rays, frame_index=i, seed=rank), dev) for i in range(8)]
     if tail == "fused":
         opt = FusedAdam(m.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15, zero_grads=True)
     else:
         opt = torch.optim.Adam(m.get_params(5e-3, 5e-4), betas=(0.9, 0.99), eps=1e-15)      # main.py:204
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 0.1 ** (it / 200000))
     scaler = torch.amp.GradScaler("cuda")
+    sync = GradSync(m.parameters()) if world > 1 else None
     g = [0]
-    # graphed=True replays the step as one CUDA graph between grid updates (radnerf_b200.train.GraphedTrainStep).  Measured in
-    # round 1: a replay takes 10.3 ms where the op-by-op step takes 8.5 ms, and every grid update costs a 25-160 ms re-capture --
-    # the step is bound by its device work, not by launches -- so the op-by-op step is what this leg times
-    graphed = GraphedTrainStep(m, opt, scaler) if (graphed and tail == "fused") else None
+    graphed = GraphedTrainStep(m, opt, scaler, sync=sync) if (graphed and tail == "fused") else None
+    upd = []
 
     def one(i):
         if g[0] % m.opt.update_extra_interval == 0 and g[0] > 0:
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record()
             with torch.autocast("cuda", dtype=torch.float16):
-                m.update_extra_state()
+                update_extra_state_replicated(m) if world > 1 else m.update_extra_state()
+            u1.record()
+            upd.append((u0, u1))
         g[0] += 1
-        loss = graphed(batches[i % 8]) if graphed is not None else train_step(m, batches[i % 8], opt, scaler, None)
+        loss = graphed(batches[i % 8]) if graphed is not None else train_step(m, batches[i % 8], opt, scaler, sync)
         sched.step()
         return loss
-    for i in range(20):
+    for i in range(22):
         one(i)
+    upd.clear()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
@@ -533,49 +667,46 @@ def training_rate(dev, n_rays=65536, steps=48, ops=None, tail="fused", graphed=F
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    upd_ms = [a.elapsed_time(b) for a, b in upd]
     samples = float(m.step_counter[:, 0].float().mean())
+    res = {}
+    if world > 1:
+        t = torch.tensor([ms, samples], device=dev, dtype=torch.float64)
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, samples = float(mx[0]), float(t[1])          # slowest rank's step time, samples of ALL ranks per step
+        # the gradient exchange alone: the same three all-reduces on the live gradient buffers, back to back
+        torch.cuda.synchronize()
+        dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            sync.begin_step()
+            sync.finish()
+        a1.record()
+        torch.cuda.synchronize()
+        ar = torch.tensor([a0.elapsed_time(a1) / 20], device=dev)
+        dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+        same = True
+        for p in m.parameters():                    # replicas must have stayed bit-identical
+            lo, hi = p.detach().clone(), p.detach().clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            same = same and bool(torch.equal(lo, hi))
+        res.update(allreduce_us_exposed=float(ar.item()) * 1e3, allreduce_bytes_per_step=sync.bytes_last, replicas_identical=same,
+                   parallelism="data-parallel over %d GPUs: %d rays per GPU per step, NCCL all-reduce (AVG) of 2 hash-table gradients + one flat "
+                               "bucket, issued between the backward graph and the optimiser graph (not overlapped: allreduce_us_exposed is "
+                               "its whole cost per step); replicated occupancy update" % (world, n_rays))
     how = "torch.optim.Adam, op by op" if tail != "fused" else "FusedAdam one-sweep tail, op by op"
     if graphed is not None:
-        how = "FusedAdam tail, step replayed as a CUDA graph (%d captures, %d replays in the run%s)" % (
+        how = "fused head forward / backward kernels, FusedAdam tail, step replayed from CUDA graph(s) (%d captures, %d replays in the run%s)" % (
             graphed.captures, graphed.replays, "" if graphed.fallback_reason is None else "; FELL BACK to op-by-op: " + graphed.fallback_reason)
-    return {"workload": "RAD-NeRF head training step (BASELINE configs[3]): %d rays/batch, fp16 autocast, grid update every 16 steps, "
-                        "%s" % (n_rays, how), "ms_per_step": ms, "rays_per_s": n_rays / ms * 1e3, "samples_per_step": samples,
-            "msamples_per_s": samples / ms / 1e3, "steps": steps, "loss": float(loss)}
-
-
-def ref_cuda_frame_rate(dev, hw, steps):
-    """the reference's own compiled kernels driven in the reference's op order on the same GPU (context, not a contract key)"""
-    import torch
-    from oracle import ref_backend
-    from radnerf_b200 import synthetic as syn
-    if not ref_backend.available():
-        return {"unavailable": "oracle/_ref/*.so not built"}
-    model = make_model(dev, ops=ref_backend.RefOps())
-    frames, intr, bg = make_frames(hw, 8)
-    bg_t = torch.from_numpy(bg).to(dev)[None]
-    kw = model.opt.render_kwargs()
-    devf = []
-    for f in frames:
-        ro, rd = syn.get_rays(f["pose"], intr, hw, hw)
-        devf.append((torch.from_numpy(ro).to(dev)[None], torch.from_numpy(rd).to(dev)[None], torch.from_numpy(f["auds"]).to(dev),
-                     torch.from_numpy(f["pose6"]).to(dev), torch.from_numpy(f["eye"]).to(dev)))
-
-    def one(i):
-        ro, rd, a, p6, eye = devf[i % len(devf)]
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
-            return model.render(ro, rd, a, bg_t, p6, eye=eye, index=0, bg_color=None, perturb=False, **kw)["image"]
-    for i in range(5):
-        one(i)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        one(5 + i)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return {"value": 1000.0 / ms, "unit": UNIT, "ms_per_step": ms, "what": "reference CUDA extensions (sm_100a build) + torch "
-            "Linear layers in the reference's op order, inputs resident", "sample_slots_per_frame": sum(s[2] for s in model.last_frame_stats)}
+    res.update({"workload": "RAD-NeRF head training step (BASELINE configs[3]): %d rays/batch per GPU, fp16 autocast, grid update every 16 steps, "
+                            "%s" % (n_rays, how), "n_gpus": world, "ms_per_step": ms, "rays_per_s": world * n_rays / ms * 1e3,
+                "samples_per_step": samples, "msamples_per_s": samples / ms / 1e3, "steps": steps, "loss": float(loss),
+                "update_extra_state_ms": float(np.mean(upd_ms)) if upd_ms else None, "scaling": "weak"})
+    return res
 
 
 def main():

@@ -105,6 +105,13 @@ int rn_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t*
                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
                         const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays,
                         int32_t* counter, const float* noises, void* stream);
+/* as rn_march_rays_train, with the sample budget on the DEVICE: buffers hold M samples, a ray is dropped when it would end past
+ * min(M, *budget).  Lets a training step captured in a CUDA graph keep fixed buffer shapes while the reference's running
+ * estimate (`mean_count`, raymarching.py:213-229, renderer.py:489-493) changes between replays.  budget == NULL: plain M. */
+int rn_march_rays_train_budget(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                               uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const int32_t* budget,
+                               const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                               int32_t* rays, int32_t* counter, const float* noises, void* stream);
 /* replaces march_rays_train_backward (raymarching.h:15, raymarching.cu:535-593); grads accumulated into */
 int rn_march_rays_train_backward(const float* grad_xyzs, const float* grad_dirs, const int32_t* rays,
                                  const float* deltas, uint32_t N, uint32_t M, float* grad_rays_o,

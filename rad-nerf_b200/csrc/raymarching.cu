@@ -187,7 +187,7 @@ march_rays_train_kernel(const float* __restrict__ rays_o, const float* __restric
                         uint32_t max_steps, uint32_t N, uint32_t M, const float* __restrict__ nears,
                         const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
                         float* __restrict__ deltas, int32_t* __restrict__ rays, int32_t* __restrict__ counter,
-                        const float* __restrict__ noises) {
+                        const float* __restrict__ noises, const int32_t* __restrict__ budget) {
     __shared__ uint32_t warp_sums[TRAIN_THREADS / 32];
     __shared__ uint32_t base_point, base_ray;
 
@@ -245,7 +245,10 @@ march_rays_train_kernel(const float* __restrict__ rays_o, const float* __restric
     rays[(size_t)ray_index * 3 + 2] = (int32_t)num_steps;
 
     if (num_steps == 0) return;
-    if (point_index + num_steps > M) return;  // over budget: the ray is dropped (raymarching.cu:457)
+    // over budget: the ray is dropped (raymarching.cu:457).  The budget is M, or -- for a step replayed from a CUDA graph,
+    // whose buffers keep a fixed capacity M while the reference's running estimate `mean_count` moves -- min(M, *budget)
+    const uint32_t limit = budget ? min(M, (uint32_t)max(__ldg(budget), 0)) : M;
+    if (point_index + num_steps > limit) return;
 
     float* px = xyzs + (size_t)point_index * 3;
     float* pd = dirs + (size_t)point_index * 3;
@@ -540,13 +543,21 @@ extern "C" int rn_march_rays_train(const float* rays_o, const float* rays_d, con
                                    float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                                    const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
                                    int32_t* rays, int32_t* counter, const float* noises, void* stream) {
+    return rn_march_rays_train_budget(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nullptr, nears, fars, xyzs, dirs,
+                                      deltas, rays, counter, noises, stream);
+}
+
+extern "C" int rn_march_rays_train_budget(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                          const int32_t* budget, const float* nears, const float* fars, float* xyzs, float* dirs,
+                                          float* deltas, int32_t* rays, int32_t* counter, const float* noises, void* stream) {
     if (N == 0) return RN_OK;
     RN_REQUIRE(rays_o && rays_d && grid && nears && fars && rays && counter && noises, "null pointer");
     RN_REQUIRE(M == 0 || (xyzs && dirs && deltas), "null sample buffers");
     RN_REQUIRE(C >= 1 && C <= 16 && H >= 1 && max_steps >= 1, "bad C/H/max_steps");
     const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H, grid);
     march_rays_train_kernel<<<div_up(N, (uint32_t)TRAIN_THREADS), TRAIN_THREADS, 0, RN_STREAM>>>(
-        rays_o, rays_d, p, max_steps, N, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises);
+        rays_o, rays_d, p, max_steps, N, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises, budget);
     return finish_launch("rn_march_rays_train");
 }
 

@@ -26,6 +26,7 @@ _PROTOS = {
     "rn_packbits": [_vp, _u32, _f32, _vp, _vp],
     "rn_morton3D_dilation": [_vp, _u32, _u32, _vp, _vp],
     "rn_march_rays_train": [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "rn_march_rays_train_budget": [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "rn_march_rays_train_backward": [_vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp],
     "rn_composite_rays_train_forward": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp],
     "rn_composite_rays_train_backward": [_vp] * 11 + [_u32, _u32, _f32, _vp, _vp, _vp, _vp],

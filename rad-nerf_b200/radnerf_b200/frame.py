@@ -593,15 +593,25 @@ def roofline_entries(model, f, bg_local, kw, hbm, tflops, reps=10):
             "launches_per_frame": n_launch / reps, "ms_per_frame": ev_ms / reps,
             "tensor_tflops": ev_samples * HEAD_FLOP_PER_SAMPLE / ev_ms / 1e9,
             "tensor_frac_of_peak": ev_samples * HEAD_FLOP_PER_SAMPLE / ev_ms / 1e9 / tflops}
-    # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/, per sample x this launch size)
+    # DRAM bytes / instructions per sample from the newest committed `ncu --set full` capture of this kernel (profiles/rNN_head_eval_ncu_full.json)
     try:
-        import json, os
-        prof = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "profiles", "r01_head_eval_ncu_full.json")
+        import glob, json, os
+        root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        prof = sorted(glob.glob(os.path.join(root, "profiles", "r*_head_eval_ncu_full.json")))[-1]
         per = json.load(open(prof))["per_sample"]
         head["traffic"] = per["dram_bytes"] * head["units"]
         head["traffic_note"] = ("dram__bytes_read+write per sample (%.1f B, profiles/%s) x samples per launch; far below the algorithmic "
                                 "812 B/sample because both hash tables (5.8 MB) stay L2-resident: the gathers are served by L1/L2"
                                 % (per["dram_bytes"], os.path.basename(prof)))
+        # what really bounds the kernel: instruction issue.  ceiling = SMs x 4 schedulers x 32 lanes x SM clock / thread-instructions per sample
+        clock_ghz = float(torch.cuda.get_device_properties(rays_o.device).clock_rate) / 1e6 if hasattr(torch.cuda.get_device_properties(rays_o.device), "clock_rate") else 1.965
+        sms = torch.cuda.get_device_properties(rays_o.device).multi_processor_count
+        ceiling = sms * 4 * 32 * clock_ghz / per["thread_instructions"]
+        head["issue"] = {"bound": "issue", "inst_per_sample": per["thread_instructions"], "ceiling_gsamples_per_s": ceiling,
+                         "achieved_gsamples_per_s": head["gunits_per_s"], "frac": head["gunits_per_s"] / ceiling, "sm_clock_ghz": clock_ghz,
+                         "l2_bytes_per_sample": per.get("l2_bytes") or None, "l1_hit_pct": per.get("l1_hit_pct"),
+                         "note": "the HBM figures above are SURVEY 8(d)'s algorithmic-bytes accounting; DRAM sees %.0f B/sample, the kernel is bound by "
+                                 "instruction issue + gather latency (profiles/%s)" % (per["dram_bytes"], os.path.basename(prof))}
     except Exception:
         head["traffic"] = None
     march = {"kernel": "march_compact_kernel (occupancy DDA + sample compaction)", "bound": "hbm", "ms_per_frame": tot[0] / reps,

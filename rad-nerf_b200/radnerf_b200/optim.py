@@ -141,12 +141,7 @@ class FusedAdam(torch.optim.Optimizer):
                                                      abi.cur_stream()), "rn_adam_groups_store")
 
     # ---- step --------------------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def step(self, closure=None):
-        loss = None
-        if closure is not None:
-            with torch.enable_grad():
-                loss = closure()
+    def _rows(self):
         rows, device = [], None
         for gi, group in enumerate(self.param_groups):
             for p in group["params"]:
@@ -159,12 +154,32 @@ class FusedAdam(torch.optim.Optimizer):
                 device = p.device
                 rows.append(dict(param=p.data_ptr(), grad=g.data_ptr(), exp_avg=st["exp_avg"].data_ptr(),
                                  exp_avg_sq=st["exp_avg_sq"].data_ptr(), step=st["step"].data_ptr(), n=p.numel(), group=gi))
-        if not rows:
-            return loss
+        return rows, device
+
+    def _ensure_table(self, rows, device):
         key = tuple((r["param"], r["grad"], r["exp_avg"], r["exp_avg_sq"], r["step"], r["group"]) for r in rows)
         if key != self._key:        # first step, or a gradient / state tensor was re-allocated: one small H2D copy
             self._table, self._n_chunks = _descriptor_table(rows, device)
             self._n_tensors, self._key = len(rows), key
+
+    @torch.no_grad()
+    def prepare(self):
+        """build the device descriptor table for the current parameter / gradient / state pointers without stepping (a step that
+        is about to be captured in a CUDA graph must not be the one that uploads it)"""
+        rows, device = self._rows()
+        if rows:
+            self._ensure_table(rows, device)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        rows, device = self._rows()
+        if not rows:
+            return loss
+        self._ensure_table(rows, device)
         scale = getattr(self, "grad_scale", None)
         found = getattr(self, "found_inf", None)
         flags = 1 if self.zero_grads else 0

@@ -112,4 +112,6 @@ def measure(model, f, bg_local, kw, path):
     roof = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
             "traffic": dom.get("traffic"), "traffic_note": dom.get("traffic_note"), "kernel": dom["kernel"], "peak_source": src + " (MEASURED_PEAKS.json)" if src == "measured" else src,
             "algorithmic_per_launch": dom.get("bytes_per_unit", 0) * dom.get("units", 0), "launch_ms": dom["ms"]}
+    if dom.get("issue"):
+        roof["issue"] = dom["issue"]
     return roof, kernels

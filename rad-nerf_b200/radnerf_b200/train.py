@@ -16,9 +16,9 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, params, world=None, table_numel=1 << 18, group=None):
-        """params: iterable of parameters to keep in sync; tensors with >= table_numel elements get their own
-        asynchronous all-reduce, the rest share a flat bucket."""
+    def __init__(self, params, world=None, table_numel=1 << 18, group=None, overlap=True):
+        """params: iterable of parameters to keep in sync; tensors with >= table_numel elements get their own all-reduce
+        (asynchronous, from an autograd hook, when `overlap`), the rest share a flat bucket."""
         self.group = group
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.params = [p for p in params if p.requires_grad]
@@ -27,37 +27,80 @@ class GradSync:
         self.works = []
         self.hooks = []
         self.bytes_last = 0
+        self.overlap = bool(overlap)
+        self.flat = None            # flatten(): the small parameters' gradients as views of ONE buffer
+        self.flat_params = []
         if self.world > 1:
             for p in self.big:
                 self.hooks.append(p.register_post_accumulate_grad_hook(self._on_table_grad))
 
+    def _avg_native(self):
+        # NCCL averages inside the collective; gloo (the CPU tests) only sums
+        return dist.get_backend(self.group) == "nccl"
+
     def _on_table_grad(self, p):
         # the gradient of this table is final for this step: start its all-reduce now, backward continues underneath
-        self.works.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if not self.overlap or (p.is_cuda and torch.cuda.is_current_stream_capturing()):
+            return
+        op = dist.ReduceOp.AVG if self._avg_native() else dist.ReduceOp.SUM
+        self.works.append((dist.all_reduce(p.grad, op=op, group=self.group, async_op=True), p))
         self.bytes_last += p.grad.numel() * p.grad.element_size()
+
+    @torch.no_grad()
+    def flatten(self):
+        """re-point the gradients of the small parameters THAT HAVE ONE (call after a first backward) at slices of one flat fp32
+        buffer, so that the bucket is exchanged in place: no gather before and no scatter after the all-reduce (about 90 small
+        launches per step otherwise).  Parameters without a gradient keep `grad is None` (an optimiser skips them, as torch's does)."""
+        ps = [p for p in self.small if p.grad is not None and p.grad.dtype == torch.float32]
+        if not ps:
+            return
+        flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=ps[0].device)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            view = flat[off:off + n].view_as(p)
+            view.copy_(p.grad)
+            p.grad = view
+            off += n
+        self.flat, self.flat_params = flat, ps
 
     def finish(self):
         """call after backward(): exchanges the small-parameter bucket, waits for the table reductions, averages"""
         if self.world <= 1:
             return
-        grads = [p.grad for p in self.small if p.grad is not None]
-        if grads:
-            flat = torch.cat([g.reshape(-1).float() for g in grads])
-            self.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-            self.bytes_last += flat.numel() * 4
-        for w in self.works:
-            w.wait()
-        self.works = []
+        avg = self._avg_native()
+        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
         inv = 1.0 / self.world
-        if grads:
-            off = 0
-            for g in grads:
-                n = g.numel()
-                g.copy_(flat[off:off + n].view_as(g) * inv)
-                off += n
-        for p in self.big:
-            if p.grad is not None:
+        started = {id(p) for _, p in self.works}
+        late = [p for p in self.big if p.grad is not None and id(p) not in started]     # no hook fired (overlap off / captured backward)
+        loose = [p for p in self.small if p.grad is not None and not any(p is q for q in self.flat_params)]
+        works = []
+        for p in late:
+            works.append((dist.all_reduce(p.grad, op=op, group=self.group, async_op=True), p if not avg else None))
+            self.bytes_last += p.grad.numel() * p.grad.element_size()
+        if self.flat is not None:
+            works.append((dist.all_reduce(self.flat, op=op, group=self.group, async_op=True), self.flat if not avg else None))
+            self.bytes_last += self.flat.numel() * 4
+        bucket = None
+        if loose:
+            bucket = torch.cat([p.grad.reshape(-1).float() for p in loose])
+            works.append((dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True), None))
+            self.bytes_last += bucket.numel() * 4
+        for w, p in self.works:       # hook-driven table reductions
+            w.wait()
+            if not avg:
                 p.grad.mul_(inv)
+        for w, t in works:
+            w.wait()
+            if t is not None:
+                (t.grad if isinstance(t, torch.nn.Parameter) else t).mul_(inv)
+        self.works = []
+        if bucket is not None:
+            off = 0
+            for p in loose:
+                n = p.numel()
+                p.grad.copy_(bucket[off:off + n].view_as(p.grad) * inv)
+                off += n
 
     def begin_step(self):
         self.bytes_last = 0
@@ -85,15 +128,11 @@ def torso_loss(out, rgb):
     return loss + 1e-4 * (-a * torch.log2(a) - (1 - a) * torch.log2(1 - a)).mean()
 
 
-def train_step(model, batch, optimizer, scaler=None, sync=None, lambda_amb=0.1, phase=None):
-    """one optimisation step on `batch` = dict(rays_o [1,N,3], rays_d, auds, bg_coords [1,N,2], poses [1,6], eye, index,
-    rgb [1,N,3], face_mask [1,N] bool, bg_color [N,3] or scalar).  phase: "head" | "torso" (default: the model's
-    --torso flag, as the reference decides).  Returns the detached loss."""
+def forward_backward(model, batch, optimizer, scaler=None, lambda_amb=0.1, phase=None):
+    """first half of a step: zero_grad, render in training mode, loss, (scaled) backward.  Returns the loss tensor."""
     model.train()
     dev = batch["rays_o"].device
     amp = bool(model.opt.fp16) and dev.type == "cuda"
-    if sync is not None:
-        sync.begin_step()
     optimizer.zero_grad(set_to_none=False)
     with torch.autocast(dev.type, dtype=torch.float16, enabled=amp):
         out = model.render(batch["rays_o"], batch["rays_d"], batch["auds"], batch["bg_coords"], batch["poses"], eye=batch.get("eye"),
@@ -105,15 +144,31 @@ def train_step(model, batch, optimizer, scaler=None, sync=None, lambda_amb=0.1, 
         loss = head_loss(out, rgb, batch["face_mask"], lambda_amb) if phase == "head" else torso_loss(out, rgb)
     if scaler is not None and amp:
         scaler.scale(loss).backward()
-        if sync is not None:
-            sync.finish()
+    else:
+        loss.backward()
+    return loss
+
+
+def optimizer_tail(model, batch, optimizer, scaler=None):
+    """second half: GradScaler's inf check + the optimiser step (one sweep with FusedAdam) + the scale update"""
+    amp = bool(model.opt.fp16) and batch["rays_o"].device.type == "cuda"
+    if scaler is not None and amp:
         scaler.step(optimizer)
         scaler.update()
     else:
-        loss.backward()
-        if sync is not None:
-            sync.finish()
         optimizer.step()
+
+
+def train_step(model, batch, optimizer, scaler=None, sync=None, lambda_amb=0.1, phase=None):
+    """one optimisation step on `batch` = dict(rays_o [1,N,3], rays_d, auds, bg_coords [1,N,2], poses [1,6], eye, index,
+    rgb [1,N,3], face_mask [1,N] bool, bg_color [N,3] or scalar).  phase: "head" | "torso" (default: the model's
+    --torso flag, as the reference decides).  Returns the detached loss."""
+    if sync is not None:
+        sync.begin_step()
+    loss = forward_backward(model, batch, optimizer, scaler, lambda_amb, phase)
+    if sync is not None:
+        sync.finish()
+    optimizer_tail(model, batch, optimizer, scaler)
     return loss.detach()
 
 
@@ -147,32 +202,37 @@ def update_extra_state_replicated(model, group=None, share_counters=True):
 
 
 class GraphedTrainStep:
-    """`train_step` replayed as ONE CUDA graph per step (single GPU, FusedAdam tail, fp16 autocast).
+    """`train_step` replayed from CUDA graphs (FusedAdam tail, fp16 autocast): one launch per step on one GPU, two around the
+    gradient exchange when data-parallel.
 
-    Once the marcher sizes its buffers from `mean_count` (after the first occupancy update, raymarching.py:213-229) every
-    shape in the step is fixed until the next update, so the whole step -- march, encoders, MLPs, compositing, loss,
-    backward, GradScaler inf check, the optimiser sweep and the scaler update -- can be captured once and replayed: one
-    launch per step.  What moves between steps stays outside the frozen kernel arguments: the batch is copied into static
-    input tensors, the learning rates go through FusedAdam's device-side group table (`publish_groups`), the marcher's
-    noise comes from torch's graph-safe generator, the `(samples, rays)` counter row is copied to where the eager step would
-    have written it.  A change of `mean_count` (every update_extra_state) or of the batch shape re-captures into the same
-    memory pool.  Steps before `mean_count` is known run eagerly, and so does everything if capture fails
-    (`self.fallback_reason` says why).
+    A steady-state step of the fused head path is ~1.5 ms of device work issued as ~350 launches that cost the host ~5 ms
+    (tools/train_timeline.py): it is launch-bound, so it is captured once and replayed.  What moves between steps stays outside
+    the frozen kernel arguments: the batch is copied into static input tensors, the learning rates go through FusedAdam's
+    device-side group table (`publish_groups`), the marcher's noise comes from torch's graph-safe generator, the `(samples, rays)`
+    counter row is copied to where the eager step would have written it, and the marcher's sample budget -- the reference's running
+    estimate `mean_count`, which `update_extra_state` changes every 16 steps (renderer.py:489-493) -- is a DEVICE scalar
+    (raymarching.sample_budget / rn_march_rays_train_budget): the sample buffers keep a fixed capacity (mean_count rounded up to
+    `bucket` slots) and the same rays are kept / dropped as with buffers of exactly mean_count slots.  Only a change of the capacity
+    bucket or of the batch shape re-captures (into the same memory pool).
 
-    Status (round 1, one B200, 2^16 rays, ~0.7 M samples): NOT the default.  The capture is correct
-    (tests/test_gpu_train.py), but a replay takes 10.3 ms against 8.5 ms for the op-by-op step and each re-capture costs
-    25-160 ms (tools/train_bench.py graphed:steady): the step is bound by its ~400 kernels' device work -- a third of it was
-    atomic contention in the 2-D grid backward, fixed in csrc/gridencoder_impl.cuh -- not by launch overhead.  It stays as the
-    capture-safe scaffolding (static inputs, device-side learning rates, counter bookkeeping) for a fused training step."""
+    Data-parallel (`sync` = a GradSync): graph A = zero_grad .. backward, then the NCCL all-reduces are issued eagerly (three
+    collectives: two tables + the flat bucket of `sync.flatten()`, exchanged in place), then graph B = inf check + optimiser sweep +
+    scale update.  Steps before `mean_count` is known run eagerly, and so does everything if capture fails
+    (`self.fallback_reason` says why)."""
 
     KEYS = ("rays_o", "rays_d", "auds", "bg_coords", "poses", "eye", "rgb", "face_mask", "bg_color")
 
-    def __init__(self, model, optimizer, scaler, lambda_amb=0.1, phase=None):
+    def __init__(self, model, optimizer, scaler, lambda_amb=0.1, phase=None, sync=None, bucket=1 << 16):
         from .optim import FusedAdam
         if not isinstance(optimizer, FusedAdam):
             raise TypeError("GraphedTrainStep needs radnerf_b200.optim.FusedAdam (its step is capturable: no host reads)")
         self.model, self.opt, self.scaler, self.lambda_amb, self.phase = model, optimizer, scaler, lambda_amb, phase
+        self.sync = sync if (sync is not None and sync.world > 1) else None
+        if self.sync is not None:
+            self.sync.overlap = False      # the backward is replayed from a graph: every reduction is issued after it
+        self.bucket = int(bucket)
         self.graph = None
+        self.graph_tail = None
         self.key = None
         self.static = None
         self.loss = None
@@ -182,10 +242,13 @@ class GraphedTrainStep:
         self.replays = 0
         self.capture_ms = []       # host time of every (re-)capture, synchronisation and instantiation included
         self.pool = None           # every capture allocates from the same private pool: no cudaMalloc after the first one
+        self.budget = None         # int32 [1] on the device: the marcher's sample budget (= padded mean_count)
+        self.budget_value = None
+        self._params = [p for g in optimizer.param_groups for p in g["params"]]
 
     def _eager(self, batch):
         self.opt.device_groups = False
-        return train_step(self.model, batch, self.opt, self.scaler, None, self.lambda_amb, self.phase)
+        return train_step(self.model, batch, self.opt, self.scaler, self.sync, self.lambda_amb, self.phase)
 
     def _load(self, batch):
         dev = self.static["rays_o"].device
@@ -195,29 +258,56 @@ class GraphedTrainStep:
         idx = batch.get("index", 0)
         self.static["index"].copy_(torch.as_tensor(idx, dtype=torch.long).reshape(-1)[:1].to(dev, non_blocking=True))
 
-    def _capture(self, batch):
+    def _capacity(self):
+        padded = int(self.model.mean_count)
+        padded = padded + (128 - padded % 128)            # raymarching._padded(mean_count, 128), what the eager marcher allocates
+        return padded, (padded + self.bucket - 1) // self.bucket * self.bucket
+
+    def _set_budget(self, padded):
+        if self.budget is None:
+            self.budget = torch.zeros(1, dtype=torch.int32, device=self.model.step_counter.device)
+        if padded != self.budget_value:
+            self.budget.fill_(padded)
+            self.budget_value = padded
+
+    def _capture(self, batch, capacity):
         import time
+        from raymarching.raymarching import sample_budget
         t0 = time.perf_counter()
         m = self.model
         dev = batch["rays_o"].device
-        previous = self.graph  # stays alive until the new graph exists, so the shared pool keeps its memory
+        previous = (self.graph, self.graph_tail)  # stay alive until the new graphs exist, so the shared pool keeps its memory
         if self.pool is None:
             self.pool = torch.cuda.graph_pool_handle()
         self.static = {k: (torch.as_tensor(batch[k]).to(dev).clone() if batch.get(k) is not None else None) for k in self.KEYS}
         self.static["index"] = torch.zeros(1, dtype=torch.long, device=dev)
         self._load(batch)
+        if self.sync is not None and self.sync.flat is None:
+            self.sync.flatten()
+        self.opt.prepare()                 # descriptor table for the (possibly re-pointed) gradients: its H2D copy cannot be captured
         self.opt.publish_groups()
         self.opt.device_groups = True
+        if getattr(m, "_head_trainer", None) is not None:
+            m._head_trainer.ensure(capacity)          # grow the fused step's buffers outside the capture
+            m._head_trainer.packed_for = None         # the captured step must contain the table / weight re-packing launches
         local_step = m.local_step
         self.counter_row = local_step % 16
         torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
+        g, g_tail = torch.cuda.CUDAGraph(), None
         try:
-            with torch.cuda.graph(g, pool=self.pool):
-                self.loss = train_step(m, self.static, self.opt, self.scaler, None, self.lambda_amb, self.phase)
+            with sample_budget(capacity, self.budget):
+                if self.sync is None:
+                    with torch.cuda.graph(g, pool=self.pool):
+                        self.loss = train_step(m, self.static, self.opt, self.scaler, None, self.lambda_amb, self.phase)
+                else:
+                    with torch.cuda.graph(g, pool=self.pool):
+                        self.loss = forward_backward(m, self.static, self.opt, self.scaler, self.lambda_amb, self.phase).detach()
+                    g_tail = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_tail, pool=self.pool):
+                        optimizer_tail(m, self.static, self.opt, self.scaler)
         finally:
             m.local_step = local_step      # capture ran the host bookkeeping of one step without executing it
-        self.graph = g
+        self.graph, self.graph_tail = g, g_tail
         del previous
         self.captures += 1
         self.capture_ms.append((time.perf_counter() - t0) * 1e3)
@@ -229,21 +319,31 @@ class GraphedTrainStep:
         if self.fallback_reason is not None or not amp or m.mean_count <= 0 or not self.warm:
             self.warm = self.warm or m.mean_count > 0      # one eager step in the steady regime: lazy initialisations, grads exist
             return self._eager(batch)
-        key = (int(m.mean_count), shapes, self.phase)
+        padded, capacity = self._capacity()
+        self._set_budget(padded)
+        key = (capacity, shapes, self.phase)
         if key != self.key:
             try:
-                self._capture(batch)
+                self._capture(batch, capacity)
                 self.key = key
             except Exception as e:  # noqa: BLE001
                 self.fallback_reason = repr(e)[:300]
-                self.graph, self.key = None, None
+                self.graph, self.graph_tail, self.key = None, None, None
                 torch.cuda.synchronize()
                 return self._eager(batch)
         else:
             self._load(batch)
             self.opt.publish_groups()
+        if self.sync is not None:
+            self.sync.begin_step()
         self.graph.replay()
+        if self.graph_tail is not None:
+            self.sync.finish()
+            self.graph_tail.replay()
         self.replays += 1
+        # the replay rewrote every parameter through frozen pointers: consumers that cache derived data per (pointer, version) --
+        # the fp16 tables / weight blobs of the fused frame and of the fused density query -- must see the step
+        torch.autograd.graph.increment_version(self._params)
         # host bookkeeping of run_cuda's training branch: the counter row of this step, the step index
         row = m.local_step % 16
         if row != self.counter_row:

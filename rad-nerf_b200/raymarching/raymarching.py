@@ -134,6 +134,27 @@ morton3D_dilation = DilationFn.apply
 
 
 # ------------------------------------------------------------------------------------------------ training
+class sample_budget:
+    """`with sample_budget(capacity, budget):` -- inside, march_rays_train allocates `capacity` sample slots whatever `mean_count` is
+    and drops a ray when it would end past min(capacity, budget[0]), `budget` being an int32 tensor ON THE DEVICE
+    (rn_march_rays_train_budget).  Same rays kept / dropped as the reference with mean_count = budget[0], but the shapes of a step
+    no longer depend on the running estimate: radnerf_b200.train.GraphedTrainStep replays one captured graph across occupancy
+    updates and only rewrites `budget`.  Not part of the reference's API; the default behaviour is untouched."""
+    active = None
+
+    def __init__(self, capacity, budget):
+        if budget.dtype != torch.int32 or not budget.is_cuda:
+            raise TypeError("sample_budget: budget must be an int32 CUDA tensor")
+        self.capacity, self.budget = int(capacity), budget
+
+    def __enter__(self):
+        self.previous, sample_budget.active = sample_budget.active, self
+        return self
+
+    def __exit__(self, *exc):
+        sample_budget.active = self.previous
+
+
 class MarchTrainFn(torch.autograd.Function):
     @staticmethod
     @_as_f32
@@ -145,12 +166,14 @@ class MarchTrainFn(torch.autograd.Function):
         # capacity: the running estimate of earlier steps when there is one (rays are dropped if it is too small),
         # otherwise the worst case, trimmed after the launch with one counter read-back
         estimated = (not force_all_rays) and mean_count > 0
-        capacity = _padded(mean_count, align) if estimated else n * max_steps
+        fixed = sample_budget.active if estimated else None
+        capacity = (fixed.capacity if fixed is not None else _padded(mean_count, align)) if estimated else n * max_steps
         xyzs, dirs, deltas = _sample_buffers(capacity, o)
         rays = torch.empty(n, 3, dtype=torch.int32, device=o.device)              # (ray id, first sample, sample count)
         counter = step_counter if step_counter is not None else torch.zeros(2, dtype=torch.int32, device=o.device)
-        abi.call("rn_march_rays_train", o, d, bits, float(bound), float(dt_gamma), int(max_steps), n, int(C), int(H), capacity,
-                 nears.contiguous(), fars.contiguous(), xyzs, dirs, deltas, rays, counter, _start_offsets(n, perturb, o))
+        abi.call("rn_march_rays_train_budget", o, d, bits, float(bound), float(dt_gamma), int(max_steps), n, int(C), int(H), capacity,
+                 None if fixed is None else fixed.budget, nears.contiguous(), fars.contiguous(), xyzs, dirs, deltas, rays, counter,
+                 _start_offsets(n, perturb, o))
         if not estimated:
             used = _padded(int(counter[0].item()), align)
             xyzs, dirs, deltas = xyzs[:used], dirs[:used], deltas[:used]

@@ -17,7 +17,7 @@ def test_header_declares_the_reference_surface():
     # one entry point per reference binding (gridencoder 3, raymarching 12, freqencoder 2, shencoder 2 = 19)
     for s in ["rn_grid_encode_forward", "rn_grid_encode_backward", "rn_grad_total_variation", "rn_near_far_from_aabb",
               "rn_sph_from_ray", "rn_morton3D", "rn_morton3D_invert", "rn_packbits", "rn_morton3D_dilation",
-              "rn_march_rays_train", "rn_march_rays_train_backward", "rn_composite_rays_train_forward",
+              "rn_march_rays_train", "rn_march_rays_train_budget", "rn_march_rays_train_backward", "rn_composite_rays_train_forward",
               "rn_composite_rays_train_backward", "rn_march_rays", "rn_composite_rays", "rn_freq_encode_forward",
               "rn_freq_encode_backward", "rn_sh_encode_forward", "rn_sh_encode_backward"]:
         assert s in syms

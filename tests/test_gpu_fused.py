@@ -55,7 +55,7 @@ def _render(model, f, bg, path):
 @pytest.mark.parametrize("hw,trained_like", [(64, True), (128, True), (128, False)])
 def test_fused_frame_matches_op_by_op_path(hw, trained_like):
     """The fused renderer against the reference-ordered op-by-op path (itself bit-checked against the reference kernels).
-    Ray schedule (n_alive, n_step per iteration) and sample counts must be IDENTICAL; image/depth/weights within 2e-3:
+    Ray schedule (n_alive, n_step per iteration) and sample counts must be IDENTICAL; image/depth/weights within 1e-3 (north_star's fp16 bound):
     the fused MLP accumulates in a different order than cuBLAS (fp32 accumulation of fp16 products), and every layer output
     is rounded to fp16 in both, so one fp16 ulp (~5e-4 relative) of drift per layer is the expected scale."""
     from radnerf_b200 import frame
@@ -72,13 +72,13 @@ def test_fused_frame_matches_op_by_op_path(hw, trained_like):
         sched = frame.frame_stats(model)
         assert [(a, s) for a, s, _ in sched] == [(a, s) for a, s, _ in sched_ref], (sched, sched_ref)
         # lip-smoothed audio code: fp16 conv/linear stack, fp32 attention
-        assert (enc_a_fused - enc_a_ref).abs().max().item() <= 2e-3 * max(1.0, enc_a_ref.abs().max().item())
+        assert (enc_a_fused - enc_a_ref).abs().max().item() <= 1e-3 * max(1.0, enc_a_ref.abs().max().item())
         d_img = (out["image"] - ref["image"]).abs().max().item()
         d_dep = (out["depth"] - ref["depth"]).abs().max().item()
         d_ta = (out["torso_alpha"] - ref["torso_alpha"]).abs().max().item()
         print(f"hw={hw} trained_like={trained_like} frame={i}: |d image|={d_img:.2e} |d depth|={d_dep:.2e} |d torso_alpha|={d_ta:.2e}")
-        assert d_img <= 2e-3 and d_dep <= 2e-3 and d_ta <= 2e-3
-        assert (out["torso_color"] - ref["torso_color"].view(-1, 3)).abs().max().item() <= 2e-3
+        assert d_img <= 1e-3 and d_dep <= 1e-3 and d_ta <= 1e-3
+        assert (out["torso_color"] - ref["torso_color"].view(-1, 3)).abs().max().item() <= 1e-3
 
 
 def test_fused_frame_sample_counts_match_reference_slots():
@@ -199,7 +199,7 @@ def _custom_scene(hw, n_frames=2, seed=0, **opt_kw):
 ])
 def test_fused_frame_on_the_reference_configurations(name, hw, opt_kw):
     """BASELINE.json's other configurations as parity cases: fused frame vs the op-by-op path, identical ray schedule,
-    image / depth / torso within 2e-3 (fp16 tables with O(1) entries)."""
+    image / depth / torso within 1e-3 (fp16 tables with O(1) entries)."""
     from radnerf_b200 import frame
     model, frames, bg = _custom_scene(hw, **opt_kw)
     assert frame.supported(model), name
@@ -214,11 +214,11 @@ def test_fused_frame_on_the_reference_configurations(name, hw, opt_kw):
         torch.cuda.synchronize()
         enc_fused = model.enc_a.clone()
         assert [(a, s) for a, s, _ in frame.frame_stats(model)] == sched_ref, name
-        assert (enc_fused - enc_ops).abs().max().item() <= 2e-3 * max(1.0, enc_ops.abs().max().item())
-        assert (out["image"] - ref["image"]).abs().max().item() <= 2e-3, name
-        assert (out["depth"] - ref["depth"]).abs().max().item() <= 2e-3, name
+        assert (enc_fused - enc_ops).abs().max().item() <= 1e-3 * max(1.0, enc_ops.abs().max().item())
+        assert (out["image"] - ref["image"]).abs().max().item() <= 1e-3, name
+        assert (out["depth"] - ref["depth"]).abs().max().item() <= 1e-3, name
         if model.torso:
-            assert (out["torso_alpha"] - ref["torso_alpha"]).abs().max().item() <= 2e-3, name
+            assert (out["torso_alpha"] - ref["torso_alpha"]).abs().max().item() <= 1e-3, name
 
 
 def test_pipelined_frames_keep_the_lip_smoothing_chain():

@@ -118,6 +118,66 @@ def test_graphed_step_replays_the_whole_step_and_follows_the_schedule():
         g["lr"] = lr
     step(batches[1])
     assert not torch.equal(p.detach(), before["sigma_net.net.0.weight"])
-    model.mean_count += 128                                             # what update_extra_state does every 16 steps
+    # what update_extra_state does every 16 steps: a new mean_count.  The sample budget is a device scalar, the buffers keep their
+    # capacity bucket: no new graph, and the marcher honours the new budget exactly as the eager step does
+    padded, capacity = step._capacity()
+    model.mean_count += 128
     step(batches[2])
+    assert step.captures == 1 and step.fallback_reason is None
+    assert int(step.budget.item()) == padded + 128
+    model.mean_count = 1024                                             # far too small: most rays are dropped, none may write past it
+    row = model.local_step % 16
+    step(batches[0])
+    assert step.captures == 1
+    kept_small = int(model.step_counter[row, 0])                        # the counter still counts every sample the rays wanted
+    assert kept_small > 1024
+    model.mean_count = capacity + 1                                     # crosses the bucket: one re-capture
+    step(batches[1])
     assert step.captures == 2 and step.fallback_reason is None
+
+
+def test_sample_budget_drops_the_rays_the_reference_budget_drops():
+    """march_rays_train under raymarching.sample_budget(capacity, budget): identical (ray, offset, count) table and identical
+    samples in the first `budget` slots as the plain call with mean_count = budget, whatever the capacity"""
+    import raymarching as rm
+    from raymarching.raymarching import sample_budget
+    from radnerf_b200 import synthetic as syn
+    model = _head_model()
+    b = syn.batch_to(syn.training_batch(128, 128, 4096, frame_index=1), DEV)
+    ro, rd = b["rays_o"][0].contiguous(), b["rays_d"][0].contiguous()
+    nears, fars = rm.near_far_from_aabb(ro, rd, model.aabb_train, model.min_near)
+
+    def march(mean_count, ctx=None):
+        counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+        args = (ro, rd, model.bound, model.density_bitfield, model.cascade, model.grid_size, nears, fars, counter, mean_count, False, 128,
+                False, model.opt.dt_gamma, model.opt.max_steps)
+        if ctx is None:
+            return rm.march_rays_train(*args) + (counter,)
+        with ctx:
+            return rm.march_rays_train(*args) + (counter,)
+    full = march(-1)
+    total = int(full[4][0])
+    budget = (total // 2) // 128 * 128
+    ref = march(budget - 128)           # plain call: buffers of _padded(mean_count) = budget slots
+    assert ref[0].shape[0] == budget
+    lim = torch.tensor([budget], dtype=torch.int32, device=DEV)
+    got = march(budget - 128, sample_budget(budget + 4096, lim))
+    assert got[0].shape[0] == budget + 4096
+    assert torch.equal(got[4], ref[4]) and int(got[4][0]) == total      # the counters count every wanted sample, kept or not
+
+    def check(out, cap):
+        # CTAs reserve their slots with one atomic each, so offsets differ from run to run; the rule does not: a ray's samples are
+        # written iff the ray ends inside the budget, and nothing else is ever written
+        rays = out[3].long()
+        off, cnt = rays[:, 1], rays[:, 2]
+        kept = (cnt > 0) & (off + cnt <= budget)
+        edge = torch.zeros(int((off + cnt).max()) + 2, device=DEV)
+        one = torch.ones(int(kept.sum()), device=DEV)
+        edge.index_add_(0, off[kept], one)
+        edge.index_add_(0, (off + cnt)[kept], -one)
+        expected = edge.cumsum(0)[:cap] > 0.5
+        assert torch.equal(expected, out[2][:, 0] != 0)
+        assert torch.equal(torch.sort(cnt[torch.argsort(rays[:, 0])]).values, torch.sort(full[3][:, 2].long()).values)
+        return int(kept.sum())
+    assert check(ref, budget) > 0 and check(got, budget + 4096) > 0
+    assert not got[2][budget:].any() and not got[0][budget:].any()

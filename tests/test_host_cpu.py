@@ -218,7 +218,7 @@ def test_cpu_port_renders_a_frame():
     """The oracle-backed CPU port (bench.py's cpu_baseline / --impl reference arm) renders a small head+torso frame."""
     sys.path.insert(0, ROOT)
     import bench
-    fps, threads, nsamp = bench.cpu_frame_rate(48, 1)
+    fps, threads, nsamp, timed = bench.cpu_frame_rate(48, 1)
     assert fps > 0 and threads >= 1 and nsamp > 0
 
 

@@ -66,7 +66,7 @@ def _errors(loss, image, counter, grads, phase="head"):
     return e
 
 
-def _check(e, tol, loss_tol, image_tol, rows_tol):
+def _check(e, tol, loss_tol, image_tol, rows_tol, norm_tol=None, colsum_tol=None):
     assert e["names_equal"]                    # the same tensors receive a gradient
     assert e["counter_equal"]                  # samples / rays the marcher emitted: exact
     assert e["loss"] <= loss_tol, e["loss"]
@@ -74,7 +74,8 @@ def _check(e, tol, loss_tol, image_tol, rows_tol):
     bad = {k: v for k, v in e["grad"].items() if v > tol}
     assert not bad, bad
     for name, t in e["table"].items():
-        assert t["norm"] <= tol and t["colsum"] <= 50 * tol and t["nonzero_rows"] <= rows_tol, (name, t)
+        assert t["norm"] <= (tol if norm_tol is None else norm_tol), (name, t)
+        assert t["colsum"] <= (50 * tol if colsum_tol is None else colsum_tol) and t["nonzero_rows"] <= rows_tol, (name, t)
 
 
 @pytest.mark.parametrize("phase", ["head", "torso"])
@@ -116,7 +117,9 @@ def test_training_step_cuda_fp32_matches_the_reference_classes():
     if os.path.isdir(out):      # measured deviations, for the record (profiles/r01_train_parity_errors.json)
         import json
         json.dump(e, open(os.path.join(out, "train_parity_errors.json"), "w"), indent=1)
-    _check(e, tol=1e-2, loss_tol=2e-6, image_tol=1e-5, rows_tol=1e-3)
+    # single entries: 1e-2 of the tensor's largest (cancelling sums, ReLU flips -- see above); the AGGREGATES are held tightly: loss
+    # 5e-7, prediction 2e-6, table-gradient norms 2e-5 (north_star's fp32 bound is 1e-5; measured 5.0e-6 / 1.1e-5), touched rows exact
+    _check(e, tol=1e-2, loss_tol=5e-7, image_tol=2e-6, rows_tol=0.0, norm_tol=2e-5, colsum_tol=5e-2)
 
 
 @pytest.mark.gpu
@@ -124,9 +127,7 @@ def test_training_step_torso_phase_cuda_fp32_against_the_reference_classes():
     """the torso phase on the CUDA operators, fp32.  The torso branch's inputs go through the frequency encoder, which on the
     GPU is `__sinf` as in the reference's CUDA build (-use_fast_math) while the golden's CPU run used libm (<= 2e-3 apart at
     2^9 rad, tests/test_oracle_golden.py; 5e-5 on the torso alpha in test_network_parity), so this cannot be as tight as the
-    head phase.  PROVISIONAL bounds (first run is the round-end run; the measured deviations are written to
-    gpurun_out/train_parity_errors_torso.json and the bounds will be set from them): loss 1e-3, prediction 5e-3, every
-    gradient tensor within 10 % of its largest entry -- enough to catch a missing term, a sign or a wrong row, not rounding"""
+    head phase on single entries; the aggregates are (bounds set from the measured deviations, see the call below)."""
     import train_case as tc
     noise = torch.from_numpy(tc.noise()).cuda()
     import raymarching.raymarching as rmod
@@ -143,4 +144,6 @@ def test_training_step_torso_phase_cuda_fp32_against_the_reference_classes():
     if os.path.isdir(out):
         import json
         json.dump(e, open(os.path.join(out, "train_parity_errors_torso.json"), "w"), indent=1)
-    _check(e, tol=1e-1, loss_tol=1e-3, image_tol=5e-3, rows_tol=0.2)   # a deformation moved by 1e-4 crosses cells of the 2048-wide level
+    # measured on a B200 (profiles/r02_train_parity_errors_torso.json): loss 6e-8, prediction 4.4e-5, table-gradient norm 1.2e-7, touched
+    # rows identical, worst single gradient entry 1.3e-3 of its tensor's largest (deformation MLP: __sinf vs libm upstream of it)
+    _check(e, tol=5e-3, loss_tol=1e-6, image_tol=2e-4, rows_tol=1e-3, norm_tol=2e-5, colsum_tol=5e-3)
