@@ -28,6 +28,10 @@ import time
 
 import numpy as np
 
+# more hardware connections than the default 8: frame lanes x side branches must not share queues (see radnerf_b200/__init__.py);
+# has to be in the environment before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "rad-nerf_b200")):
     if p not in sys.path:
@@ -49,7 +53,8 @@ def parse():
     ap.add_argument("--repeats", type=int, default=0, help="timed windows of --steps frames (0 = at least 15, enough to cover ~1 s)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE configs[0], [1], [4] legs")
     ap.add_argument("--hw", type=int, default=HW)
-    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU (fused path; 1 = strictly one frame at a time)")
+    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (fused path; 1 = strictly one frame at a time; 0 = 8: a frame is a "
+                    "chain of ~20 dependent launches of which only the network kernel fills the GPU -- and on 4-8 GPUs not even that)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE configs[3]) of the N=1 line")
     ap.add_argument("--no-ref-cuda", action="store_true")
@@ -243,6 +248,8 @@ def run_ours(args):
     abi.lib()  # fail loudly if the CUDA library is missing
 
     hw = args.hw
+    if args.lanes <= 0:
+        args.lanes = 8
     model = make_model(dev)
     frames, intr, bg = make_frames(hw)
     bg_t = torch.from_numpy(bg).to(dev)[None]
@@ -253,7 +260,8 @@ def run_ours(args):
 
     from radnerf_b200.sharding import FrameSharder
     sharder = FrameSharder(hw, hw, world, rank, dev)
-    gather_impl = "none" if world == 1 else ("peer stores over NVLink (symmetric memory) + barrier" if sharder.enable_peer_gather(n_buffers=max(2, args.lanes))
+    gather_impl = "none" if world == 1 else ("gather-to-root: peer stores over NVLink into rank 0's frame buffer (symmetric memory), arrival counter + "
+                                              "consumed flags (release/acquire, system scope), no barrier" if sharder.enable_peer_gather(n_buffers=max(2, args.lanes))
                                               and os.environ.get("RADNERF_GATHER", "peer") == "peer" else "nccl all_gather + un-permute")
     if gather_impl.startswith("nccl"):
         sharder.peer = None
@@ -711,10 +719,33 @@ def training_rate(dev, n_rays=65536, steps=64, ops=None, tail="fused", graphed=T
 
 def main():
     args = parse()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner, the reference's wrappers at import)
+    # are sent to stderr for the duration of the run, the line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    captured = []
+    import builtins
+    _print = builtins.print
+
+    def emit(*a, **k):
+        if k.get("file") in (None, sys.stdout) and len(a) == 1 and isinstance(a[0], str) and a[0].startswith("{"):
+            captured.append(a[0])
+        else:
+            _print(*a, **k)
+    builtins.print = emit
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_ours(args)
+    finally:
+        builtins.print = _print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in captured:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":

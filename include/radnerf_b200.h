@@ -179,6 +179,22 @@ int rn_image_to_uint8(const float* image, uint8_t* out, uint64_t n_values, void*
  * orders the stores against the readers with a cross-rank barrier. */
 int rn_scatter_rows_to_peers(const float* local, const int32_t* ids, uint32_t n_local, uint32_t run_pixels,
                              const uint64_t* peers, uint32_t world, void* stream);
+/* Gather-to-root with flags instead of a barrier (the frames are delivered by ONE rank, so only its buffer is assembled):
+ * a non-root rank waits until the root has consumed frame seq-1 of frame buffer `slot` (ctrl word 2*slot+1 in ITS OWN control
+ * block, written by the root), stores its rows into the root's frame buffer and adds 1 per CTA (rn_scatter_signal_ctas of them) to
+ * the root's arrival counter (ctrl word 2*slot; release, system scope).  The root stores its own rows with the same call (no flags).
+ * frame_peers / ctrl_peers: DEVICE arrays of `world` base addresses of the [H*W,3] fp32 frame buffers / of the uint64 control blocks
+ * (>= 2 * slots words, zero-initialised before the first frame).  seq = 1, 2, ... per slot, the same on every rank. */
+int rn_scatter_rows_to_root(const float* local, const int32_t* ids, uint32_t n_local, uint32_t run_pixels, const uint64_t* frame_peers,
+                            const uint64_t* ctrl_peers, uint32_t world, uint32_t rank, uint32_t root, uint32_t slot, uint64_t seq,
+                            void* stream);
+uint32_t rn_scatter_signal_ctas(uint32_t n_local, uint32_t run_pixels);
+/* Root side: waits until seq * (world-1) * scatter_ctas arrivals have been counted for `slot`, copies the assembled frame (n_values
+ * fp32) to dst -- as fp32, or as uint8 `(v * 255)` truncated when to_uint8 (dst NULL: nothing is copied) -- and then writes seq into
+ * every other rank's consumed word.  ctrl_peers NULL: plain copy / conversion without any exchange (one GPU).  ticket: a zeroed
+ * device uint32 owned by the caller (one per slot). */
+int rn_stage_frame_at_root(const float* frame, void* dst, uint64_t n_values, uint32_t to_uint8, const uint64_t* ctrl_peers, uint32_t world,
+                           uint32_t root, uint32_t slot, uint64_t seq, uint32_t scatter_ctas, uint32_t* ticket, void* stream);
 
 /* ------------------------------------------------------------------ fused inference frame ------------ */
 /* One call per stage of NeRFRenderer.run_cuda's inference branch (nerf/renderer.py:158-316) with no host round trip:
@@ -284,7 +300,7 @@ int rn_frame_finalize(uint32_t N, const float* weights_sum, float* depth, float*
  * (the frame loop of Trainer.test, nerf/utils.py:905-960, in steady state: every buffer, stream, event and the lane's
  * captured frame graph are fixed; see csrc/pipeline.cu for the choreography).  Events come from rn_event_create.
  * phase bit 0: copy-in, rays, conditioning, frame graph [, scatter to peers]; bit 1: [staging + device->host copy,] ev_done.
- * Both bits in one call when there is no cross-rank barrier to issue in between. */
+ * Both bits in one call when there is no cross-rank barrier to issue in between (one GPU, or the flag-based gather-to-root). */
 typedef struct rn_lane_submit {
     void* lane_stream; void* cond_stream; void* copy_stream;
     void* ev_in; void* ev_cond; void* ev_done; void* ev_staged; void* ev_delivered;
@@ -298,6 +314,10 @@ typedef struct rn_lane_submit {
     uint32_t n_local, run_pixels, world, phase;
     const void* stage_src; void* stage_dst; void* host_dst; uint64_t image_bytes;   /* host_dst NULL: no delivery */
     uint32_t to_uint8, reserved;   /* to_uint8: stage_src holds image_bytes/4 fp32 values; stage_dst / host_dst receive image_bytes/4 bytes */
+    /* gather-to-root exchange (rn_scatter_rows_to_root / rn_stage_frame_at_root); ctrl_peers NULL: the older all-to-all scatter, whose
+     * cross-rank barrier the caller issues between phase 1 and phase 2 */
+    const uint64_t* ctrl_peers; uint32_t* ticket; uint64_t frame_seq;
+    uint32_t rank, root, slot, scatter_ctas;
 } rn_lane_submit;
 int rn_lane_submit_frame(const rn_lane_submit* s);
 int rn_event_create(void** ev);

@@ -73,13 +73,32 @@ extern "C" int rn_lane_submit_frame(const rn_lane_submit* s) {
         RN_CU(cudaGraphLaunch((cudaGraphExec_t)s->graph_exec, ls));
         rn_note_graph_replay(s->graph_kernels);
         if (s->peers && s->world > 1) {
-            rc = rn_scatter_rows_to_peers(s->image_local, s->ids, s->n_local, s->run_pixels, s->peers, s->world, ls);
+            rc = s->ctrl_peers ? rn_scatter_rows_to_root(s->image_local, s->ids, s->n_local, s->run_pixels, s->peers, s->ctrl_peers, s->world, s->rank,
+                                                         s->root, s->slot, s->frame_seq, ls)
+                               : rn_scatter_rows_to_peers(s->image_local, s->ids, s->n_local, s->run_pixels, s->peers, s->world, ls);
             if (rc) return rc;
         }
     }
     if (s->phase & 2u) {
         RN_REQUIRE(s->ev_done, "phase 2 needs ev_done");
-        if (s->host_dst) {
+        const bool exchange = s->ctrl_peers && s->world > 1;
+        if (exchange && s->rank == s->root) {
+            // the root assembles: wait for the other ranks' rows (arrival counter), stage, release the buffer (consumed flags) -- one kernel
+            const bool deliver = s->host_dst != nullptr;
+            if (deliver) {
+                RN_REQUIRE(s->ev_staged && s->ev_delivered && s->stage_src && s->stage_dst, "delivery needs staging buffers and events");
+                RN_CU(cudaStreamWaitEvent(ls, (cudaEvent_t)s->ev_delivered, 0));   // the copy that last read this staging slot has drained
+            }
+            int rc = rn_stage_frame_at_root((const float*)s->stage_src, deliver ? s->stage_dst : nullptr, s->image_bytes / 4, s->to_uint8, s->ctrl_peers,
+                                            s->world, s->root, s->slot, s->frame_seq, s->scatter_ctas, s->ticket, ls);
+            if (rc) return rc;
+            if (deliver) {
+                RN_CU(cudaEventRecord((cudaEvent_t)s->ev_staged, ls));
+                RN_CU(cudaStreamWaitEvent(xs, (cudaEvent_t)s->ev_staged, 0));
+                RN_CU(cudaMemcpyAsync(s->host_dst, s->stage_dst, s->to_uint8 ? s->image_bytes / 4 : s->image_bytes, cudaMemcpyDeviceToHost, xs));
+                RN_CU(cudaEventRecord((cudaEvent_t)s->ev_delivered, xs));
+            }
+        } else if (s->host_dst && !exchange) {
             RN_REQUIRE(s->ev_staged && s->ev_delivered && s->stage_src && s->stage_dst, "delivery needs staging buffers and events");
             RN_CU(cudaStreamWaitEvent(ls, (cudaEvent_t)s->ev_delivered, 0));   // the copy that last read this staging slot has drained
             uint64_t out_bytes = s->image_bytes;

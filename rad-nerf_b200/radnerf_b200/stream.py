@@ -39,7 +39,9 @@ class LaneSubmit(C.Structure):   # rn_lane_submit (include/radnerf_b200.h)
                 ("image_local", _vp), ("ids", _vp), ("peers", _vp),
                 ("n_local", _u32), ("run_pixels", _u32), ("world", _u32), ("phase", _u32),
                 ("stage_src", _vp), ("stage_dst", _vp), ("host_dst", _vp), ("image_bytes", _u64),
-                ("to_uint8", _u32), ("reserved", _u32)]
+                ("to_uint8", _u32), ("reserved", _u32),
+                ("ctrl_peers", _vp), ("ticket", _vp), ("frame_seq", _u64),
+                ("rank", _u32), ("root", _u32), ("slot", _u32), ("scatter_ctas", _u32)]
 
 
 abi.register("rn_lane_submit_frame", [C.POINTER(LaneSubmit)])
@@ -164,6 +166,20 @@ class FrameStreamer:
 
     def _post(self, out, k):
         """on lane k's stream, right after the frame: assemble the image, stage it, start the copy-out"""
+        if self.sharder.world > 1 and self.sharder.ctrl is not None:
+            # flag-based gather-to-root: scatter + (on the root) wait / stage / release in two launches, no barrier
+            ls = torch.cuda.current_stream(self.dev)
+            if self.deliver:
+                ls.wait_event(self.delivered[k])      # the copy that last read this staging slot has drained
+            img = self.sharder.gather_to_root(out["image"].view(-1, 3), slot=k, stage_to=self.dev_stage[k] if self.deliver else None,
+                                              to_uint8=self.u8)
+            if self.deliver:
+                self.staged[k].record(ls)
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(self.staged[k])
+                    self.host_out[k].copy_(self.dev_stage[k], non_blocking=True)
+                    self.delivered[k].record(self.copy_stream)
+            return img
         img = self.sharder.gather(out["image"].view(-1, 3), slot=k)
         if self.deliver:
             ls = torch.cuda.current_stream(self.dev)
@@ -273,6 +289,11 @@ class FrameStreamer:
             bufs, hdls, ids32 = peer
             s.ids, s.peers, s.n_local, s.run_pixels, s.world = ids32.data_ptr(), hdls[k % len(bufs)].buffer_ptrs_dev, image.shape[0], self.W, self.sharder.world
             s.stage_src = bufs[k % len(bufs)].data_ptr()
+            if self.sharder.ctrl is not None:
+                ctrl, ctrl_hdl, tickets, _, ctas = self.sharder.ctrl
+                s.ctrl_peers, s.scatter_ctas = ctrl_hdl.buffer_ptrs_dev, ctas
+                s.rank, s.root, s.slot = self.sharder.rank, self.sharder.root, k % len(bufs)
+                s.ticket = tickets[s.slot:s.slot + 1].data_ptr()
         else:
             s.stage_src = image.data_ptr()
         s.stage_dst, s.host_dst = self.dev_stage[k].data_ptr(), (self.host_out[k].data_ptr() if self.deliver else None)
@@ -301,7 +322,9 @@ class FrameStreamer:
         s.packed_bytes = 4 * (24 if head_only else self.n_in)   # streaming: the audio part is already in the lane's block
         self.__dict__.setdefault("_keep", {})[k] = packed   # the async copy-in reads it: alive until the lane's next frame
         L = abi.lib()
-        if barrier is None:
+        if barrier is None or s.ctrl_peers:
+            if s.ctrl_peers:
+                s.frame_seq = self.sharder.next_seq(s.slot)
             s.phase = 3
             abi.check(L.rn_lane_submit_frame(C.byref(s)))
         else:
