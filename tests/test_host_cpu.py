@@ -298,7 +298,6 @@ def test_config1_case(oracle):
     shuffled["rays"] = new_rays
     for key in pieces:
         shuffled[key] = np.concatenate(pieces[key])
-    for key in ("weights_sum", "ambient_sum", "depth", "image"):
-        shuffled[key] = res[key][perm]
+    # per-ray outputs are addressed by ray id (raymarching.cu:622, 690-697): a different slot order leaves them where they are
     e = c1.compare(shuffled, res)
     assert all(v is True or v == 0.0 for v in e.values()), e
