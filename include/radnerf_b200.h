@@ -93,6 +93,14 @@ int rn_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* strea
 int rn_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream);
 /* replaces packbits (raymarching.h:11, raymarching.cu:267-300). grid [8N] f32 -> bitfield [N] u8, LSB first */
 int rn_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream);
+/* as rn_packbits with the threshold min(density_thresh, *mean_density), mean_density a DEVICE scalar (NULL: plain density_thresh):
+ * the `min(self.mean_density, self.density_thresh)` of update_extra_state (nerf/renderer.py:471) without reading the mean back */
+int rn_packbits_min(const float* grid, uint32_t N, float density_thresh, const float* mean_density, uint8_t* bitfield, void* stream);
+/* The grid merge of update_extra_state (nerf/renderer.py:463-468) in one pass: where grid >= 0 and fresh >= 0,
+ * grid = max(grid * decay, fresh) (in place); *mean_out = mean(clamp(grid, 0)) over all n cells (deterministic two-stage sum in
+ * double).  workspace: rn_occupancy_merge_workspace_bytes() bytes, zeroed once before the first call. */
+int rn_occupancy_merge(float* grid, const float* fresh, uint32_t n, float decay, void* workspace, float* mean_out, void* stream);
+uint32_t rn_occupancy_merge_workspace_bytes(void);
 /* replaces morton3D_dilation (raymarching.h:12, raymarching.cu:304-341). grid [C,H^3] f32 Morton-indexed */
 int rn_morton3D_dilation(const float* grid, uint32_t C, uint32_t H, float* grid_dilation, void* stream);
 

@@ -122,8 +122,9 @@ __device__ __forceinline__ uint32_t pack8(const float4 a, const float4 b, float 
 }
 
 __global__ void __launch_bounds__(256)
-packbits_kernel(const float* __restrict__ grid, uint32_t N, float thresh, uint8_t* __restrict__ bitfield,
+packbits_kernel(const float* __restrict__ grid, uint32_t N, float thresh, const float* __restrict__ thresh_dev, uint8_t* __restrict__ bitfield,
                 uint32_t vec_ok) {
+    if (thresh_dev) thresh = fminf(__ldg(thresh_dev), thresh);   // min(mean density on the device, density_thresh): renderer.py:471
     const uint32_t nwords = vec_ok ? N / 4 : 0;
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
         const float4* g = reinterpret_cast<const float4*>(grid) + (size_t)w * 8;
@@ -142,6 +143,46 @@ packbits_kernel(const float* __restrict__ grid, uint32_t N, float thresh, uint8_
 #pragma unroll
         for (int i = 0; i < 8; ++i) bits |= (g[i] > thresh) ? (1u << i) : 0u;
         bitfield[n] = (uint8_t)bits;
+    }
+}
+
+// Occupancy merge of update_extra_state (nerf/renderer.py:463-468): where BOTH the running grid and the freshly queried (dilated) grid
+// are valid (>= 0), grid = max(grid * decay, fresh); then mean(clamp(grid, 0)) over all cells.  One pass, in place, and the mean
+// stays on the device (per-CTA partial sums in double, added in CTA order by the last CTA: deterministic) -- the reference's boolean
+// mask indexing and `.item()` cost three host synchronisations per update.
+__global__ void __launch_bounds__(256)
+occupancy_merge_kernel(float* __restrict__ grid, const float* __restrict__ fresh, uint32_t n, float decay, double* __restrict__ partials,
+                       uint32_t* __restrict__ ticket, float* __restrict__ mean_out) {
+    __shared__ double s_sum[8];
+    __shared__ uint32_t s_last;
+    double acc = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float g = grid[i];
+        const float f = __ldg(fresh + i);
+        if (g >= 0.f && f >= 0.f) {
+            g = fmaxf(__fmul_rn(g, decay), f);
+            grid[i] = g;
+        }
+        acc += (double)fmaxf(g, 0.f);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_sum[w];
+        partials[blockIdx.x] = t;
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (uint32_t b = 0; b < gridDim.x; ++b) t += partials[b];
+        *mean_out = (float)(t / (double)n);
+        *ticket = 0u;
     }
 }
 
@@ -521,12 +562,27 @@ extern "C" int rn_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* c
 }
 
 extern "C" int rn_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream) {
+    return rn_packbits_min(grid, N, density_thresh, nullptr, bitfield, stream);
+}
+
+extern "C" int rn_packbits_min(const float* grid, uint32_t N, float density_thresh, const float* mean_density, uint8_t* bitfield, void* stream) {
     if (N == 0) return RN_OK;
     RN_REQUIRE(grid && bitfield, "null pointer");
     const uint32_t vec_ok = ((uintptr_t)grid % 16 == 0) && ((uintptr_t)bitfield % 4 == 0);
     const uint32_t work = vec_ok ? (N + 3) / 4 : N;
-    packbits_kernel<<<wave_grid(work, 256, 8), 256, 0, RN_STREAM>>>(grid, N, density_thresh, bitfield, vec_ok);
+    packbits_kernel<<<wave_grid(work, 256, 8), 256, 0, RN_STREAM>>>(grid, N, density_thresh, mean_density, bitfield, vec_ok);
     return finish_launch("rn_packbits");
+}
+
+extern "C" uint32_t rn_occupancy_merge_workspace_bytes(void) { return RN_NUM_SMS * 8 * (uint32_t)sizeof(double) + 16; }
+
+extern "C" int rn_occupancy_merge(float* grid, const float* fresh, uint32_t n, float decay, void* workspace, float* mean_out, void* stream) {
+    RN_REQUIRE(grid && fresh && workspace && mean_out && n >= 1, "null pointer");
+    RN_REQUIRE(((uintptr_t)workspace & 7) == 0, "workspace must be 8-byte aligned");
+    double* partials = (double*)workspace;
+    uint32_t* ticket = (uint32_t*)((uint8_t*)workspace + RN_NUM_SMS * 8 * sizeof(double));   // zero before the first call; the kernel re-arms it
+    occupancy_merge_kernel<<<wave_grid(n, 256 * 4, 8), 256, 0, RN_STREAM>>>(grid, fresh, n, decay, partials, ticket, mean_out);
+    return finish_launch("rn_occupancy_merge");
 }
 
 extern "C" int rn_morton3D_dilation(const float* grid, uint32_t C, uint32_t H, float* grid_dilation, void* stream) {

@@ -412,6 +412,30 @@ class NeRFNetwork(nn.Module):
         results['image'] = image
         return results
 
+    # ---- mean_density / mean_count: plain Python numbers for every reader (the reference keeps them as such, renderer.py:470, 493), but
+    #      update_extra_state leaves them on the DEVICE and the host copy is only made when somebody asks: no host synchronisation
+    #      inside the training loop (GraphedTrainStep consumes the device values directly)
+    @property
+    def mean_density(self):
+        if self._mean_density_host is None:
+            self._mean_density_host = float(self._mean_density_dev.item())
+        return self._mean_density_host
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self._mean_density_host, self._mean_density_dev = float(v), None
+
+    @property
+    def mean_count(self):
+        if self._mean_count_host is None:
+            self._mean_count_host = int(self._mean_count_dev.item())
+        return self._mean_count_host
+
+    @mean_count.setter
+    def mean_count(self, v):
+        self._mean_count_host, self._mean_count_dev = int(v), None
+        self.mean_count_version = getattr(self, "mean_count_version", 0) + 1
+
     # fused_train: "auto" (default) = use the fused training kernels of radnerf_b200.fused_train whenever the step is the one they
     # implement (CUDA, fp16 autocast, the stock head architecture, this repo's operators); False = always op by op (the parity yardstick)
     fused_train = "auto"
@@ -527,11 +551,23 @@ class NeRFNetwork(nn.Module):
         if not self.torso:   # the head grid is frozen while the torso trains
             eye = self.eye_area[[rand_idx]].to(dev) if self.exp_eye else None
             fresh = rm.morton3D_dilation(self._query_density_grid(enc_a, eye))
-            both_valid = (self.density_grid >= 0) & (fresh >= 0)
-            self.density_grid[both_valid] = torch.maximum(self.density_grid[both_valid] * decay, fresh[both_valid])
-            self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()   # untrained (-1) cells count as empty
-            self.iter_density += 1
-            self.density_bitfield = rm.packbits(self.density_grid, min(self.mean_density, self.density_thresh), self.density_bitfield)
+            if isinstance(self.ops, DefaultOps) and dev.type == "cuda":
+                # merge, mean and re-pack on the device: two launches, no boolean-mask indexing (a hidden sync each), no `.item()`
+                from . import abi
+                if getattr(self, "_occ_ws", None) is None or self._occ_ws.device != dev:
+                    self._occ_ws = torch.zeros(int(abi.lib().rn_occupancy_merge_workspace_bytes()) // 8 + 1, dtype=torch.float64, device=dev)
+                mean = torch.empty(1, dtype=torch.float32, device=dev)
+                abi.call("rn_occupancy_merge", self.density_grid, fresh.contiguous(), self.density_grid.numel(), float(decay), self._occ_ws, mean)
+                abi.call("rn_packbits_min", self.density_grid, self.density_bitfield.numel(), float(self.density_thresh), mean, self.density_bitfield)
+                torch.autograd.graph.increment_version(self.density_bitfield)     # written through the raw pointer (see PackbitsFn)
+                self._mean_density_dev, self._mean_density_host = mean, None     # untrained (-1) cells count as empty
+                self.iter_density += 1
+            else:
+                both_valid = (self.density_grid >= 0) & (fresh >= 0)
+                self.density_grid[both_valid] = torch.maximum(self.density_grid[both_valid] * decay, fresh[both_valid])
+                self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()   # untrained (-1) cells count as empty
+                self.iter_density += 1
+                self.density_bitfield = rm.packbits(self.density_grid, min(self.mean_density, self.density_thresh), self.density_bitfield)
         else:
             from .posemath import convert_poses
             k = random.randint(0, self.poses.shape[0] - 1)
@@ -543,5 +579,10 @@ class NeRFNetwork(nn.Module):
 
         steps = min(16, self.local_step)
         if steps > 0:
-            self.mean_count = int(self.step_counter[:steps, 0].sum().item() / steps)
+            if dev.type == "cuda":      # int(sum / steps) of the reference, left on the device; read back lazily (`mean_count` property)
+                self._mean_count_dev = torch.div(self.step_counter[:steps, 0].sum(), steps, rounding_mode="floor").to(torch.int32).reshape(1)
+                self._mean_count_host = None
+                self.mean_count_version = getattr(self, "mean_count_version", 0) + 1
+            else:
+                self.mean_count = int(self.step_counter[:steps, 0].sum().item() / steps)
         self.local_step = 0

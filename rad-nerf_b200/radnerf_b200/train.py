@@ -244,6 +244,9 @@ class GraphedTrainStep:
         self.pool = None           # every capture allocates from the same private pool: no cudaMalloc after the first one
         self.budget = None         # int32 [1] on the device: the marcher's sample budget (= padded mean_count)
         self.budget_value = None
+        self.mc_version = None     # model.mean_count_version the budget was last refreshed for
+        self.mc_host = 0           # last mean_count known to the HOST (decides the capacity bucket)
+        self.mc_pending = None     # (pinned int32, event): an asynchronous read-back of a device-side mean_count
         self._params = [p for g in optimizer.param_groups for p in g["params"]]
 
     def _eager(self, batch):
@@ -258,8 +261,8 @@ class GraphedTrainStep:
         idx = batch.get("index", 0)
         self.static["index"].copy_(torch.as_tensor(idx, dtype=torch.long).reshape(-1)[:1].to(dev, non_blocking=True))
 
-    def _capacity(self):
-        padded = int(self.model.mean_count)
+    def _capacity(self, mean_count=None):
+        padded = int(self.mc_host if mean_count is None else mean_count)
         padded = padded + (128 - padded % 128)            # raymarching._padded(mean_count, 128), what the eager marcher allocates
         return padded, (padded + self.bucket - 1) // self.bucket * self.bucket
 
@@ -269,6 +272,33 @@ class GraphedTrainStep:
         if padded != self.budget_value:
             self.budget.fill_(padded)
             self.budget_value = padded
+
+    def _follow_mean_count(self):
+        """keep the device-side budget equal to the padded mean_count without stalling the host: a mean_count that update_extra_state
+        left on the device is padded there and copied into `budget` in stream order; its value reaches the host through an asynchronous
+        copy that is only LOOKED at once it has completed (it decides whether the capacity bucket must grow -- until then the marcher
+        clamps to the current capacity, i.e. at worst drops a few more rays for a few steps)"""
+        m = self.model
+        v = getattr(m, "mean_count_version", 0)
+        if v != self.mc_version:
+            self.mc_version = v
+            t = getattr(m, "_mean_count_dev", None)
+            if t is None or self.budget is None or self.graph is None:
+                self.mc_host = int(m.mean_count)           # host value (or the very first capture): plain path
+                self.mc_pending = None
+                self._set_budget(self._capacity()[0])
+            else:
+                self.budget.copy_(t + (128 - t % 128))
+                self.budget_value = None
+                host = torch.empty(1, dtype=torch.int32).pin_memory()
+                host.copy_(t, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                self.mc_pending = (host, ev)
+        if self.mc_pending is not None and self.mc_pending[1].query():
+            self.mc_host = int(self.mc_pending[0].item())
+            self.budget_value = self._capacity()[0]
+            self.mc_pending = None
 
     def _capture(self, batch, capacity):
         import time
@@ -293,6 +323,7 @@ class GraphedTrainStep:
         local_step = m.local_step
         self.counter_row = local_step % 16
         torch.cuda.synchronize(dev)
+        _ = m.mean_count                   # run_cuda reads it as a Python int: make the host copy NOW, a capture cannot synchronise
         g, g_tail = torch.cuda.CUDAGraph(), None
         try:
             with sample_budget(capacity, self.budget):
@@ -316,11 +347,13 @@ class GraphedTrainStep:
         m = self.model
         amp = bool(m.opt.fp16)
         shapes = tuple((k, tuple(torch.as_tensor(batch[k]).shape)) for k in self.KEYS if batch.get(k) is not None)
-        if self.fallback_reason is not None or not amp or m.mean_count <= 0 or not self.warm:
-            self.warm = self.warm or m.mean_count > 0      # one eager step in the steady regime: lazy initialisations, grads exist
+        if self.fallback_reason is not None or not amp:
             return self._eager(batch)
+        if not self.warm:        # (the only place the host reads mean_count itself: the cold regime synchronises every step anyway)
+            self.warm = m.mean_count > 0                   # one eager step in the steady regime: lazy initialisations, grads exist
+            return self._eager(batch)
+        self._follow_mean_count()
         padded, capacity = self._capacity()
-        self._set_budget(padded)
         key = (capacity, shapes, self.phase)
         if key != self.key:
             try:

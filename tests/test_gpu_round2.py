@@ -85,3 +85,32 @@ def test_grid_backward3_variants_match_the_generic_kernel(variant, clustered):
     scale = ref.abs().max().item()
     assert (gen.double() - ref).abs().max().item() <= 1e-5 * scale      # the generic kernel vs the double restatement
     assert (out.double() - ref).abs().max().item() <= 1e-5 * scale, variant
+
+
+def test_occupancy_merge_and_device_threshold_packbits():
+    """rn_occupancy_merge + rn_packbits_min (the occupancy update without host synchronisation) against the reference's expressions
+    (nerf/renderer.py:463-471): masked max(grid * decay, fresh), mean(clamp(grid, 0)), packbits at min(mean, density_thresh)"""
+    import raymarching as rm
+    from radnerf_b200 import abi
+    g = torch.Generator().manual_seed(5)
+    n = 128 ** 3
+    grid = (torch.rand(n, generator=g) * 30).cuda()
+    grid[torch.rand(n, generator=g).cuda() < 0.2] = -1.0           # untrained cells
+    fresh = (torch.rand(n, generator=g) * 30).cuda()
+    fresh[torch.rand(n, generator=g).cuda() < 0.1] = -1.0
+    want = grid.clone()
+    both = (want >= 0) & (fresh >= 0)
+    want[both] = torch.maximum(want[both] * 0.95, fresh[both])
+    want_mean = want.clamp(min=0).double().mean()
+    ws = torch.zeros(int(abi.lib().rn_occupancy_merge_workspace_bytes()) // 8 + 1, dtype=torch.float64, device="cuda")
+    mean = torch.empty(1, device="cuda")
+    for rep in range(2):        # twice: the kernel re-arms its ticket
+        got = grid.clone()
+        abi.call("rn_occupancy_merge", got, fresh, n, 0.95, ws, mean)
+        assert torch.equal(got, want)
+        assert abs(float(mean) - float(want_mean)) <= 1e-6 * float(want_mean)
+    for thresh in (1e9, 5.0):   # the mean wins / density_thresh wins
+        bits = torch.empty(n // 8, dtype=torch.uint8, device="cuda")
+        abi.call("rn_packbits_min", got, n // 8, float(thresh), mean, bits)
+        ref = rm.packbits(got.view(1, -1), min(float(mean), thresh))
+        assert torch.equal(bits, ref.view(-1))
