@@ -49,7 +49,6 @@ def parse():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--path", default=os.environ.get("RADNERF_PATH", "fused"), choices=["fused", "ops"])
     ap.add_argument("--repeats", type=int, default=0, help="timed windows of --steps frames (0 = at least 15, enough to cover ~1 s)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE configs[0], [1], [4] legs")
     ap.add_argument("--hw", type=int, default=HW)
@@ -254,9 +253,8 @@ def run_ours(args):
     frames, intr, bg = make_frames(hw)
     bg_t = torch.from_numpy(bg).to(dev)[None]
     kw = model.opt.render_kwargs()
-    path = args.path
-    if path == "fused":
-        from radnerf_b200 import frame  # noqa: F401  (no fallback: a broken fused renderer must fail the bench, not change what it times)
+    path = "fused"    # the only inference path of the product; a broken fused renderer fails the bench (no fallback)
+    from radnerf_b200 import frame  # noqa: F401
 
     from radnerf_b200.sharding import FrameSharder
     sharder = FrameSharder(hw, hw, world, rank, dev)
@@ -275,7 +273,7 @@ def run_ours(args):
                                eye=torch.from_numpy(f["eye"]).to(dev)))
     bg_local = sharder.shard(bg_t[0])[None]
 
-    lanes = max(1, args.lanes) if path == "fused" else 1
+    lanes = max(1, args.lanes)
 
     def streamer_loop(st, blocks):
         def render(i):
@@ -300,14 +298,6 @@ def run_ours(args):
         resident = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
                                  deliver=False, depth=lanes, **kw)
         render_resident, drain_resident = streamer_loop(resident, packed_dev)
-    else:
-        def render_resident(i):
-            f = dev_frames[i % len(dev_frames)]
-            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=model.opt.fp16):
-                out = model.render(f["ro"], f["rd"], f["auds"], bg_local, f["pose6"], eye=f["eye"], index=0, bg_color=None,
-                                   perturb=False, path=path, **kw)
-            return sharder.gather(out["image"][0])
-        drain_resident = None
 
     # ---- host inputs for `e2e`: one pinned block per frame (pose, pose6, eye, audio window); the public streaming API
     #      (radnerf_b200.stream.FrameStreamer) copies it in, generates the rays on the device, renders, all-gathers the tiles
@@ -317,32 +307,6 @@ def run_ours(args):
                                  deliver=(rank == 0), depth=max(2, lanes), **kw)
         h2d_bytes, d2h_bytes = streamer.h2d_bytes, streamer.d2h_bytes
         render_e2e, drain_e2e = streamer_loop(streamer, packed)
-    else:
-        pinned = [dict(pose=torch.from_numpy(f["pose"]).pin_memory(), auds=torch.from_numpy(f["auds"]).pin_memory(),
-                       pose6=torch.from_numpy(f["pose6"]).pin_memory(), eye=torch.from_numpy(f["eye"]).pin_memory()) for f in frames]
-        host_img = torch.empty(hw * hw, 3, dtype=torch.float32).pin_memory()
-        from radnerf_b200.rays import RayGenerator
-        raygen = RayGenerator(hw, hw, intr, dev, sharder)
-        h2d_bytes = sum(t.numel() * t.element_size() for t in pinned[0].values())
-        d2h_bytes = host_img.numel() * host_img.element_size()
-
-        def render_e2e(i):
-            p = pinned[i % len(pinned)]
-            pose = p["pose"].to(dev, non_blocking=True)
-            auds = p["auds"].to(dev, non_blocking=True)
-            pose6 = p["pose6"].to(dev, non_blocking=True)
-            eye = p["eye"].to(dev, non_blocking=True)
-            ro, rd = raygen(pose)
-            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=model.opt.fp16):
-                out = model.render(ro[None], rd[None], auds, bg_local, pose6, eye=eye, index=0, bg_color=None, perturb=False,
-                                   path=path, **kw)
-            img = sharder.gather(out["image"][0])
-            if rank == 0:
-                host_img.copy_(img, non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the frame is only "delivered" once it is on the host
-
-        def drain_e2e():
-            pass
 
     def barrier():
         if world > 1:
@@ -443,8 +407,7 @@ def run_ours(args):
                                                                   lanes * (hw * hw * 24 / 1e6 + 21.0 * hw * hw / 262144 + 8.5 * hw * hw / 262144))},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "api": "radnerf_b200.stream.FrameStreamer (depth-2: the image copy-out of frame i overlaps frame i+1)" if path == "fused"
-                           else "model.render per frame, synchronous copy-out",
+                    "api": "radnerf_b200.stream.FrameStreamer (%d frames in flight: the image copy-out of frame i overlaps the following frames)" % max(2, lanes),
                     "ms_per_step": ms_e2e / K, "repeats": t_e2e["repeats"], "window_ms": {"median": ms_e2e, "min": t_e2e["min"], "max": t_e2e["max"]}}}
     if e2e_u8 is not None:
         line["e2e_uint8"] = e2e_u8

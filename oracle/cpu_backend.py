@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import oracle as O
+from . import ops_frame  # noqa: F401  (registers the op-by-op inference loop with radnerf_b200.model)
 
 
 def _np(t):

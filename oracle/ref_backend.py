@@ -16,6 +16,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import ops_frame  # noqa: F401  (registers the op-by-op inference loop with radnerf_b200.model)
+
 _REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 _mods = {}
 

@@ -54,6 +54,9 @@ constexpr int HEAD_GROUPS = 4;
 constexpr uint32_t HEAD_SMEM = HEAD_BLOB_BYTES + HEAD_GROUPS * GROUP_BYTES;
 constexpr uint32_t TMEM_COLS_PER_GROUP = 128;
 
+// PROF: the per-phase cycle counters of tools/frame_breakdown.py; compiled out of the production instantiation (the clock reads and
+// their bookkeeping were ~3 % of the kernel's instructions even with the counters switched off at run time)
+template <bool PROF>
 __global__ void __launch_bounds__(HEAD_GROUPS * 128, 1)
 head_eval_kernel(HeadEvalParams p, const FrameCur* cur) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -129,10 +132,10 @@ head_eval_kernel(HeadEvalParams p, const FrameCur* cur) {
     const uint2* table2 = reinterpret_cast<const uint2*>(p.table2);
 
     long long c_enc3 = 0, c_enc2 = 0, c_mma = 0, c_epi = 0, c_tile = 0, c_last = 0;
-    const bool prof = p.prof != nullptr && t == 0;
-#define RN_TICK(acc) if (prof) { const long long now = clock64(); acc += now - c_last; c_last = now; }
+    const bool prof = PROF && p.prof != nullptr && t == 0;
+#define RN_TICK(acc) if constexpr (PROF) { if (prof) { const long long now = clock64(); acc += now - c_last; c_last = now; } }
     for (uint32_t tile = blockIdx.x * HEAD_GROUPS + g; tile < n_tiles; tile += gridDim.x * HEAD_GROUPS) {
-        if (prof) c_last = clock64();
+        if constexpr (PROF) { if (prof) c_last = clock64(); }
         const long long c_start = c_last;
         const uint32_t s = tile * EVAL_TILE + t;
         const bool valid = s < n_samples;
@@ -222,9 +225,9 @@ head_eval_kernel(HeadEvalParams p, const FrameCur* cur) {
         // the next tile's first MMA overwrites the accumulator: retire this tile's TMEM reads first
         umma::fence_before_sync();
         umma::group_sync(bar_id, 128);
-        if (prof) c_tile += clock64() - c_start;
+        if constexpr (PROF) { if (prof) c_tile += clock64() - c_start; }
     }
-    if (prof) {
+    if (PROF && prof) {
         atomicAdd(p.prof + 0, (unsigned long long)c_enc3);
         atomicAdd(p.prof + 1, (unsigned long long)c_enc2);
         atomicAdd(p.prof + 2, (unsigned long long)c_mma);
@@ -242,16 +245,16 @@ head_eval_kernel(HeadEvalParams p, const FrameCur* cur) {
 }  // namespace
 
 int launch_head_eval(const HeadEvalParams& p, const FrameCur* cur, uint32_t max_tiles, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(head_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM);
-        if (e != cudaSuccess) { set_error("head_eval: cannot reserve %u bytes of shared memory: %s", HEAD_SMEM, cudaGetErrorString(e)); return (int)e; }
-        configured = true;
-    }
+    // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute: set it before every launch (the call is
+    // cheap and capture-safe) instead of caching a process-wide flag that would be wrong for a second device
+    cudaError_t e = p.prof ? cudaFuncSetAttribute(head_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM)
+                           : cudaFuncSetAttribute(head_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM);
+    if (e != cudaSuccess) { set_error("head_eval: cannot reserve %u bytes of shared memory: %s", HEAD_SMEM, cudaGetErrorString(e)); return (int)e; }
     uint32_t grid = (max_tiles + HEAD_GROUPS - 1) / HEAD_GROUPS;
     if (grid > RN_NUM_SMS) grid = RN_NUM_SMS;
     if (grid == 0) grid = 1;
-    head_eval_kernel<<<grid, HEAD_GROUPS * 128, HEAD_SMEM, st>>>(p, cur);
+    if (p.prof) head_eval_kernel<true><<<grid, HEAD_GROUPS * 128, HEAD_SMEM, st>>>(p, cur);
+    else head_eval_kernel<false><<<grid, HEAD_GROUPS * 128, HEAD_SMEM, st>>>(p, cur);
     return finish_launch("head_eval");
 }
 

@@ -64,10 +64,9 @@ static __device__ __noinline__ void epilogue_save(uint32_t tmem_row, uint32_t co
     for (int c = 0; c < NCH32; ++c) {
         uint32_t h[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            h[j] = pack2(__uint_as_float(v[c][2 * j]), __uint_as_float(v[c][2 * j + 1]));
-            if (relu) h[j] = relu2(h[j]);
-        }
+        for (int j = 0; j < 16; ++j)
+            h[j] = relu ? pack2_relu(__uint_as_float(v[c][2 * j]), __uint_as_float(v[c][2 * j + 1]))
+                        : pack2(__uint_as_float(v[c][2 * j]), __uint_as_float(v[c][2 * j + 1]));
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const uint32_t off = umma::il_offset(row, dcol0 + 32 * c + 8 * q, Kdst);

@@ -18,6 +18,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
+// fp32 pair -> packed fp16 with ReLU in the conversion itself (cvt.rn.relu.f16x2.f32): relu(round(x)) == round(relu(x)), one
+// instruction instead of F2FP + HMNMX2 (the epilogues were 14 % of head_eval's instructions)
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));    // upper half <- first source
+    return d;
+}
 __device__ __forceinline__ uint32_t relu2(uint32_t v) {
     const __half2 h = __hmax2(*reinterpret_cast<const __half2*>(&v), __float2half2_rn(0.f));
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -36,10 +43,9 @@ static __device__ __noinline__ void epilogue_to_operand(uint32_t tmem_row, uint3
     for (int c = 0; c < NCH32; ++c) {
         uint32_t h[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            h[j] = pack2(__uint_as_float(v[c][2 * j]), __uint_as_float(v[c][2 * j + 1]));
-            if (relu) h[j] = relu2(h[j]);
-        }
+        for (int j = 0; j < 16; ++j)
+            h[j] = relu ? pack2_relu(__uint_as_float(v[c][2 * j]), __uint_as_float(v[c][2 * j + 1]))
+                        : pack2(__uint_as_float(v[c][2 * j]), __uint_as_float(v[c][2 * j + 1]));
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             *reinterpret_cast<uint4*>(dst + umma::il_offset(row, dcol0 + 32 * c + 8 * q, Kdst)) =

@@ -8,12 +8,13 @@ are absent offline, and they only know the op-by-op execution order.  This modul
     (nerf/network.py:91-167, nerf/renderer.py:84-133);
   * `render(rays_o, rays_d, auds, bg_coords, poses, **kw)` with the reference's keyword contract and result keys
     (nerf/renderer.py:158-316, 504-537); `update_extra_state`, `mark_untrained_grid` (renderer.py:318-501);
-  * two execution paths:  `path="ops"`  -- the reference's op-by-op order on the drop-in operators + torch Linear layers
-    (the parity yardstick and the autograd/training path);  `path="fused"` -- one call into the fused sm_100a frame
-    renderer (radnerf_b200.frame), no per-iteration host sync.
+  * execution: inference = `path="fused"`, one call into the fused sm_100a frame renderer (radnerf_b200.frame), no per-iteration
+    host sync; training = the autograd path over the drop-in operators with the head network in the fused training kernels
+    (radnerf_b200.fused_train).  The reference's op-by-op inference loop is NOT here: it is a test-side restatement
+    (oracle/ops_frame.py, registered through `register_ops_frame`) used by the parity tests and the CPU port; the GPU yardstick is the
+    reference's own classes (baseline/stock.py).
 
-`ops` can be swapped for a bundle that calls the reference's own compiled kernels (oracle/ref_backend.py) -- bench.py
-uses that as the reference-CUDA comparison arm.
+`ops` can be swapped for another operator bundle (the CPU oracle, oracle/cpu_backend.py).
 """
 import math
 import random
@@ -67,6 +68,16 @@ class DefaultOps:
         self.rm = raymarching
         self.get_encoder = get_encoder
         self.trunc_exp = trunc_exp
+
+
+# the op-by-op inference frame (a restatement of the reference's host loop) is registered by oracle/ops_frame.py -- tests, smoke() and
+# the CPU port only; the product renders frames through radnerf_b200.frame
+_OPS_FRAME = None
+
+
+def register_ops_frame(fn):
+    global _OPS_FRAME
+    _OPS_FRAME = fn
 
 
 # ------------------------------------------------------------------------------------------- audio nets / MLP
@@ -330,87 +341,70 @@ class NeRFNetwork(nn.Module):
 
     def run_cuda(self, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=0, dt_gamma=0, bg_color=None, perturb=False,
                  force_all_rays=False, max_steps=1024, T_thresh=1e-4, **kwargs):
-        """op-by-op frame / training batch, in the reference's order (renderer.py:158-316)."""
-        rm = self.ops.rm
-        prefix = rays_o.shape[:-1]
-        rays_o = rays_o.contiguous().view(-1, 3)
-        rays_d = rays_d.contiguous().view(-1, 3)
-        bg_coords = bg_coords.contiguous().view(-1, 2)
-        N = rays_o.shape[0]
-        device = rays_o.device
-        results = {}
+        """one batch of rays through the op-by-op operators with the reference's result keys (renderer.py:158-316).
 
-        nears, fars = rm.near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer, self.min_near)
-        nears, fars = nears.detach(), fars.detach()
+        Training mode is the product's autograd path: marcher -> head network (fused kernels when the step is the one they
+        implement) -> compositor.  The op-by-op INFERENCE loop of the reference (renderer.py:229-262: march / network / composite per
+        iteration with a host synchronisation each) is not part of the product -- inference is `path="fused"` -- and lives with the rest
+        of the reference restatements in oracle/ops_frame.py, which registers itself here for the parity tests and the CPU port."""
+        dev = rays_o.device
+        lead = rays_o.shape[:-1]
+        origins, directions = rays_o.contiguous().view(-1, 3), rays_d.contiguous().view(-1, 3)
+        pixels = bg_coords.contiguous().view(-1, 2)
+        n_rays = origins.shape[0]
+        box = self.aabb_train if self.training else self.aabb_infer
+        nears, fars = (t.detach() for t in self.ops.rm.near_far_from_aabb(origins, directions, box, self.min_near))
         enc_a, ind_code = self._frame_conditioning(auds, index)
-
+        out = {}
         if self.training:
-            counter = self.step_counter[self.local_step % 16]
-            counter.zero_()
-            self.local_step += 1
-            xyzs, dirs, deltas, rays = rm.march_rays_train(rays_o, rays_d, self.bound, self.density_bitfield, self.cascade,
-                                                           self.grid_size, nears, fars, counter, self.mean_count, perturb, 128,
-                                                           force_all_rays, dt_gamma, max_steps)
-            if self._use_fused_train(enc_a, ind_code, eye):
-                from . import fused_train    # ONE forward kernel (+ 2 backward kernels) instead of 8 GEMMs + ~150 elementwise launches
-                sigmas, rgbs, ambient = fused_train.head_forward(self, xyzs, dirs, enc_a, ind_code, eye)
-            else:
-                sigmas, rgbs, ambient = self(xyzs, dirs, enc_a, ind_code, eye)
-            sigmas = self.density_scale * sigmas
-            weights_sum, ambient_sum, depth, image = rm.composite_rays_train(sigmas, rgbs, ambient.abs().sum(-1), deltas, rays)
-            results['weights_sum'] = weights_sum
-            results['ambient'] = ambient_sum
+            weights_sum, depth, image = self._training_batch(out, origins, directions, nears, fars, enc_a, ind_code, eye, dt_gamma, perturb,
+                                                             force_all_rays, max_steps)
         else:
-            weights_sum = torch.zeros(N, dtype=torch.float32, device=device)
-            depth = torch.zeros(N, dtype=torch.float32, device=device)
-            image = torch.zeros(N, 3, dtype=torch.float32, device=device)
-            rays_alive = torch.arange(N, dtype=torch.int32, device=device)
-            rays_t = nears.clone()
-            step = 0
-            self.last_frame_stats = []
-            while step < max_steps:
-                n_alive = rays_alive.shape[0]
-                if n_alive <= 0:
-                    break
-                n_step = max(min(N // n_alive, 8), 1)
-                xyzs, dirs, deltas = rm.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
-                                                   self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128,
-                                                   perturb if step == 0 else False, dt_gamma, max_steps)
-                sigmas, rgbs, ambient = self(xyzs, dirs, enc_a, ind_code, eye)
-                sigmas = self.density_scale * sigmas
-                rm.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh)
-                rays_alive = rays_alive[rays_alive >= 0]  # host sync: the new length is needed on the CPU
-                self.last_frame_stats.append((n_alive, n_step, xyzs.shape[0]))
-                step += n_step
-
-        if bg_color is None:
-            bg_color = 1
-
+            if _OPS_FRAME is None:
+                raise RuntimeError("the op-by-op inference frame is test infrastructure (oracle/ops_frame.py registers it); "
+                                   "render(..., path='fused') is the inference path of this library")
+            weights_sum, depth, image = _OPS_FRAME(self, origins, directions, nears, fars, enc_a, ind_code, eye, dt_gamma, perturb, max_steps, T_thresh)
+        background = 1 if bg_color is None else bg_color
         if self.torso:
-            ind_code_torso = None
-            if self.individual_dim_torso > 0:
-                ind_code_torso = self.individual_codes_torso[index] if self.training else self.individual_codes_torso[0]
-            density_thresh_torso = min(self.density_thresh_torso, self.mean_density_torso)
-            occupancy = F.grid_sample(self.density_grid_torso.view(1, 1, self.grid_size, self.grid_size),
-                                      bg_coords.view(1, -1, 1, 2), align_corners=True).view(-1)
-            mask = occupancy > density_thresh_torso
-            torso_alpha = torch.zeros([N, 1], device=device)
-            torso_color = torch.zeros([N, 3], device=device)
-            if mask.any():
-                torso_alpha_mask, torso_color_mask, deform = self.forward_torso(bg_coords[mask], poses, enc_a, ind_code_torso)
-                torso_alpha[mask] = torso_alpha_mask.float()
-                torso_color[mask] = torso_color_mask.float()
-                results['deform'] = deform
-            bg_color = torso_color * torso_alpha + bg_color * (1 - torso_alpha)
-            results['torso_alpha'] = torso_alpha
-            results['torso_color'] = bg_color
+            background = self._torso_over(out, pixels, poses, enc_a, index, background, n_rays, dev)
+        out['depth'] = (torch.clamp(depth - nears, min=0) / (fars - nears)).view(*lead)
+        out['image'] = (image + (1 - weights_sum).unsqueeze(-1) * background).view(*lead, 3).clamp(0, 1)
+        return out
 
-        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
-        image = image.view(*prefix, 3).clamp(0, 1)
-        depth = torch.clamp(depth - nears, min=0) / (fars - nears)
-        results['depth'] = depth.view(*prefix)
-        results['image'] = image
-        return results
+    def _training_batch(self, out, origins, directions, nears, fars, enc_a, ind_code, eye, dt_gamma, perturb, force_all_rays, max_steps):
+        """renderer.py:207-236: all samples of all rays at once, sized by the running estimate `mean_count`"""
+        rm = self.ops.rm
+        counter = self.step_counter[self.local_step % 16]
+        counter.zero_()
+        self.local_step += 1
+        xyzs, dirs, deltas, rays = rm.march_rays_train(origins, directions, self.bound, self.density_bitfield, self.cascade, self.grid_size,
+                                                       nears, fars, counter, self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps)
+        if self._use_fused_train(enc_a, ind_code, eye):
+            from . import fused_train    # ONE forward kernel (+ 2 backward kernels) instead of 8 GEMMs + ~150 elementwise launches
+            sigmas, rgbs, ambient = fused_train.head_forward(self, xyzs, dirs, enc_a, ind_code, eye)
+        else:
+            sigmas, rgbs, ambient = self(xyzs, dirs, enc_a, ind_code, eye)
+        weights_sum, ambient_sum, depth, image = rm.composite_rays_train(self.density_scale * sigmas, rgbs, ambient.abs().sum(-1), deltas, rays)
+        out['weights_sum'], out['ambient'] = weights_sum, ambient_sum
+        return weights_sum, depth, image
+
+    def _torso_over(self, out, pixels, poses, enc_a, index, background, n_rays, dev):
+        """the 2-D torso layer composited over the background colour (renderer.py:267-297): evaluated only where the 2-D occupancy
+        grid, sampled bilinearly at the pixel's background coordinate, exceeds its threshold"""
+        code = None
+        if self.individual_dim_torso > 0:
+            code = self.individual_codes_torso[index] if self.training else self.individual_codes_torso[0]
+        occupancy = F.grid_sample(self.density_grid_torso.view(1, 1, self.grid_size, self.grid_size), pixels.view(1, -1, 1, 2),
+                                  align_corners=True).view(-1)
+        hit = occupancy > min(self.density_thresh_torso, self.mean_density_torso)
+        alpha, color = torch.zeros([n_rays, 1], device=dev), torch.zeros([n_rays, 3], device=dev)
+        if hit.any():
+            a, c, deform = self.forward_torso(pixels[hit], poses, enc_a, code)
+            alpha[hit], color[hit] = a.float(), c.float()
+            out['deform'] = deform
+        over = color * alpha + background * (1 - alpha)
+        out['torso_alpha'], out['torso_color'] = alpha, over
+        return over
 
     # ---- mean_density / mean_count: plain Python numbers for every reader (the reference keeps them as such, renderer.py:470, 493), but
     #      update_extra_state leaves them on the DEVICE and the host copy is only made when somebody asks: no host synchronisation
@@ -448,12 +442,15 @@ class NeRFNetwork(nn.Module):
         from . import fused_train
         return fused_train.supported(self)
 
-    def render(self, rays_o, rays_d, auds, bg_coords, poses, staged=False, max_ray_batch=4096, path="ops", **kwargs):
+    def render(self, rays_o, rays_d, auds, bg_coords, poses, staged=False, max_ray_batch=4096, path=None, **kwargs):
         """entry point with the reference's contract (renderer.py:504-537); cuda_ray never stages.
-        path="fused" (inference only) runs the whole frame inside the fused sm_100a renderer."""
-        if path == "fused" and not self.training:
+        path: "fused" = the whole frame inside the fused sm_100a renderer (inference); "ops" = operator by operator (training always;
+        inference only with the test-side loop of oracle/ops_frame.py registered); None = fused for inference whenever the fused
+        kernels implement this model on this device, "ops" otherwise."""
+        if not self.training and path != "ops":
             from . import frame
-            return frame.render_frame(self, rays_o, rays_d, auds, bg_coords, poses, **kwargs)
+            if path == "fused" or (rays_o.is_cuda and isinstance(self.ops, DefaultOps) and frame.supported(self) and _OPS_FRAME is None):
+                return frame.render_frame(self, rays_o, rays_d, auds, bg_coords, poses, **kwargs)
         return self.run_cuda(rays_o, rays_d, auds, bg_coords, poses, **kwargs)
 
     # ------------------------------------------------------------------------------------- occupancy maintenance

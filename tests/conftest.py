@@ -9,6 +9,11 @@ for p in (ROOT, os.path.join(ROOT, "rad-nerf_b200"), os.path.join(ROOT, "tests")
         sys.path.insert(0, p)
 
 
+# the reference's op-by-op inference loop is test infrastructure (oracle/ops_frame.py): `model.render(..., path="ops")` in eval mode
+# needs it registered
+from oracle import ops_frame  # noqa: E402,F401
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
