@@ -269,12 +269,23 @@ typedef struct rn_frame_head_desc {
                                     An unrolled iteration that finds the loop finished costs ~1.3 us per kernel, a WHILE
                                     iteration ~7 us more than an unrolled one: pass the iteration count typical of the scene.
                                     Outside capture all max_steps iterations are launched. */
-    uint32_t reserved;
+    uint32_t occ_words;          /* with occ_pack: 32-bit words of packed occupancy bits the marcher stages in shared memory (the pack's
+                                    total_words as read back by the host when the pack was built; sizes the launch) */
     const float* occ_aabb;       /* optional device [6] (xmin,ymin,zmin,xmax,ymax,zmax): a CONSERVATIVE bounding box of every occupied
                                     cell of the bitfield, all cascades, inflated by at least one cell.  A ray whose [near, far]
                                     segment provably misses it cannot emit a sample, so it is not marched (same outputs; about
                                     70% of the rays of a talking-head frame).  NULL = march every ray. */
+    const void* occ_pack;        /* optional: rn_occupancy_pack() output for `bitfield` -- the occupied boxes of every cascade as linear
+                                    bit arrays; each marcher CTA copies them into SHARED memory and probes there (same cells, same
+                                    samples; replaces the global-memory probes of kernel_march_rays, raymarching.cu:892-905).  Its
+                                    bytes 16..39 are the occ_aabb box.  NULL (or a pack marked unusable) = probe the Morton bitfield. */
 } rn_frame_head_desc;
+
+/* Box-packed copy of the occupancy bitfield for shared-memory staging (csrc/occ_pack.cu).  pack: rn_occupancy_pack_bytes() bytes,
+ * 16-byte aligned.  Header (int32): [0] cascades, [1] total_words, [2] usable; floats [4..9] = world box of all occupied cells inflated
+ * by one cell.  Run whenever the bitfield changes. */
+int rn_occupancy_pack(const uint8_t* bitfield, uint32_t C, uint32_t H, float bound, void* pack, void* stream);
+uint32_t rn_occupancy_pack_bytes(void);
 
 typedef struct rn_frame_torso_desc {
     uint32_t N, grid_size;

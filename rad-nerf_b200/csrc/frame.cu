@@ -60,6 +60,7 @@ static int frame_head_impl(const rn_frame_head_desc* d, cudaStream_t st, cudaEve
     RN_REQUIRE(d->max_steps >= 1 && d->max_steps <= (uint32_t)FRAME_MAX_ITERS, "max_steps must be in [1, 64] for the fused frame");
     RN_REQUIRE(d->cascade >= 1 && d->cascade <= 16 && d->grid_size >= 1, "bad cascade/grid_size");
     RN_REQUIRE(((uintptr_t)d->head_blob & 15) == 0, "head_blob must be 16-byte aligned");
+    RN_REQUIRE(!d->occ_pack || (((uintptr_t)d->occ_pack & 15) == 0 && d->occ_words * 4u <= rn_occupancy_pack_bytes()), "occ_pack misaligned or occ_words too large");
     FrameWorkspace w;
     carve(w, (uint8_t*)d->workspace, d->N);
     int rc = launch_frame_init(d->rays_o, d->rays_d, d->aabb, d->occ_aabb, d->N, d->min_near, d->max_steps, d->nears, d->fars, w, d->weights_sum,
@@ -77,7 +78,7 @@ static int frame_head_impl(const rn_frame_head_desc* d, cudaStream_t st, cudaEve
     // the kernels read the iteration index from the workspace and the loop controller (last CTA of composite) advances it.
     auto iteration = [&](cudaStream_t s, uint32_t ev_it, bool first, unsigned long long cond) -> int {
         int r;
-        if ((r = launch_march_compact(d->N, w, d->rays_o, d->rays_d, d->fars, mp, d->noises, s))) return r;
+        if ((r = launch_march_compact(d->N, w, d->rays_o, d->rays_d, d->fars, mp, d->noises, d->occ_pack, d->occ_words, d->occ_aabb, s))) return r;
         if (ev) cudaEventRecord(ev[3 * ev_it + 1], s);
         if (first && d->consts_ready_event) cudaStreamWaitEvent(s, (cudaEvent_t)d->consts_ready_event, 0);
         if ((r = launch_head_eval(hp, w.cur, max_tiles, s))) return r;

@@ -119,7 +119,8 @@ struct AudioParams {
 int launch_frame_init(const float* rays_o, const float* rays_d, const float* aabb, const float* occ_aabb /*nullable*/, uint32_t N,
                       float min_near, uint32_t max_steps, float* nears, float* fars, const FrameWorkspace& w, float* weights_sum, float* depth, float* image, cudaStream_t st);
 int launch_march_compact(uint32_t N, const FrameWorkspace& w, const float* rays_o, const float* rays_d, const float* fars,
-                         const MarchParams& p, const float* noises, cudaStream_t st);
+                         const MarchParams& p, const float* noises, const void* occ_pack /*nullable*/, uint32_t occ_words,
+                         const float* occ_aabb /*nullable*/, cudaStream_t st);
 // cond_handle: cudaGraphConditionalHandle of the WHILE node that repeats the iteration (0 = none); the loop controller sets it
 int launch_composite_compact(uint32_t N, uint32_t max_steps, float T_thresh, const FrameWorkspace& w, float* weights_sum,
                              float* depth, float* image, unsigned long long cond_handle, cudaStream_t st);

@@ -135,7 +135,9 @@ march_compact_kernel(FrameCur* cur, const int32_t* __restrict__ alive0,
                      const int32_t* __restrict__ alive1, const float* __restrict__ rays_t, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                      const float* __restrict__ fars, MarchParams p, const float* __restrict__ noises,
                      uint32_t* __restrict__ ray_cnt, uint32_t* __restrict__ sample_idx, uint32_t N, float4* __restrict__ samples,
-                     float2* __restrict__ deltas) {
+                     float2* __restrict__ deltas, const OccPack* __restrict__ occ, uint32_t occ_words, const float* __restrict__ occ_aabb) {
+    extern __shared__ __align__(16) uint32_t s_occ[];      // occ_words words: the box-packed occupancy bits (occ_pack.cu)
+    __shared__ OccLevel s_lv[OCC_MAX_LEVELS];
     __shared__ float4 s_xyz[8][CTL_THREADS];
     __shared__ float2 s_dt[8][CTL_THREADS];
     __shared__ unsigned long long s_wsum[CTL_THREADS / 32];
@@ -150,6 +152,18 @@ march_compact_kernel(FrameCur* cur, const int32_t* __restrict__ alive0,
     const int32_t* __restrict__ alive = (it & 1u) ? alive1 : alive0;
     if (it != 0) noises = nullptr;   // the per-ray start offset is applied once, by the first march of the frame
 
+    // stage the occupancy bits: every DDA probe below is then a shared-memory read instead of a dependent L2 round trip.
+    // (CTA-uniform: the launch was sized for `occ_words`, the pack says whether it was written and still has that size)
+    if (occ && occ_words && occ->usable && (uint32_t)occ->total_words <= occ_words) {
+        const uint32_t n16 = ((uint32_t)occ->total_words + 3u) / 4u;
+        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(occ->bits);
+        for (uint32_t k = threadIdx.x; k < n16; k += CTL_THREADS) reinterpret_cast<uint4*>(s_occ)[k] = __ldg(src + k);
+        if (threadIdx.x < OCC_MAX_LEVELS) s_lv[threadIdx.x] = occ->lv[threadIdx.x];
+        __syncthreads();
+        p.occ_bits = s_occ;
+        p.occ_lv = s_lv;
+    }
+
     uint32_t cnt = 0;
     int32_t ray = 0;
     if (j < n_alive) {
@@ -157,7 +171,18 @@ march_compact_kernel(FrameCur* cur, const int32_t* __restrict__ alive0,
         Ray r;
         r.load(rays_o + (size_t)ray * 3, rays_d + (size_t)ray * 3);
         float t = __ldg(rays_t + ray);
-        const float far = __ldg(fars + ray);
+        float far = __ldg(fars + ray);
+        if (occ_aabb) {
+            // Past the exit of the (one-cell inflated) box of all occupied cells a ray can only probe empty cells: stop there instead of
+            // stepping cell by cell to the far plane (up to ~60 dependent probes of ~100 instructions each, the bulk of this kernel's
+            // latency for rays that leave the head).  Same samples: everything between the exit and `far` emits nothing.  A NaN slab
+            // (0 * inf) compares false in fminf's favour of the other operand, i.e. falls back to `far`.
+            const float ax = (__ldg(occ_aabb + 0) - r.ox) * r.rdx, bx = (__ldg(occ_aabb + 3) - r.ox) * r.rdx;
+            const float ay = (__ldg(occ_aabb + 1) - r.oy) * r.rdy, by = (__ldg(occ_aabb + 4) - r.oy) * r.rdy;
+            const float az = (__ldg(occ_aabb + 2) - r.oz) * r.rdz, bz = (__ldg(occ_aabb + 5) - r.oz) * r.rdz;
+            const float t_exit = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
+            far = fminf(far, t_exit);
+        }
         const float noise = noises ? __ldg(noises + j) : 0.0f;
         t = __fmaf_rn(noise, step_size(p, t), t);  // raymarching.cu:873
         float x, y, z, dt;
@@ -246,11 +271,25 @@ composite_compact_kernel(FrameCur* cur, FrameCtl* __restrict__ history, uint32_t
         float r = image[(size_t)ray * 3], g = image[(size_t)ray * 3 + 1], b = image[(size_t)ray * 3 + 2];
         float t = 0.f;
         uint32_t step = 0;
-        while (step < n_step) {
+        // all of the ray's <= 8 samples are fetched before the serial compositing recurrence: two dependent memory round trips per
+        // ray instead of two per sample (the kernel is a latency chain: one thread per ray, a handful of warps per SM)
+        const uint32_t n_have = min(cnt, n_step);
+        uint32_t pos_k[8];
+        float2 dd_k[8];
+        float4 ev_k[8];
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) pos_k[k] = k < n_have ? __ldg(sample_idx + (size_t)k * N + j) : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            if (k < n_have) { dd_k[k] = __ldg(deltas + pos_k[k]); ev_k[k] = __ldg(evals + pos_k[k]); }
+            else { dd_k[k] = make_float2(0.f, 0.f); ev_k[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            if (step != k || step >= n_step) continue;   // (the loop below, unrolled so that the prefetched registers are indexed statically)
             if (step >= cnt) break;  // the marcher ran out of samples (zero-filled slot in the reference)
-            const uint32_t pos = __ldg(sample_idx + (size_t)step * N + j);
-            const float2 dd = __ldg(deltas + pos);
-            const float4 e = __ldg(evals + pos);
+            const float2 dd = dd_k[k];
+            const float4 e = ev_k[k];
             const float alpha = 1.0f - __expf(-e.x * dd.x);
             const float T = 1 - ws;
             const float weight = __fmul_rn(alpha, T);
@@ -392,10 +431,18 @@ int launch_frame_init(const float* rays_o, const float* rays_d, const float* aab
 }
 
 int launch_march_compact(uint32_t N, const FrameWorkspace& w, const float* rays_o, const float* rays_d, const float* fars,
-                         const MarchParams& p, const float* noises, cudaStream_t st) {
-    march_compact_kernel<<<div_up(N, (uint32_t)CTL_THREADS), CTL_THREADS, 0, st>>>(w.cur, w.alive[0], w.alive[1], w.rays_t,
-                                                                                 rays_o, rays_d, fars, p, noises, w.ray_cnt,
-                                                                                 w.sample_idx, N, w.samples, w.deltas);
+                         const MarchParams& p, const float* noises, const void* occ_pack, uint32_t occ_words, const float* occ_aabb, cudaStream_t st) {
+    // dynamic shared memory = the packed occupancy bits (rounded to 16 bytes); with the 24 KiB of sample staging a CTA stays under the
+    // 48 KiB that need no opt-in as long as the pack is <= 20 KiB, larger packs opt in
+    const uint32_t smem = occ_pack ? ((occ_words * 4u + 15u) & ~15u) : 0u;
+    if (smem > 20u * 1024u) {
+        cudaError_t e = cudaFuncSetAttribute(march_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RN_OCC_PACK_MAX_BYTES);
+        if (e != cudaSuccess) { set_error("march_compact: cannot reserve %u bytes of shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
+    }
+    march_compact_kernel<<<div_up(N, (uint32_t)CTL_THREADS), CTL_THREADS, smem, st>>>(w.cur, w.alive[0], w.alive[1], w.rays_t,
+                                                                                    rays_o, rays_d, fars, p, noises, w.ray_cnt,
+                                                                                    w.sample_idx, N, w.samples, w.deltas,
+                                                                                    (const OccPack*)occ_pack, occ_pack ? occ_words : 0u, occ_aabb);
     return finish_launch("march_compact");
 }
 

@@ -214,7 +214,7 @@ head_train_fwd_kernel(FwdParams p) {
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    umma::mbar_wait(&mbar_w, 0);
+    bool weights_ready = false;     // awaited at the first MMA (see head_eval.cu)
 
     const uint32_t tmem_acc = tmem_slot + g * TMEM_COLS_PER_GROUP;
     const uint32_t tmem_row = tmem_acc + (((warp & 3u) * 32u) << 16);
@@ -249,6 +249,7 @@ head_train_fwd_kernel(FwdParams p) {
             encode_save<3>(x, table3, lv3, sA0, REC(T_A0), t, 32, nullptr);
         }
         // ---- ambient L1 -> H0 (saved as HA1)
+        if (!weights_ready) { umma::mbar_wait(&mbar_w, 0); weights_ready = true; }
         mma_stage(tmem_acc, aA0, 32, 0, aW + B_WA1, 32, 0, 0, 0, aOnes, aB0, 64, mbar, phase, bar_id, t);
         epilogue_save<2>(tmem_row, 0, true, sH0, REC(T_HA1), t, 64, 0);
         // ---- ambient L2 -> H1 (saved as HA2)

@@ -4,6 +4,7 @@
 // SASS of the reference build), so emitted samples are bit-identical to the reference's.
 #pragma once
 #include "common.cuh"
+#include "occ_pack.cuh"
 
 namespace rn {
 
@@ -12,6 +13,9 @@ struct MarchParams {
     float Hf, halfH, Hm1f, rH, H3f, rbound;
     int Cm1;
     const uint8_t* __restrict__ grid;
+    // optional: the occupied boxes of the bitfield as linear bit arrays staged in SHARED memory (occ_pack.cuh); null = probe `grid`
+    const uint32_t* occ_bits;
+    const OccLevel* occ_lv;
 };
 
 __host__ __device__ inline MarchParams make_march_params(float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
@@ -31,6 +35,8 @@ __host__ __device__ inline MarchParams make_march_params(float bound, float dt_g
     p.rbound = 1.0f / bound;  // IEEE division, same value the device computes for 1 / mip_bound when mip_bound == bound
     p.Cm1 = (int)C - 1;
     p.grid = grid;
+    p.occ_bits = nullptr;
+    p.occ_lv = nullptr;
     return p;
 }
 
@@ -80,9 +86,21 @@ __device__ __forceinline__ bool march_probe(const MarchParams& p, const Ray& r, 
     const int ny = (int)clampf(__fmul_rn(__fmaf_rn(y, mip_rbound, 1.0f), p.halfH), 0.0f, p.Hm1f);
     const int nz = (int)clampf(__fmul_rn(__fmaf_rn(z, mip_rbound, 1.0f), p.halfH), 0.0f, p.Hm1f);
 
-    // level * H^3 + morton, evaluated in fp32 as the reference does (H3 is a float there, raymarching.cu:380,419)
-    const uint32_t index = (uint32_t)__fmaf_rn((float)level, p.H3f, (float)morton_encode(nx, ny, nz));
-    const bool occ = (__ldg(p.grid + (index >> 3)) >> (index & 7u)) & 1u;
+    bool occ;
+    if (p.occ_bits) {
+        // the same cell, looked up in the box-packed copy in shared memory: outside the box of the occupied cells every bit is zero
+        const OccLevel& L = p.occ_lv[level];
+        const uint32_t bx = (uint32_t)(nx - L.lo[0]), by = (uint32_t)(ny - L.lo[1]), bz = (uint32_t)(nz - L.lo[2]);
+        occ = false;
+        if (bx < (uint32_t)L.dim[0] && by < (uint32_t)L.dim[1] && bz < (uint32_t)L.dim[2]) {
+            const uint32_t i = (bz * (uint32_t)L.dim[1] + by) * (uint32_t)L.dim[0] + bx;
+            occ = (p.occ_bits[(uint32_t)L.word_off + (i >> 5)] >> (i & 31u)) & 1u;
+        }
+    } else {
+        // level * H^3 + morton, evaluated in fp32 as the reference does (H3 is a float there, raymarching.cu:380,419)
+        const uint32_t index = (uint32_t)__fmaf_rn((float)level, p.H3f, (float)morton_encode(nx, ny, nz));
+        occ = (__ldg(p.grid + (index >> 3)) >> (index & 7u)) & 1u;
+    }
     if (occ) return true;
 
     // distance to the next voxel boundary along each axis              (raymarching.cu:431-439)

@@ -39,6 +39,7 @@ _PROTOS = {
     "rn_get_rays": [_vp, _f32, _f32, _f32, _f32, _u32, _u32, _vp, _u32, _vp, _vp, _vp],
     "rn_scatter_rows_to_peers": [_vp, _vp, _u32, _u32, _vp, _u32, _vp],
     "rn_image_to_uint8": [_vp, _vp, C.c_uint64, _vp],
+    "rn_occupancy_pack": [_vp, _u32, _u32, _f32, _vp, _vp],
     "rn_packbits_min": [_vp, _u32, _f32, _vp, _vp, _vp],
     "rn_occupancy_merge": [_vp, _vp, _u32, _f32, _vp, _vp, _vp],
     "rn_scatter_rows_to_root": [_vp, _vp, _u32, _u32, _vp, _vp, _u32, _u32, _u32, _u32, C.c_uint64, _vp],

@@ -42,7 +42,7 @@ class FrameHeadDesc(C.Structure):
                 ("weights_sum", _vp), ("depth", _vp), ("image", _vp), ("nears", _vp), ("fars", _vp),
                 ("workspace", _vp), ("workspace_bytes", _u64),
                 ("grid3d", GridTable), ("grid2d", GridTable), ("head_blob", _vp), ("head_consts", _vp), ("consts_ready_event", _vp),
-                ("capture_unroll", _u32), ("reserved", _u32), ("occ_aabb", _vp)]
+                ("capture_unroll", _u32), ("occ_words", _u32), ("occ_aabb", _vp), ("occ_pack", _vp)]
 
 
 class FrameTorsoDesc(C.Structure):
@@ -138,30 +138,31 @@ class FusedShared:
 
     def occupied_box(self, model):
         """device [6]: bounding box of all occupied cells of the density bitfield (every cascade, world coordinates), inflated
-        by one cell per side -- rn_frame_head_desc.occ_aabb.  Recomputed into the SAME buffer when the bitfield changes."""
+        by one cell per side -- rn_frame_head_desc.occ_aabb.  It lives inside the box-packed copy of the bitfield that the fused
+        marcher stages in shared memory (rn_occupancy_pack, csrc/occ_pack.cu): `self.occ_pack` / `self.occ_words`.  Rebuilt into the
+        SAME buffer when the bitfield changes (three small launches and one 16-byte read-back of the pack's size)."""
         bf = model.density_bitfield
         tag = (bf.data_ptr(), bf._version)
         if getattr(self, "_occ_tag", None) != tag:
-            H, Cc, bound = int(model.grid_size), int(model.cascade), float(model.bound)
-            bits = ((bf.view(-1, 1) >> torch.arange(8, device=bf.device, dtype=torch.uint8)) & 1).view(Cc, H ** 3)
-            lo = torch.full((3,), float("inf"), device=bf.device)
-            hi = torch.full((3,), float("-inf"), device=bf.device)
-            for lvl in range(Cc):
-                idx = bits[lvl].nonzero().view(-1).to(torch.int32).contiguous()
-                if idx.numel() == 0:
-                    continue
-                coords = torch.empty(idx.numel(), 3, dtype=torch.int32, device=bf.device)
-                abi.check(abi.lib().rn_morton3D_invert(abi.ptr(idx), idx.numel(), abi.ptr(coords), abi.cur_stream()))
-                b = min(2.0 ** lvl, bound)
-                cell = 2.0 * b / H
-                lo = torch.minimum(lo, coords.min(0).values.float() * cell - b - cell)
-                hi = torch.maximum(hi, (coords.max(0).values.float() + 1) * cell - b + cell)
-            box = torch.cat([lo, hi])
-            if not hasattr(self, "_occ_box"):
-                self._occ_box = torch.empty(6, device=bf.device)
-            self._occ_box.copy_(box)   # an empty grid leaves (+inf, -inf): every ray is pruned, as it would find nothing
+            L = abi.lib()
+            if getattr(self, "occ_pack", None) is None or self.occ_pack.device != bf.device:
+                self.occ_pack = torch.zeros(int(L.rn_occupancy_pack_bytes()), dtype=torch.uint8, device=bf.device)
+                self._occ_box = self.occ_pack[16:40].view(torch.float32)
+            with torch.cuda.device(bf.device):
+                abi.check(L.rn_occupancy_pack(abi.ptr(bf), int(model.cascade), int(model.grid_size), float(model.bound), abi.ptr(self.occ_pack),
+                                              abi.cur_stream()), "rn_occupancy_pack")
+            words, usable = self.occ_pack[4:12].view(torch.int32).tolist()     # outside any capture: a bitfield change is not steady state
+            self.occ_words = int(words) if usable else 0
             self._occ_tag = tag
         return self._occ_box
+
+
+# Staging the box-packed occupancy bits in shared memory (north_star's sketch; csrc/occ_pack.cu, march_compact_kernel) is implemented and
+# bit-exact, but it is NOT faster on B200 and therefore off by default (RADNERF_OCC_PACK=1 turns it on): the DDA is bound by the ~100
+# dependent instructions of a probe, not by the bitfield load, which hits L1 for the coherent rays of a frame.  Measured per launch at
+# 512x512 (tools/frame_timeline.py, profiles/r02_frame_timeline_512_occ_pack.txt): 6.2 / 9.2 / 8.6 / 8.2 / 7.4 us staged vs 4.1 / 8.2 / 7.7 /
+# 7.2 / 6.4 us from global memory; frames/s 3 318 vs 3 432.
+_NO_OCC_PACK = not bool(int(__import__("os").environ.get("RADNERF_OCC_PACK", "0")))
 
 
 class FusedState:
@@ -393,6 +394,8 @@ def head_desc(model, st, rays_o, rays_d, noises, dt_gamma, max_steps, T_thresh):
     hd.head_blob, hd.head_consts = st.head_blob.data_ptr(), st.head_consts.data_ptr()
     hd.capture_unroll = st.capture_unroll
     hd.occ_aabb = st.occupied_box(model).data_ptr()
+    if st.shared.occ_words and not _NO_OCC_PACK:
+        hd.occ_pack, hd.occ_words = st.shared.occ_pack.data_ptr(), st.shared.occ_words
     return hd, (weights_sum, depth, image, nears, fars)
 
 
@@ -483,7 +486,8 @@ def render_frame(model, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=
 
     if st.use_graph and not perturb:
         key = (N, None if auds_t is None else tuple(auds_t.shape), eye_t is not None, bg_t is not None, bg_scalar, float(dt_gamma),
-               int(max_steps), float(T_thresh), float(model.mean_density_torso), model.density_bitfield.data_ptr(), bool(external_cond))
+               int(max_steps), float(T_thresh), float(model.mean_density_torso), model.density_bitfield.data_ptr(), bool(external_cond),
+               int(st.shared.occ_words))
         entry = st.graphs.get(key)
         if entry is None:
             # small per-frame inputs live in ONE block [pose 4x4 | pose6 | eye | pad | auds] so that a streaming caller

@@ -114,3 +114,68 @@ def test_occupancy_merge_and_device_threshold_packbits():
         abi.call("rn_packbits_min", got, n // 8, float(thresh), mean, bits)
         ref = rm.packbits(got.view(1, -1), min(float(mean), thresh))
         assert torch.equal(bits, ref.view(-1))
+
+
+@pytest.mark.parametrize("C,H,fill", [(1, 128, "head"), (2, 64, "blobs"), (1, 32, "empty"), (1, 64, "full")])
+def test_occupancy_pack_is_the_bitfield_restricted_to_its_boxes(C, H, fill):
+    """rn_occupancy_pack (the copy of the bitfield the fused marcher stages in shared memory): per cascade the box is exactly the
+    bounding box of the set bits, every cell inside it carries the bitfield's bit, and the world box is the inflated hull"""
+    import numpy as np
+    from radnerf_b200 import abi, synthetic as syn
+    rng = np.random.default_rng(C * 1000 + H)
+    occ = np.zeros((C, H, H, H), bool)                      # [level, x, y, z]
+    if fill == "head":
+        grid = syn.head_density_grid(H, semi_axes=(0.34, 0.24, 0.37))          # Morton-ordered density, one cascade
+        bits_np = syn.packbits_np(grid, min(float(np.clip(grid, 0, None).mean()), 10.0))
+    else:
+        if fill == "blobs":
+            occ[0, 10:30, 5:9, 40:64] = rng.random((20, 4, 24)) < 0.5
+            occ[1, 3:5, 60:64, 0:2] = True
+        elif fill == "full":
+            occ[:] = True
+        from oracle import oracle as O
+        xs = np.stack(np.meshgrid(np.arange(H), np.arange(H), np.arange(H), indexing="ij"), -1).reshape(-1, 3).astype(np.int32)
+        m = O.morton3D(xs).astype(np.int64)
+        flat = np.zeros((C, H ** 3), np.uint8)
+        for l in range(C):
+            flat[l, m] = occ[l].reshape(-1)
+        bits_np = np.packbits(flat.reshape(-1), bitorder="little")
+    bf = torch.from_numpy(bits_np).cuda()
+    pack = torch.zeros(int(abi.lib().rn_occupancy_pack_bytes()), dtype=torch.uint8, device="cuda")
+    bound = float(2 ** (C - 1))
+    abi.check(abi.lib().rn_occupancy_pack(abi.ptr(bf), C, H, bound, abi.ptr(pack), abi.cur_stream()))
+    torch.cuda.synchronize()
+    raw = pack.cpu().numpy()
+    hdr = raw[:16].view(np.int32)
+    box = raw[16:40].view(np.float32)
+    lv = raw[48:48 + 32 * 16].view(np.int32).reshape(16, 8)
+    words = raw[560:].view(np.uint32)
+    # decode the bitfield on the host
+    from oracle import oracle as O
+    xs = np.stack(np.meshgrid(np.arange(H), np.arange(H), np.arange(H), indexing="ij"), -1).reshape(-1, 3).astype(np.int32)
+    m = O.morton3D(xs).astype(np.int64)
+    allbits = np.unpackbits(bits_np, bitorder="little").reshape(C, H ** 3)
+    want_lo, want_hi, total = np.full(3, np.inf), np.full(3, -np.inf), 0
+    for l in range(C):
+        cells = allbits[l][m].reshape(H, H, H).astype(bool)
+        lo, dim, off = lv[l, 0:3], lv[l, 3:6], lv[l, 6]
+        if not cells.any():
+            assert (dim == 0).all()
+            continue
+        idx = np.argwhere(cells)
+        assert (lo == idx.min(0)).all() and (lo + dim - 1 == idx.max(0)).all()
+        n = int(dim.prod())
+        sub = cells[lo[0]:lo[0] + dim[0], lo[1]:lo[1] + dim[1], lo[2]:lo[2] + dim[2]]
+        got = np.unpackbits(words[off:off + (n + 31) // 32].view(np.uint8), bitorder="little")[:n].reshape(dim[2], dim[1], dim[0])
+        assert hdr[2] == 1 and np.array_equal(got.astype(bool), sub.transpose(2, 1, 0))      # x fastest
+        b = min(2.0 ** l, bound)
+        cell = 2 * b / H
+        want_lo = np.minimum(want_lo, idx.min(0) * cell - b - cell)
+        want_hi = np.maximum(want_hi, (idx.max(0) + 1) * cell - b + cell)
+        assert off == total
+        total += (n + 31) // 32
+    assert hdr[0] == C and hdr[1] == total
+    if total:
+        assert np.allclose(box[:3], want_lo, atol=1e-6) and np.allclose(box[3:], want_hi, atol=1e-6)
+    else:
+        assert hdr[2] == 0 and (box[:3] > box[3:]).all()        # empty grid: every ray is pruned

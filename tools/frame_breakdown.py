@@ -75,6 +75,8 @@ p = prof.cpu().numpy()
 tot = p[4]
 print("head_eval phase cycles (sum over %d group-runs): enc3 %.1f%% enc2 %.1f%% mma-wait %.1f%% epilogue(4-chunk) %.1f%% other %.1f%%; cycles/tile/group = %.0f" % (
     p[5], 100*p[0]/tot, 100*p[1]/tot, 100*p[2]/tot, 100*p[3]/tot, 100*(tot-p[0]-p[1]-p[2]-p[3])/tot, tot / (815354/128)))
+print("head_eval CTA set-up (kernel entry -> first tile; barriers, TMA issue, TMEM alloc, level tables): %.0f cycles = %.2f us per group-run" % (
+    p[6] / max(1, p[5]), p[6] / max(1, p[5]) / 1965.0))
 
 # ---- conditioning kernel alone: 20 launches inside one CUDA graph -> pure device time
 st = model._fused
