@@ -230,7 +230,10 @@ typedef struct rn_grid_table {
  * quarter-rate conversion pipe); auds, eye, codes and pose stay fp32. */
 typedef struct rn_conditioning_desc {
     const float* auds;           /* [F, Cin, 16] or NULL (no audio) */
-    uint32_t F, Cin, att, smooth, reserved;
+    uint32_t F, Cin, att, smooth;
+    uint32_t reserved;           /* phase: 0 = whole conditioning; 1 = audio features only (AudioNet + attention; the raw code is parked in
+                                    head_consts[0..63]); 2 = smoothing + hoisted terms only (reads it back).  1 then 2 == 0; the split lets
+                                    frames in flight evaluate their audio nets concurrently and serialises only the EMA tail */
     const void* conv_w[4]; const void* conv_b[4];      /* fp16 */
     const void* fc_w[2]; const void* fc_b[2];
     const void* att_w[5]; const void* att_b[5];

@@ -160,12 +160,19 @@ audio_frame_kernel(const __grid_constant__ AudioParams p, const __grid_constant_
 
     // ---- stage every weight matrix of the frame in shared memory: one TMA bulk copy + one mbarrier per matrix, each issued
     //      by its own thread, so a layer only waits for its own weights
+    // phase (AudioParams::reserved): 0 = the whole conditioning; 1 = FEATURES only -- AudioNet + attention of this frame, the raw
+    // (unsmoothed) code parked in head_consts[0..63]; 2 = SMOOTH + HOIST only -- picks the raw code up there.  Frames in flight on
+    // several lanes are coupled only through the lip-smoothing EMA: with the split, the ~35 us of network evaluation run concurrently
+    // on the lanes' own streams and only the ~5 us tail is serialised in frame order (one 40 us kernel per frame in frame order
+    // capped a GPU at ~21 k frames/s and put 20 x 46 us in front of a 20-frame window on 8 GPUs).
+    const uint32_t phase = p.reserved;
+    auto staged = [&](uint32_t slot) { return phase == 0 || ((phase == 1) == (slot < 12)); };
     if (tid < N_SLOTS) {
         const AudioSlot& sl = pg.slots[tid];
         umma::mbar_init(&mbar[tid], 1);
         umma::fence_mbar_init();
         s_tma[tid] = sl.tma;
-        if (sl.tma) {
+        if (sl.tma && staged(tid)) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(&mbar[tid])), "r"(sl.bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(umma::smem_u32(smem + sl.off)),
                          "l"(sl.src), "r"(sl.bytes), "r"(umma::smem_u32(&mbar[tid]))
@@ -177,7 +184,7 @@ audio_frame_kernel(const __grid_constant__ AudioParams p, const __grid_constant_
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_layers);
         for (uint32_t i = tid; i < sizeof(pg.layers) / 4; i += blockDim.x) dst[i] = src[i];
     }
-    if (p.auds) {
+    if (p.auds && phase != 2) {
         const uint32_t cp0 = pg.cp0;
         uint32_t* z = reinterpret_cast<uint32_t*>(hA);
         for (uint32_t i = tid; i < F * 18 * cp0 / 2; i += blockDim.x) z[i] = 0u;
@@ -188,7 +195,7 @@ audio_frame_kernel(const __grid_constant__ AudioParams p, const __grid_constant_
 #pragma unroll 1
     for (int i = 0; i < N_SLOTS; ++i) {   // odd-sized / unaligned matrices: plain copy, re-strided to an even row pitch
         const AudioSlot& sl = pg.slots[i];
-        if (sl.bytes == 0 || sl.tma) continue;
+        if (sl.bytes == 0 || sl.tma || !staged((uint32_t)i)) continue;
         __half* dst = reinterpret_cast<__half*>(smem + sl.off);
         for (uint32_t j = tid; j < (uint32_t)sl.rows * sl.ld_src; j += blockDim.x) {
             const uint32_t r = j / sl.ld_src, cc = j - r * sl.ld_src;
@@ -196,7 +203,7 @@ audio_frame_kernel(const __grid_constant__ AudioParams p, const __grid_constant_
         }
     }
     __syncthreads();
-    if (p.auds) {   // [F][Cin][16] fp32 -> [F][1 + 16 + 1][cp0] fp16
+    if (p.auds && phase != 2) {   // [F][Cin][16] fp32 -> [F][1 + 16 + 1][cp0] fp16
         const uint32_t Cin = p.Cin, cp0 = pg.cp0;
         for (uint32_t i = tid; i < F * Cin * 16; i += blockDim.x) {
             const uint32_t l = i & 15, fc = i >> 4, f = fc / Cin, ci = fc - f * Cin;
@@ -210,7 +217,11 @@ audio_frame_kernel(const __grid_constant__ AudioParams p, const __grid_constant_
     cx.smem = smem; cx.hA = hA; cx.hB = hB; cx.vec = s_vec; cx.bias = &s_bias[0][0]; cx.mbar = mbar; cx.layers = s_layers; cx.slot_tma = s_tma;
     cx.head_consts = p.head_consts; cx.torso_consts = p.torso_consts; cx.prof = prof;
 
-    if (p.auds) {
+    if (p.auds && phase == 2) {
+        if (tid < 64) s_enc[tid] = p.head_consts[tid];      // the raw code of this frame, left there by the phase-1 launch
+        __syncthreads();
+    }
+    if (p.auds && phase != 2) {
         run_layers(cx, 0, pg.n_net);   // AudioNet convs + fcs -> x, attention convs + fc -> logits hB[256 .. 256+F)
         const __half* x = hA + (p.att > 0 ? 64 : 0);   // rows 1..F of the attention input layout
         if (p.att > 0) {
@@ -231,6 +242,12 @@ audio_frame_kernel(const __grid_constant__ AudioParams p, const __grid_constant_
             s_enc[tid] = __half2float(x[tid]);
         }
         __syncthreads();
+        if (phase == 1) {
+            if (tid < 64) p.head_consts[tid] = s_enc[tid];
+            return;
+        }
+    }
+    if (p.auds) {
         if (tid < 64) {
             float e = s_enc[tid];
             if (p.smooth) {

@@ -63,10 +63,21 @@ extern "C" int rn_lane_submit_frame(const rn_lane_submit* s) {
             int rc = rn_get_rays(s->pose, s->fx, s->fy, s->cx, s->cy, s->H, s->W, s->pixel_ids, s->n_rays, s->rays_o, s->rays_d, ls);
             if (rc) return rc;
         }
+        // conditioning in two launches: the audio nets of THIS frame on the lane's own stream (concurrent across lanes; the lane's
+        // previous frame, which read the hoisted-term vectors, precedes it in stream order), then only the lip-smoothing EMA + the
+        // hoisted products in frame order on the conditioning stream
+        rn_conditioning_desc cd = *s->cond;
+        const bool split = cd.auds != nullptr && cd.reserved == 0;
+        if (split) {
+            cd.reserved = 1;
+            int rc1 = rn_frame_conditioning(&cd, ls);
+            if (rc1) return rc1;
+            cd.reserved = 2;
+        }
         RN_CU(cudaEventRecord((cudaEvent_t)s->ev_in, ls));
-        RN_CU(cudaStreamWaitEvent(cs, (cudaEvent_t)s->ev_in, 0));     // the conditioning reads the input block
+        RN_CU(cudaStreamWaitEvent(cs, (cudaEvent_t)s->ev_in, 0));     // the conditioning reads the input block / the parked raw code
         RN_CU(cudaStreamWaitEvent(cs, (cudaEvent_t)s->ev_done, 0));   // lane's previous frame no longer reads its hoisted-term vectors
-        int rc = rn_frame_conditioning(s->cond, cs);
+        int rc = rn_frame_conditioning(&cd, cs);
         if (rc) return rc;
         RN_CU(cudaEventRecord((cudaEvent_t)s->ev_cond, cs));
         RN_CU(cudaStreamWaitEvent(ls, (cudaEvent_t)s->ev_cond, 0));
