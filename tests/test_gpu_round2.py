@@ -1,4 +1,6 @@
 """Round-2 kernels in isolation: the MN-major tcgen05 contraction (weight gradients) and the restructured 3-D table backward."""
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -179,3 +181,57 @@ def test_occupancy_pack_is_the_bitfield_restricted_to_its_boxes(C, H, fill):
         assert np.allclose(box[:3], want_lo, atol=1e-6) and np.allclose(box[3:], want_hi, atol=1e-6)
     else:
         assert hdr[2] == 0 and (box[:3] > box[3:]).all()        # empty grid: every ray is pruned
+
+
+def test_gather_to_root_protocol_with_two_ranks_emulated_on_one_gpu():
+    """rn_scatter_rows_to_root + rn_stage_frame_at_root (arrival counter / consumed flags, csrc/peer_gather.cu) with TWO ranks emulated
+    on one device: both 'ranks' own a frame buffer and a control block in this process's memory, their kernels run on separate streams.
+    Every staged frame must be exactly frame i (fp32 and uint8 staging), the arrival counter and the consumed flags must end at their
+    expected values.  The real
+    multi-process run is tools/gather_to_root_check.py (profiles/r02_gather_to_root_2gpu.json)."""
+    import numpy as np
+    from radnerf_b200 import abi
+    from radnerf_b200.sharding import local_pixel_ids
+    L = abi.lib()
+    H = W = 64
+    world, n_slots, n_frames = 2, 2, 12
+    ids = [local_pixel_ids(H, W, world, r).to(torch.int32).cuda() for r in range(world)]
+    n_local = ids[0].numel()
+    frames_buf = [[torch.zeros(H * W, 3, device="cuda") for _ in range(n_slots)] for _ in range(world)]
+    ctrl = [torch.zeros(2 * n_slots + 2, dtype=torch.int64, device="cuda") for _ in range(world)]
+    frame_peers = [torch.tensor([frames_buf[r][k].data_ptr() for r in range(world)], dtype=torch.int64, device="cuda") for k in range(n_slots)]
+    ctrl_peers = torch.tensor([c.data_ptr() for c in ctrl], dtype=torch.int64, device="cuda")
+    tickets = torch.zeros(n_slots, dtype=torch.int32, device="cuda")
+    ctas = int(L.rn_scatter_signal_ctas(n_local, W))
+    assert ctas >= 1
+    base = torch.rand(H * W, 3, generator=torch.Generator().manual_seed(1)).cuda()
+    rows = [base.index_select(0, i.long()).contiguous() for i in ids]
+    staged32 = [torch.zeros(H * W, 3, device="cuda") for _ in range(n_frames)]
+    staged8 = [torch.zeros(H * W * 3, dtype=torch.uint8, device="cuda") for _ in range(n_frames)]
+    s_root, s_peer = torch.cuda.Stream(), torch.cuda.Stream()
+    # every buffer exists before the first launch: an allocation (cudaMalloc) while the peer's kernel spins on a flag that only later
+    # launches of this same thread can set would stall the host against the device
+    locs = [[(rows[r] * ((i + 1) / 16.0)).contiguous() for i in range(n_frames)] for r in range(world)]
+    torch.cuda.synchronize()
+    # launches interleaved in frame order (as the two processes would issue them): every wait is on a launch that precedes it even if
+    # both streams share a hardware queue; the peer still runs a frame ahead of the root's staging, so frame i+2 of a buffer is only
+    # written after the consumed flag of frame i
+    for i in range(n_frames):
+        k, seq = i % n_slots, i // n_slots + 1
+        with torch.cuda.stream(s_peer):
+            abi.check(L.rn_scatter_rows_to_root(abi.ptr(locs[1][i]), abi.ptr(ids[1]), n_local, W, abi.ptr(frame_peers[k]), abi.ptr(ctrl_peers), world, 1, 0, k,
+                                                seq, C.c_void_p(s_peer.cuda_stream)))
+        with torch.cuda.stream(s_root):
+            abi.check(L.rn_scatter_rows_to_root(abi.ptr(locs[0][i]), abi.ptr(ids[0]), n_local, W, abi.ptr(frame_peers[k]), abi.ptr(ctrl_peers), world, 0, 0, k,
+                                                seq, C.c_void_p(s_root.cuda_stream)))
+            u8 = i % 2 == 1
+            abi.check(L.rn_stage_frame_at_root(abi.ptr(frames_buf[0][k]), abi.ptr(staged8[i] if u8 else staged32[i]), H * W * 3, 1 if u8 else 0,
+                                               abi.ptr(ctrl_peers), world, 0, k, seq, ctas, tickets[k:k + 1].data_ptr(), C.c_void_p(s_root.cuda_stream)))
+    torch.cuda.synchronize()
+    for i in range(n_frames):
+        want = base * ((i + 1) / 16.0)
+        if i % 2 == 1:
+            assert torch.equal(staged8[i].view(-1, 3), (want * 255.0).to(torch.uint8)), i
+        else:
+            assert torch.equal(staged32[i], want), i
+    assert int(ctrl[0][0]) == (n_frames // n_slots) * ctas and int(ctrl[1][1]) == n_frames // n_slots       # arrivals at the root, frames consumed
