@@ -53,11 +53,14 @@ static_assert(G_H0 >= 128 * 80 * 2, "CIN must fit in A0 + H1");
 constexpr int HEAD_GROUPS = 4;
 constexpr uint32_t HEAD_SMEM = HEAD_BLOB_BYTES + HEAD_GROUPS * GROUP_BYTES;
 constexpr uint32_t TMEM_COLS_PER_GROUP = 128;
+// (a register cap through a larger launch bound -- 80 registers, so that the small kernels of other frame lanes fit next to a resident
+// CTA -- was measured in round 2: the spills cost more than the co-residency gives, 56.7 vs 52.6 us per launch, 3 200 vs 3 300 frames/s)
+#define HEAD_LAUNCH_BOUND (HEAD_GROUPS * 128)
 
 // PROF: the per-phase cycle counters of tools/frame_breakdown.py; compiled out of the production instantiation (the clock reads and
 // their bookkeeping were ~3 % of the kernel's instructions even with the counters switched off at run time)
 template <bool PROF>
-__global__ void __launch_bounds__(HEAD_GROUPS * 128, 1)
+__global__ void __launch_bounds__(HEAD_LAUNCH_BOUND, 1)
 head_eval_kernel(HeadEvalParams p, const FrameCur* cur) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ FastLevel lv3[16], lv2[16];
