@@ -83,7 +83,7 @@ def frame_rate(dev, hw, steps, warmup=5, backend="ref", torso=True, asr_model="c
                                                          else "this repository's drop-in operator packages (rad-nerf_b200/)")}
 
 
-def train_rate(dev, n_rays=65536, steps=48, warmup=20, backend="ref"):
+def train_rate(dev, n_rays=65536, steps=48, warmup=70, backend="ref"):
     from radnerf_b200 import synthetic as syn
     if not stock.available(backend):
         return {"unavailable": "baseline/_ref (reference Python) or oracle/_ref (reference extensions) not installed"}

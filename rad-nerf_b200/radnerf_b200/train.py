@@ -11,6 +11,8 @@ NCCL over NVLink and divided by the world size.  The three hash tables carry ~99
 from an autograd hook the moment its gradient is accumulated -- asynchronously, overlapping the remainder of backward --
 while every small parameter (MLPs, audio nets, codes) travels in ONE flat bucket once backward is done.  There is no
 collective in the forward pass."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -247,6 +249,7 @@ class GraphedTrainStep:
         self.mc_version = None     # model.mean_count_version the budget was last refreshed for
         self.mc_host = 0           # last mean_count known to the HOST (decides the capacity bucket)
         self.mc_pending = None     # (pinned int32, event): an asynchronous read-back of a device-side mean_count
+        self.capacity = None       # sample slots of the captured step's buffers
         self._params = [p for g in optimizer.param_groups for p in g["params"]]
 
     def _eager(self, batch):
@@ -262,9 +265,16 @@ class GraphedTrainStep:
         self.static["index"].copy_(torch.as_tensor(idx, dtype=torch.long).reshape(-1)[:1].to(dev, non_blocking=True))
 
     def _capacity(self, mean_count=None):
+        """(padded mean_count = the marcher's budget, capacity of the captured buffers).  The capacity has HEADROOM and HYSTERESIS: 20 %
+        above the estimate at capture time, rounded up to `bucket` slots, and kept while the estimate stays inside [60 %, 100 %] of it --
+        the estimate drifts by a few per cent at every occupancy update, and a re-capture (the step run eagerly under capture +
+        instantiation: 10-100 ms depending on the host) must not happen every few updates."""
         padded = int(self.mc_host if mean_count is None else mean_count)
         padded = padded + (128 - padded % 128)            # raymarching._padded(mean_count, 128), what the eager marcher allocates
-        return padded, (padded + self.bucket - 1) // self.bucket * self.bucket
+        cap = self.capacity
+        if cap is None or padded > cap or padded < 0.6 * cap:
+            cap = (int(padded * 1.2) + self.bucket - 1) // self.bucket * self.bucket
+        return padded, cap
 
     def _set_budget(self, padded):
         if self.budget is None:
@@ -356,9 +366,11 @@ class GraphedTrainStep:
         padded, capacity = self._capacity()
         key = (capacity, shapes, self.phase)
         if key != self.key:
+            if os.environ.get("RADNERF_DEBUG_CAPTURE"):
+                print("GraphedTrainStep capture: mean_count(host) %s padded %d capacity %s -> %d" % (self.mc_host, padded, self.capacity, capacity), flush=True)
             try:
                 self._capture(batch, capacity)
-                self.key = key
+                self.key, self.capacity = key, capacity
             except Exception as e:  # noqa: BLE001
                 self.fallback_reason = repr(e)[:300]
                 self.graph, self.graph_tail, self.key = None, None, None

@@ -125,13 +125,15 @@ def test_graphed_step_replays_the_whole_step_and_follows_the_schedule():
     step(batches[2])
     assert step.captures == 1 and step.fallback_reason is None
     assert int(step.budget.item()) == padded + 128
-    model.mean_count = 1024                                             # far too small: most rays are dropped, none may write past it
+    model.mean_count = int(0.65 * capacity)                             # inside [60 %, 100 %] of the captured capacity: still no new graph
+    step(batches[0])
+    assert step.captures == 1 and int(step.budget.item()) == model.mean_count + (128 - model.mean_count % 128)
+    model.mean_count = 1024                                             # far below: most rays are dropped; the smallest bucket stays
     row = model.local_step % 16
     step(batches[0])
-    assert step.captures == 1
-    kept_small = int(model.step_counter[row, 0])                        # the counter still counts every sample the rays wanted
-    assert kept_small > 1024
-    model.mean_count = capacity + 1                                     # crosses the bucket: one re-capture
+    assert step.captures == 1 and int(step.budget.item()) == 1152
+    assert int(model.step_counter[row, 0]) > 1024                       # the counter still counts every sample the rays wanted
+    model.mean_count = step.capacity + 1                                # exceeds the captured capacity: one re-capture
     step(batches[1])
     assert step.captures == 2 and step.fallback_reason is None
 
