@@ -429,6 +429,11 @@ typedef struct rn_head_train_desc {
                                                         encoder-fed weight columns + the three column sums that carry the hoisted
                                                         columns (layout: csrc/head_train.cuh G_*) */
     void* workspace; uint64_t workspace_bytes;       /* rn_head_train_workspace_bytes(M) */
+    const int32_t* m_valid;                          /* optional DEVICE scalar: only rows [0, min(M, *m_valid)) hold samples (the marcher's
+                                                        counter, clamped to its budget); the rest of the buffers is padding -- zero
+                                                        positions that would all fall into the same grid cells.  Padding tiles are not
+                                                        evaluated (forward outputs there are left untouched: pre-zero them) and are marked
+                                                        out of range for the table scatters.  NULL: all M rows are samples. */
 } rn_head_train_desc;
 uint64_t rn_head_train_acts_bytes(uint32_t M);
 uint64_t rn_head_train_workspace_bytes(uint32_t M);

@@ -45,6 +45,7 @@ struct BwdParams {
     float* amb01;       // [M_pad, 2]   the 2-D encoder's input, recomputed with the forward's own expression
     float* x01;         // [M_pad, 3]   the 3-D encoder's input
     float* partials;    // [gridDim.x][DW_COLS][128]
+    const int32_t* m_valid;   // optional device scalar: rows >= min(M, *m_valid) are padding
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
@@ -167,8 +168,23 @@ head_train_bwd_kernel(BwdParams p) {
     __shared__ __align__(8) uint64_t bar_ready[BWD_GROUPS], bar_done[BWD_GROUPS], bar_ld[BWD_GROUPS][2], bar_w;
     __shared__ uint32_t tmem_slot;
 
-    const uint32_t n_tiles = (p.M + 127) / 128;
-    if (blockIdx.x * BWD_GROUPS >= n_tiles) return;
+    const uint32_t M_eff = p.m_valid ? min(p.M, (uint32_t)max(__ldg(p.m_valid), 0)) : p.M;
+    const uint32_t n_tiles = (M_eff + 127) / 128, n_tiles_all = (p.M + 127) / 128;
+    // padding rows (zero positions: all in the same grid cells) are marked out of range for the table scatter that follows this kernel;
+    // whole padding tiles by a grid-stride sweep here, the tail of the last real tile by its own threads below
+    {
+        const uint32_t first = n_tiles * 128u, last = n_tiles_all * 128u;
+        for (uint32_t s = first + blockIdx.x * blockDim.x + threadIdx.x; s < last; s += gridDim.x * blockDim.x) {
+            if constexpr (WHICH == 1) { p.amb01[(size_t)s * 2] = -1.0f; p.amb01[(size_t)s * 2 + 1] = -1.0f; }
+            else { p.x01[(size_t)s * 3] = -1.0f; p.x01[(size_t)s * 3 + 1] = -1.0f; p.x01[(size_t)s * 3 + 2] = -1.0f; }
+        }
+    }
+    if (blockIdx.x * BWD_GROUPS >= n_tiles) {
+        // no tile for this CTA (the launch was sized for M, the batch holds fewer samples): its partial sums are zeros
+        float* out = p.partials + (size_t)blockIdx.x * P::DW_COLS * 128;
+        for (uint32_t i = threadIdx.x; i < P::DW_COLS * 128; i += blockDim.x) out[i] = 0.0f;
+        return;
+    }
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     uint8_t* s_groups = smem;                                     // groups first: the MN-major reads of an 80-wide operand run 768 bytes
     uint8_t* s_blob = smem + BWD_GROUPS * GRP_BYTES;              // past their buffer -- into valid shared memory
@@ -260,7 +276,7 @@ head_train_bwd_kernel(BwdParams p) {
         };
         for (uint32_t tile = blockIdx.x * BWD_GROUPS + g; tile < n_tiles; tile += stride) {
             const uint32_t s = tile * 128 + t;
-            const bool valid = s < p.M;
+            const bool valid = s < M_eff;
             const uint32_t k0 = k;
             if constexpr (WHICH == 1) {
                 // ---- dL/d(colour pre-activation) = dL/d(rgb) * sigmoid'  -> dZc2 [128 x 16]
@@ -325,7 +341,7 @@ head_train_bwd_kernel(BwdParams p) {
                     float a0 = 0.f, a1 = 0.f;
                     if (valid) { a0 = __ldg(p.ambient + (size_t)s * 2); a1 = __ldg(p.ambient + (size_t)s * 2 + 1); }
                     *reinterpret_cast<float2*>(p.amb01 + (size_t)s * 2) =
-                        make_float2(__fmul_rn(__fadd_rn(a0, 1.0f), 0.5f), __fmul_rn(__fadd_rn(a1, 1.0f), 0.5f));
+                        valid ? make_float2(__fmul_rn(__fadd_rn(a0, 1.0f), 0.5f), __fmul_rn(__fadd_rn(a1, 1.0f), 0.5f)) : make_float2(-1.0f, -1.0f);
                 }
             } else {
                 // ---- dL/d(ambient pre-activation) = (compositor path + 0.5 * 2-D grid path) * tanh'  -> dZa3 [128 x 16]
@@ -367,9 +383,9 @@ head_train_bwd_kernel(BwdParams p) {
                     float px = 0.f, py = 0.f, pz = 0.f;
                     if (valid) { px = __ldg(p.xyzs + (size_t)s * 3); py = __ldg(p.xyzs + (size_t)s * 3 + 1); pz = __ldg(p.xyzs + (size_t)s * 3 + 2); }
                     float* xo = p.x01 + (size_t)s * 3;
-                    xo[0] = __fmul_rn(__fadd_rn(px, p.bound), p.inv2bound);
-                    xo[1] = __fmul_rn(__fadd_rn(py, p.bound), p.inv2bound);
-                    xo[2] = __fmul_rn(__fadd_rn(pz, p.bound), p.inv2bound);
+                    xo[0] = valid ? __fmul_rn(__fadd_rn(px, p.bound), p.inv2bound) : -1.0f;
+                    xo[1] = valid ? __fmul_rn(__fadd_rn(py, p.bound), p.inv2bound) : -1.0f;
+                    xo[2] = valid ? __fmul_rn(__fadd_rn(pz, p.bound), p.inv2bound) : -1.0f;
                 }
             }
         }
@@ -498,6 +514,7 @@ extern "C" int rn_head_train_backward(const rn_head_train_desc* d, void* stream)
     p.d_sigma = d->d_sigma; p.d_rgb = d->d_rgb; p.rgb = d->rgb; p.sigma_pre = d->sigma_pre;
     p.d_ambient = d->d_ambient; p.d_amb01 = w.d_amb01; p.xyzs = d->xyzs; p.bound = d->bound; p.inv2bound = 1.0f / (2.0f * d->bound);
     p.ambient = d->ambient; p.dEx = w.dEx; p.dEw = w.dEw; p.amb01 = w.amb01; p.x01 = w.x01;
+    p.m_valid = d->m_valid;
 
     // ---- colour + sigma nets
     {

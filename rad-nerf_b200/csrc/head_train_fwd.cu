@@ -50,6 +50,7 @@ struct FwdParams {
     float* sigma; float* rgb; float* ambient; float* sigma_pre;
     uint8_t* acts; __half* dy_dx2;
     float bound, inv2bound;
+    const int32_t* m_valid;
 };
 
 // TMEM row -> (ReLU) -> fp16 -> the next layer's A operand row in shared memory AND the same row of the tile record in global memory
@@ -173,7 +174,9 @@ head_train_fwd_kernel(FwdParams p) {
     __shared__ __align__(8) uint64_t mbar_w;
     __shared__ uint32_t tmem_slot;
 
-    const uint32_t n_tiles = (p.M + EVAL_TILE - 1) / EVAL_TILE;
+    // rows past *m_valid are padding of the sample buffers: whole padding tiles are skipped (their outputs stay as the caller left them)
+    const uint32_t M_eff = p.m_valid ? min(p.M, (uint32_t)max(__ldg(p.m_valid), 0)) : p.M;
+    const uint32_t n_tiles = (M_eff + EVAL_TILE - 1) / EVAL_TILE;
     if (blockIdx.x * FWD_GROUPS >= n_tiles) return;
 
     const uint32_t tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = tid >> 5;
@@ -235,7 +238,7 @@ head_train_fwd_kernel(FwdParams p) {
 
     for (uint32_t tile = blockIdx.x * FWD_GROUPS + g; tile < n_tiles; tile += gridDim.x * FWD_GROUPS) {
         const uint32_t s = tile * EVAL_TILE + t;
-        const bool valid = s < p.M;
+        const bool valid = s < M_eff;
         // p.acts == nullptr: nothing is saved (the density query of the occupancy update); REC(x) = where layer input x is saved
         uint8_t* rec = p.acts ? p.acts + (size_t)tile * TILE_RECORD_BYTES : nullptr;
 #define REC(off) (rec ? rec + (off) : nullptr)
@@ -402,6 +405,7 @@ int launch_head_train_fwd(const rn_head_train_desc* d, cudaStream_t st) {
     p.sigma = d->sigma; p.rgb = d->rgb; p.ambient = d->ambient; p.sigma_pre = d->sigma_pre;
     p.acts = (uint8_t*)d->acts; p.dy_dx2 = (__half*)d->dy_dx2;
     p.bound = d->bound; p.inv2bound = 1.0f / (2.0f * d->bound);
+    p.m_valid = d->m_valid;
     cudaError_t e = cudaFuncSetAttribute(head_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
     if (e != cudaSuccess) { set_error("head_train_fwd: cannot reserve %u bytes of shared memory: %s", FWD_SMEM, cudaGetErrorString(e)); return (int)e; }
     const uint32_t n_tiles = (d->M + EVAL_TILE - 1) / EVAL_TILE;

@@ -34,7 +34,7 @@ class HeadTrainDesc(C.Structure):   # rn_head_train_desc
                 ("acts", _vp), ("dy_dx2", _vp),
                 ("d_sigma", _vp), ("d_rgb", _vp), ("d_ambient", _vp),
                 ("d_table3", _vp), ("d_table2", _vp), ("d_weights", _vp),
-                ("workspace", _vp), ("workspace_bytes", _u64)]
+                ("workspace", _vp), ("workspace_bytes", _u64), ("m_valid", _vp)]
 
 
 abi.register("rn_head_train_acts_bytes", [_u32], _u64)
@@ -157,7 +157,7 @@ def _hoisted(model, enc_a, ind_code, eye, out):
 class _HeadFn(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)     # fp32 in, autocast off inside (the kernels do their own fp16)
-    def forward(ctx, model, xyzs, dirs, enc_a, ind_code, eye, emb3, emb2, wa1, wa2, wa3, ws1, ws2, ws3, wc1, wc2):
+    def forward(ctx, model, xyzs, dirs, enc_a, ind_code, eye, n_valid, emb3, emb2, wa1, wa2, wa3, ws1, ws2, ws3, wc1, wc2):
         tr = trainer(model)
         xyzs = xyzs.detach().float().contiguous()
         dirs = dirs.detach().float().contiguous()
@@ -167,14 +167,17 @@ class _HeadFn(torch.autograd.Function):
             tr.refresh(model)
             tr.ensure(M)
             _hoisted(model, enc_a, ind_code, eye, tr.consts)
-        sigma = torch.empty(M, device=dev)
-        rgb = torch.empty(M, 3, device=dev)
-        ambient = torch.empty(M, 2, device=dev)
+        # with a device-side sample count the kernels skip the padding rows of the marcher's buffers: their outputs must be defined
+        alloc = torch.empty if n_valid is None else torch.zeros
+        sigma = alloc(M, device=dev)
+        rgb = alloc(M, 3, device=dev)
+        ambient = alloc(M, 2, device=dev)
         d = tr.desc(model, xyzs, dirs, M)
         d.sigma, d.rgb, d.ambient, d.sigma_pre = sigma.data_ptr(), rgb.data_ptr(), ambient.data_ptr(), tr.sigma_pre.data_ptr()
         d.acts, d.dy_dx2 = tr.acts.data_ptr(), tr.dy_dx2.data_ptr()
+        d.m_valid = None if n_valid is None else n_valid.data_ptr()
         abi.check(abi.lib().rn_head_train_forward(C.byref(d), abi.cur_stream()), "rn_head_train_forward")
-        ctx.model, ctx.M = model, M
+        ctx.model, ctx.M, ctx.n_valid = model, M, n_valid
         ctx.save_for_backward(xyzs, dirs, sigma, rgb, ambient, enc_a, ind_code, eye)
         return sigma, rgb, ambient
 
@@ -197,6 +200,7 @@ class _HeadFn(torch.autograd.Function):
         d.d_sigma, d.d_rgb, d.d_ambient = d_sigma.data_ptr(), d_rgb.data_ptr(), d_ambient.data_ptr()
         d.d_table3, d.d_table2, d.d_weights = d_t3.data_ptr(), d_t2.data_ptr(), tr.d_weights.data_ptr()
         d.workspace, d.workspace_bytes = tr.workspace.data_ptr(), tr.workspace.numel()
+        d.m_valid = None if ctx.n_valid is None else ctx.n_valid.data_ptr()
         abi.check(abi.lib().rn_head_train_backward(C.byref(d), abi.cur_stream()), "rn_head_train_backward")
 
         def g(name):
@@ -211,18 +215,20 @@ class _HeadFn(torch.autograd.Function):
         d_enc_a = (cs_a1 @ _h(wa1[:, 32:96])).view_as(enc_a).to(enc_a.dtype) if ctx.needs_input_grad[3] else None
         d_ind = (cs_c1 @ _h(wc1[:, 80:84])).view_as(ind_code).to(ind_code.dtype) if ctx.needs_input_grad[4] else None
         d_eye = (cs_s1 @ _h(ws1[:, 64])).view_as(eye).to(eye.dtype) if ctx.needs_input_grad[5] else None
-        return (None, None, None, d_enc_a, d_ind, d_eye, d_t3, d_t2, d_wa1, g("wa2").clone(), g("wa3").clone(), d_ws1, g("ws2").clone(),
+        return (None, None, None, d_enc_a, d_ind, d_eye, None, d_t3, d_t2, d_wa1, g("wa2").clone(), g("wa3").clone(), d_ws1, g("ws2").clone(),
                 g("ws3").clone(), d_wc1, g("wc2").clone())
 
 
-def head_forward(model, xyzs, dirs, enc_a, ind_code, eye):
+def head_forward(model, xyzs, dirs, enc_a, ind_code, eye, n_valid=None):
     """NeRFNetwork.forward on march_rays_train samples through the fused kernels: -> sigma [M] fp32, color [M,3] fp32 (fp16-rounded
-    values, as the autocast path produces), ambient [M,2] fp32"""
+    values, as the autocast path produces), ambient [M,2] fp32.  n_valid: optional int32 DEVICE tensor [1] -- only the first
+    min(M, n_valid) rows are samples, the rest is the zero padding of the marcher's buffers (outputs there are zeros, no table
+    gradient: the reference evaluates them as points at the origin, all in the same grid cells)."""
     if not supported(model):
         raise NotImplementedError("model configuration outside the fused training kernels' specialisation")
     if enc_a is None or ind_code is None or eye is None:
         raise NotImplementedError("the fused head step needs the audio code, the individual code and the eye value")
-    return _HeadFn.apply(model, xyzs, dirs, enc_a, ind_code, eye, model.encoder.embeddings, model.encoder_ambient.embeddings, *_weights(model))
+    return _HeadFn.apply(model, xyzs, dirs, enc_a, ind_code, eye, n_valid, model.encoder.embeddings, model.encoder_ambient.embeddings, *_weights(model))
 
 
 @torch.no_grad()

@@ -381,7 +381,12 @@ class NeRFNetwork(nn.Module):
                                                        nears, fars, counter, self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps)
         if self._use_fused_train(enc_a, ind_code, eye):
             from . import fused_train    # ONE forward kernel (+ 2 backward kernels) instead of 8 GEMMs + ~150 elementwise launches
-            sigmas, rgbs, ambient = fused_train.head_forward(self, xyzs, dirs, enc_a, ind_code, eye)
+            # samples occupy the first min(counter, budget) rows of the buffers; the fused kernels skip the zero padding behind them
+            n_valid = counter[:1]
+            budget = getattr(getattr(rm, "raymarching", None), "sample_budget", None)
+            if budget is not None and budget.active is not None:
+                n_valid = torch.minimum(n_valid, budget.active.budget)
+            sigmas, rgbs, ambient = fused_train.head_forward(self, xyzs, dirs, enc_a, ind_code, eye, n_valid=n_valid)
         else:
             sigmas, rgbs, ambient = self(xyzs, dirs, enc_a, ind_code, eye)
         weights_sum, ambient_sum, depth, image = rm.composite_rays_train(self.density_scale * sigmas, rgbs, ambient.abs().sum(-1), deltas, rays)
