@@ -18,6 +18,7 @@
 // contracts the reference expressions, and in fp16 mode the per-corner rounding of c10::Half arithmetic
 // (product rounded to half, then a half add; gridencoder.cu:163,186) so forward results are bit-identical.
 #pragma once
+#include <algorithm>
 #include "common.cuh"
 
 namespace rn {
@@ -417,7 +418,30 @@ grid_backward_kernel(const T* __restrict__ grad, const float* __restrict__ input
 // sample loop is uniform per CTA) so every shuffle runs with the full mask.
 constexpr int kMaxGroups = 8;
 
-template <typename T, typename G, int C>
+// Second stage for the clustered case (HASH = true; fp32 table gradient, C = 2): what a warp has aggregated goes into a small hash
+// table in SHARED memory keyed by the table row (all levels share it), and the CTA -- persistent, a few thousand samples each --
+// flushes every touched row to global memory once.  As training proceeds the ambient coordinates of the whole batch collapse onto a
+// few cells per level; after the warp stage that still left ~60 atomics per sample-warp aimed at a few hundred L2 addresses, and
+// the kernel grew from 0.14 to 0.79 ms per step over the first 70 steps of a run (profiles/r02_train_timeline_graphed_after_70_steps.txt).
+// A full table (linear probing, 4 probes) falls back to the global atomic, so uniform inputs cost what they did.
+constexpr uint32_t kHashLog = 11, kHashSlots = 1u << kHashLog, kHashEmpty = 0xffffffffu;
+
+__device__ __forceinline__ bool hash_accumulate(uint32_t* keys, float2* vals, uint32_t key, float a, float b) {
+    uint32_t slot = (key * 2654435761u) >> (32 - kHashLog);
+#pragma unroll
+    for (int probe = 0; probe < 4; ++probe) {
+        const uint32_t prev = atomicCAS(&keys[slot], kHashEmpty, key);
+        if (prev == kHashEmpty || prev == key) {
+            atomicAdd(&vals[slot].x, a);
+            atomicAdd(&vals[slot].y, b);
+            return true;
+        }
+        slot = (slot + 1) & (kHashSlots - 1);
+    }
+    return false;
+}
+
+template <typename T, typename G, int C, bool HASH = false>
 __global__ void __launch_bounds__(256)
 grid_backward_shared_cell_kernel(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
                                  G* __restrict__ grad_table, const T* __restrict__ dy_dx, T* __restrict__ grad_inputs, uint32_t B,
@@ -426,8 +450,13 @@ grid_backward_shared_cell_kernel(const T* __restrict__ grad, const float* __rest
     constexpr int D = 2;
     constexpr uint32_t FULL = 0xffffffffu;
     __shared__ LevelMeta meta[MAX_LEVELS];
+    __shared__ uint32_t h_keys[HASH ? kHashSlots : 1];
+    __shared__ float2 h_vals[HASH ? kHashSlots : 1];
     for (uint32_t l = threadIdx.x; l < L; l += blockDim.x)
         make_level_meta(meta[l], l, offsets, S, H, D, gridtype, align_corners != 0);
+    if constexpr (HASH) {
+        for (uint32_t i = threadIdx.x; i < kHashSlots; i += blockDim.x) { h_keys[i] = kHashEmpty; h_vals[i] = make_float2(0.f, 0.f); }
+    }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
 
@@ -445,11 +474,51 @@ grid_backward_shared_cell_kernel(const T* __restrict__ grad, const float* __rest
         }
         float gin[D] = {0.0f, 0.0f};
 
+        // fp16 rows of 16 levels x 2 features in [B, L*C] order (the fused training step, the autocast GridEncoder): the sample's whole
+        // gradient row (64 B) and d(features)/d(x) row (128 B) are fetched with 12 wide loads BEFORE the level loop -- one memory round
+        // trip per sample instead of two per level (the kernel sat at 27 % issue utilisation waiting on 32 dependent 4- and 8-byte loads)
+        constexpr bool kRowPrefetch = sizeof(T) == 2 && C == 2;
+        const bool prefetch = kRowPrefetch && layout == RN_LAYOUT_BLC && L == 16 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0 &&
+                              (reinterpret_cast<uintptr_t>(dy_dx) & 15) == 0;     // CTA-uniform
+        uint32_t gw[16], dw[32];    // indexed by the level below: lives in (L1-resident) local memory, ~30 cycles instead of an L2 round trip
+        if (prefetch && in_range) {
+            const uint4* gp4 = reinterpret_cast<const uint4*>(grad + (size_t)b * 32);
+            uint4 q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = __ldg(gp4 + i);
+            uint4 r[8] = {};
+            if (dy_dx) {
+                const uint4* dp4 = reinterpret_cast<const uint4*>(dy_dx + (size_t)b * 64);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = __ldg(dp4 + i);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { gw[4 * i] = q[i].x; gw[4 * i + 1] = q[i].y; gw[4 * i + 2] = q[i].z; gw[4 * i + 3] = q[i].w; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { dw[4 * i] = r[i].x; dw[4 * i + 1] = r[i].y; dw[4 * i + 2] = r[i].z; dw[4 * i + 3] = r[i].w; }
+        }
+
+#pragma unroll 1
         for (uint32_t l = 0; l < L; ++l) {
             float gf[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) gf[c] = 0.0f;
-            if (in_range) {
+            if (prefetch) {
+                if constexpr (kRowPrefetch) {
+                    if (in_range) {
+                        // level l: features = 32-bit word l of the 16-word gradient row, derivatives = words 2l, 2l+1 of the 32-word row
+                        const uint32_t g32 = gw[l & 15u];
+                        const __half2 gh = *reinterpret_cast<const __half2*>(&g32);
+                        gf[0] = __low2float(gh); gf[1] = __high2float(gh);
+                        if (dy_dx) {
+                            const uint32_t d0 = dw[(2 * l) & 31u], d1 = dw[(2 * l + 1) & 31u];
+                            const __half2 dx = *reinterpret_cast<const __half2*>(&d0), dy = *reinterpret_cast<const __half2*>(&d1);
+                            gin[0] = __fmaf_rn(gf[0], __low2float(dx), gin[0]); gin[0] = __fmaf_rn(gf[1], __high2float(dx), gin[0]);
+                            gin[1] = __fmaf_rn(gf[0], __low2float(dy), gin[1]); gin[1] = __fmaf_rn(gf[1], __high2float(dy), gin[1]);
+                        }
+                    }
+                }
+            } else if (in_range) {
                 const T* gp = (layout == RN_LAYOUT_BLC) ? grad + (size_t)b * L * C + (size_t)l * C
                                                         : grad + ((size_t)l * B + b) * C;
                 const Row<T, C> g = load_row<T, C>(gp);
@@ -502,7 +571,13 @@ grid_backward_shared_cell_kernel(const T* __restrict__ grad, const float* __rest
                     }
                     if ((int)lane == src) {
 #pragma unroll
-                        for (uint32_t k = 0; k < 4; ++k) scatter_row<G, C>(gt + (size_t)corner_row<D>(m, cell.pg, k) * C, v[k]);
+                        for (uint32_t k = 0; k < 4; ++k) {
+                            const uint32_t row = corner_row<D>(m, cell.pg, k);
+                            if constexpr (HASH) {
+                                if (hash_accumulate(h_keys, h_vals, m.offset + row, v[k][0], v[k][1])) continue;
+                            }
+                            scatter_row<G, C>(gt + (size_t)row * C, v[k]);
+                        }
                     }
                 }
             } else if (valid) {
@@ -519,6 +594,18 @@ grid_backward_shared_cell_kernel(const T* __restrict__ grad, const float* __rest
         if (dy_dx && grad_inputs && in_range) {
 #pragma unroll
             for (int d = 0; d < D; ++d) grad_inputs[(size_t)b * D + d] = from_f<T>(gin[d]);
+        }
+    }
+    if constexpr (HASH) {   // one flush per CTA: every touched row once
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < kHashSlots; i += blockDim.x) {
+            const uint32_t key = h_keys[i];
+            if (key == kHashEmpty) continue;
+            const float2 a = h_vals[i];
+            float v[C];
+            v[0] = a.x;
+            if constexpr (C > 1) v[1] = a.y;
+            scatter_row<G, C>(grad_table + (size_t)key * C, v);
         }
     }
 }
@@ -636,7 +723,19 @@ template <typename T, typename G, int D, int C>
 int launch_backward(const BwdArgs& a) {
     const uint32_t threads = 256;
     const uint32_t grid = wave_grid(a.B, threads, 32);
-    if constexpr (D == 2) {   // the ambient / torso grids: lanes of a warp that share a cell are summed before the atomics
+// measured at 0.82 M clustered samples of a real training step (tools/train_timeline.py, WARM=70): 816 us before, 732 us with the row
+// prefetch alone, 603 us with prefetch + hash stage; uniform inputs (tests/test_gpu_kernel_rows.py): 0.65 ms without, 0.70 ms with the
+// hash stage (smaller persistent grid).  The training case is the clustered one.
+#ifndef RN_BWD2_HASH
+#define RN_BWD2_HASH 1
+#endif
+    if constexpr (RN_BWD2_HASH && D == 2 && C == 2 && sizeof(G) == 4) {
+        // the ambient / torso grids: warp stage + per-CTA hash stage; a persistent grid (4 CTAs per SM) so that a CTA sees a few thousand
+        // samples before it flushes
+        const uint32_t pgrid = std::min(grid, (uint32_t)RN_NUM_SMS * 4u);
+        grid_backward_shared_cell_kernel<T, G, C, true><<<pgrid, threads, 0, a.st>>>((const T*)a.grad, a.inputs, a.offsets, (G*)a.gt,
+            (const T*)a.dy_dx, (T*)a.gin, a.B, a.L, a.S, a.H, a.gridtype, a.ac, a.interp, a.layout);
+    } else if constexpr (D == 2) {   // lanes of a warp that share a cell are summed before the atomics
         grid_backward_shared_cell_kernel<T, G, C><<<grid, threads, 0, a.st>>>((const T*)a.grad, a.inputs, a.offsets, (G*)a.gt,
             (const T*)a.dy_dx, (T*)a.gin, a.B, a.L, a.S, a.H, a.gridtype, a.ac, a.interp, a.layout);
     } else {
