@@ -46,8 +46,8 @@ N_FRAMES_DISTINCT = 64  # distinct poses / audio windows cycled through
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200, help="frames per timed window (the window is repeated, see --repeats)")
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--repeats", type=int, default=0, help="timed windows of --steps frames (0 = at least 15, enough to cover ~1 s)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE configs[0], [1], [4] legs")
@@ -287,26 +287,24 @@ def run_ours(args):
             st.sync()
         return render, drain
 
-    if path == "fused":
-        # `value`: the per-frame input blocks (pose, pose6, eye, audio window) are resident on the device; rays are generated
-        # on the device from the pose, `lanes` frames are in flight on separate streams (FramePipeline inside FrameStreamer;
-        # the lip-smoothing chain is kept by running the conditioning kernels in frame order on their own stream); no
-        # host<->device copies in the timed region.
-        from radnerf_b200.stream import FrameStreamer, pack_inputs
-        packed = [pack_inputs(f["pose"], f["auds"], f["pose6"], f["eye"]) for f in frames]
-        packed_dev = [p.to(dev) for p in packed]
-        resident = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
-                                 deliver=False, depth=lanes, **kw)
-        render_resident, drain_resident = streamer_loop(resident, packed_dev)
+    # `value`: the per-frame input blocks (pose, pose6, eye, audio window) are resident on the device; rays are generated
+    # on the device from the pose, `lanes` frames are in flight on separate streams (FramePipeline inside FrameStreamer;
+    # the lip-smoothing chain is kept by running the conditioning kernels in frame order on their own stream); no
+    # host<->device copies in the timed region.
+    from radnerf_b200.stream import FrameStreamer, pack_inputs
+    packed = [pack_inputs(f["pose"], f["auds"], f["pose6"], f["eye"]) for f in frames]
+    packed_dev = [p.to(dev) for p in packed]
+    resident = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
+                             deliver=False, depth=lanes, **kw)
+    render_resident, drain_resident = streamer_loop(resident, packed_dev)
 
     # ---- host inputs for `e2e`: one pinned block per frame (pose, pose6, eye, audio window); the public streaming API
     #      (radnerf_b200.stream.FrameStreamer) copies it in, generates the rays on the device, renders, all-gathers the tiles
     #      and copies the image back to pinned host memory -- the device->host copy of frame i overlaps frame i+1 (depth 2)
-    if path == "fused":
-        streamer = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
-                                 deliver=(rank == 0), depth=max(2, lanes), **kw)
-        h2d_bytes, d2h_bytes = streamer.h2d_bytes, streamer.d2h_bytes
-        render_e2e, drain_e2e = streamer_loop(streamer, packed)
+    streamer = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
+                             deliver=(rank == 0), depth=max(2, lanes), **kw)
+    h2d_bytes, d2h_bytes = streamer.h2d_bytes, streamer.d2h_bytes
+    render_e2e, drain_e2e = streamer_loop(streamer, packed)
 
     def barrier():
         if world > 1:
@@ -374,23 +372,22 @@ def run_ours(args):
     ms_e2e = t_e2e["ms"]
     e2e_u8 = None
     latency = None
-    if path == "fused":
-        # the same end-to-end loop with the output stage on the device (uint8 frames, what the reference's video writer consumes)
-        streamer8 = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
-                                  deliver=(rank == 0), depth=max(2, lanes), output="uint8", **kw)
-        t_u8 = timed(*((lambda rd: (rd[0], K, W, rd[1]))(streamer_loop(streamer8, packed))))
-        e2e_u8 = {"value": K / (t_u8["ms"] / 1e3), "unit": UNIT, "h2d_bytes_per_step": streamer8.h2d_bytes,
-                  "d2h_bytes_per_step": streamer8.d2h_bytes, "repeats": t_u8["repeats"], "what": "as e2e, but frames are converted to uint8 on the device "
-                  "((pred * 255).astype(uint8), the reference's host-side expression) before the copy-out"}
-        # single-frame latency: ONE frame in flight, host block in -> image on the host, next frame only after that
-        one = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
-                            deliver=(rank == 0), depth=1, **kw)
+    # the same end-to-end loop with the output stage on the device (uint8 frames, what the reference's video writer consumes)
+    streamer8 = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
+                              deliver=(rank == 0), depth=max(2, lanes), output="uint8", **kw)
+    t_u8 = timed(*((lambda rd: (rd[0], K, W, rd[1]))(streamer_loop(streamer8, packed))))
+    e2e_u8 = {"value": K / (t_u8["ms"] / 1e3), "unit": UNIT, "h2d_bytes_per_step": streamer8.h2d_bytes,
+              "d2h_bytes_per_step": streamer8.d2h_bytes, "repeats": t_u8["repeats"], "what": "as e2e, but frames are converted to uint8 on the device "
+              "((pred * 255).astype(uint8), the reference's host-side expression) before the copy-out"}
+    # single-frame latency: ONE frame in flight, host block in -> image on the host, next frame only after that
+    one = FrameStreamer(model, hw, hw, intr, bg_local[0], frames[0]["auds"].shape, use_eye=True, sharder=sharder,
+                        deliver=(rank == 0), depth=1, **kw)
 
-        def render_one(i):
-            one.submit(packed[i % len(packed)])
-            one.collect()
-        t_lat = timed(render_one, K, W, None, repeats=15)
-        latency = t_lat["ms"] / K
+    def render_one(i):
+        one.submit(packed[i % len(packed)])
+        one.collect()
+    t_lat = timed(render_one, K, W, None, repeats=15)
+    latency = t_lat["ms"] / K
     fps, fps_e2e = K / (ms / 1e3), K / (ms_e2e / 1e3)
 
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "repeats": t_res["repeats"],
@@ -418,7 +415,7 @@ def run_ours(args):
 
     # ---- N > 1: the same job in FRAME-parallel mode (whole frames per GPU, no collective), reported next to the ray-sharded
     #      headline: ray sharding cuts latency, but a 512x512 frame cannot scale past its ~0.29 ms dependency chain
-    if world > 1 and path == "fused":
+    if world > 1:
         from radnerf_b200.stream import FrameStreamer as _FS
         full = _FS(model, hw, hw, intr, bg_t[0], frames[0]["auds"].shape, use_eye=True, deliver=True, depth=max(2, lanes), **kw)
         t_fp = timed(*((lambda rd: (rd[0], K, W, rd[1]))(streamer_loop(full, packed))))
@@ -428,7 +425,7 @@ def run_ours(args):
         model.enc_a = None
 
     # ---- the other BASELINE configurations, as extra keys (every rank takes part: the frames are ray-sharded like the headline)
-    if path == "fused" and not args.no_extra_configs:
+    if not args.no_extra_configs:
         try:
             line["configs"] = extra_configs(args, dev, world, rank, timed, streamer_loop)
         except Exception as e:  # noqa: BLE001

@@ -162,7 +162,7 @@ class FusedShared:
 # dependent instructions of a probe, not by the bitfield load, which hits L1 for the coherent rays of a frame.  Measured per launch at
 # 512x512 (tools/frame_timeline.py, profiles/r02_frame_timeline_512_occ_pack.txt): 6.2 / 9.2 / 8.6 / 8.2 / 7.4 us staged vs 4.1 / 8.2 / 7.7 /
 # 7.2 / 6.4 us from global memory; frames/s 3 318 vs 3 432.
-_NO_OCC_PACK = not bool(int(__import__("os").environ.get("RADNERF_OCC_PACK", "0")))
+_USE_OCC_PACK = bool(int(__import__("os").environ.get("RADNERF_OCC_PACK", "0")))
 
 
 class FusedState:
@@ -394,7 +394,7 @@ def head_desc(model, st, rays_o, rays_d, noises, dt_gamma, max_steps, T_thresh):
     hd.head_blob, hd.head_consts = st.head_blob.data_ptr(), st.head_consts.data_ptr()
     hd.capture_unroll = st.capture_unroll
     hd.occ_aabb = st.occupied_box(model).data_ptr()
-    if st.shared.occ_words and not _NO_OCC_PACK:
+    if st.shared.occ_words and _USE_OCC_PACK:
         hd.occ_pack, hd.occ_words = st.shared.occ_pack.data_ptr(), st.shared.occ_words
     return hd, (weights_sum, depth, image, nears, fars)
 
