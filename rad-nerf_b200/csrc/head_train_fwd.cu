@@ -78,6 +78,34 @@ static __device__ __noinline__ void epilogue_save(uint32_t tmem_row, uint32_t co
     }
 }
 
+// mma_stage (mlp_tile.cuh) that also SAVES the stage's freshly published A operand: the tile sits in shared memory in exactly the
+// interleaved layout of its slot in the tile record, so thread 0 hands it to the TMA engine as one bulk store (8-20 KB) right after
+// issuing the MMAs -- instead of every thread mirroring each of its 16-byte operand stores to global memory (58 per sample: the
+// forward ran at half the speed of the inference kernel because of them).  The source buffer is only rewritten by an epilogue that
+// follows a LATER stage's MMA, and thread 0 waits for the reads of all earlier bulk stores before it issues that later stage.
+static __device__ __noinline__ void mma_stage_save(uint32_t tmem_acc, uint32_t a0, uint32_t Ka0, uint32_t ka0, uint32_t b0, uint32_t K0,
+                                                   uint32_t a1, uint32_t b1, uint32_t K1, uint32_t a2, uint32_t b2, uint32_t N, uint64_t* mbar,
+                                                   uint32_t& phase, uint32_t bar_id, uint32_t t, uint8_t* save_dst, uint32_t save_src, uint32_t save_bytes) {
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    umma::group_sync(bar_id, 128);
+    if (t == 0) {
+        umma::fence_after_sync();
+        if (save_dst) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // earlier saves have left shared memory
+        umma::gemm_issue(tmem_acc, a0, b0, Ka0, K0, ka0, K0, N, false);
+        if (K1) umma::gemm_issue(tmem_acc, a1, b1, K1, K1, 0, K1, N, true);
+        if (a2) umma::gemm_issue(tmem_acc, a2, b2, 16, 16, 0, 16, N, true);
+        umma::commit(mbar);
+        if (save_dst) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(save_dst), "r"(save_src), "r"(save_bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    umma::mbar_wait(mbar, phase);
+    phase ^= 1u;
+    umma::fence_after_sync();
+}
+
 // fast_encode<D> (mlp_tile.cuh) + the saved copy; for D == 2 additionally d(features)/d(x) per level, dy_dx[l][d][c] fp16
 // (the reference's kernel_grid with calc_grad_inputs, gridencoder.cu:200-243; fp32 accumulation, one rounding)
 template <int D>
@@ -249,17 +277,17 @@ head_train_fwd_kernel(FwdParams p) {
         {
             float x[3] = {__fmul_rn(__fadd_rn(px, p.bound), p.inv2bound), __fmul_rn(__fadd_rn(py, p.bound), p.inv2bound),
                           __fmul_rn(__fadd_rn(pz, p.bound), p.inv2bound)};
-            encode_save<3>(x, table3, lv3, sA0, REC(T_A0), t, 32, nullptr);
+            encode_save<3>(x, table3, lv3, sA0, nullptr, t, 32, nullptr);
         }
-        // ---- ambient L1 -> H0 (saved as HA1)
+        // ---- ambient L1 -> H0 (A0 saved)
         if (!weights_ready) { umma::mbar_wait(&mbar_w, 0); weights_ready = true; }
-        mma_stage(tmem_acc, aA0, 32, 0, aW + B_WA1, 32, 0, 0, 0, aOnes, aB0, 64, mbar, phase, bar_id, t);
-        epilogue_save<2>(tmem_row, 0, true, sH0, REC(T_HA1), t, 64, 0);
-        // ---- ambient L2 -> H1 (saved as HA2)
-        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WA2, 64, 0, 0, 0, 0, 0, 64, mbar, phase, bar_id, t);
-        epilogue_save<2>(tmem_row, 0, true, sH1, REC(T_HA2), t, 64, 0);
-        // ---- ambient L3 -> tanh -> 2-D encode -> EW
-        mma_stage(tmem_acc, aH1, 64, 0, aW + B_WA3, 64, 0, 0, 0, 0, 0, 16, mbar, phase, bar_id, t);
+        mma_stage_save(tmem_acc, aA0, 32, 0, aW + B_WA1, 32, 0, 0, 0, aOnes, aB0, 64, mbar, phase, bar_id, t, REC(T_A0), aA0, 128 * 32 * 2);
+        epilogue_save<2>(tmem_row, 0, true, sH0, nullptr, t, 64, 0);
+        // ---- ambient L2 -> H1 (H0 saved as HA1)
+        mma_stage_save(tmem_acc, aH0, 64, 0, aW + B_WA2, 64, 0, 0, 0, 0, 0, 64, mbar, phase, bar_id, t, REC(T_HA1), aH0, 128 * 64 * 2);
+        epilogue_save<2>(tmem_row, 0, true, sH1, nullptr, t, 64, 0);
+        // ---- ambient L3 -> tanh -> 2-D encode -> EW (H1 saved as HA2)
+        mma_stage_save(tmem_acc, aH1, 64, 0, aW + B_WA3, 64, 0, 0, 0, 0, 0, 16, mbar, phase, bar_id, t, REC(T_HA2), aH1, 128 * 64 * 2);
         {
             uint32_t v[16];
             umma::tmem_ld16(tmem_row, v);
@@ -269,19 +297,19 @@ head_train_fwd_kernel(FwdParams p) {
             if (valid && p.ambient) *reinterpret_cast<float2*>(p.ambient + (size_t)s * 2) = make_float2(a0, a1);
             float x[2] = {__fmul_rn(__fadd_rn(a0, 1.0f), 0.5f), __fmul_rn(__fadd_rn(a1, 1.0f), 0.5f)};
             // rows past M still own 128 bytes of dy_dx2 (the buffer is sized for whole tiles)
-            encode_save<2>(x, table2, lv2, sEW, REC(T_EW), t, 32, p.dy_dx2 ? p.dy_dx2 + (size_t)s * 64 : nullptr);
+            encode_save<2>(x, table2, lv2, sEW, nullptr, t, 32, p.dy_dx2 ? p.dy_dx2 + (size_t)s * 64 : nullptr);
         }
-        // ---- sigma L1 -> H1 (saved as HS1)
-        mma_stage(tmem_acc, aA0, 32, 0, aW + B_WS1A, 32, aEW, aW + B_WS1B, 32, aOnes, aB1, 64, mbar, phase, bar_id, t);
-        epilogue_save<2>(tmem_row, 0, true, sH1, REC(T_HS1), t, 64, 0);
-        // ---- sigma L2 -> H0 (saved as HS2)
-        mma_stage(tmem_acc, aH1, 64, 0, aW + B_WS2, 64, 0, 0, 0, 0, 0, 64, mbar, phase, bar_id, t);
-        epilogue_save<2>(tmem_row, 0, true, sH0, REC(T_HS2), t, 64, 0);
-        // ---- sigma L3 -> geo_feat (columns 0..63), log-density (column 64)
-        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WS3, 64, 0, 0, 0, 0, 0, 80, mbar, phase, bar_id, t);
+        // ---- sigma L1 -> H1 (EW saved)
+        mma_stage_save(tmem_acc, aA0, 32, 0, aW + B_WS1A, 32, aEW, aW + B_WS1B, 32, aOnes, aB1, 64, mbar, phase, bar_id, t, REC(T_EW), aEW, 128 * 32 * 2);
+        epilogue_save<2>(tmem_row, 0, true, sH1, nullptr, t, 64, 0);
+        // ---- sigma L2 -> H0 (H1 saved as HS1)
+        mma_stage_save(tmem_acc, aH1, 64, 0, aW + B_WS2, 64, 0, 0, 0, 0, 0, 64, mbar, phase, bar_id, t, REC(T_HS1), aH1, 128 * 64 * 2);
+        epilogue_save<2>(tmem_row, 0, true, sH0, nullptr, t, 64, 0);
+        // ---- sigma L3 -> geo_feat (columns 0..63), log-density (column 64)  (H0 saved as HS2)
+        mma_stage_save(tmem_acc, aH0, 64, 0, aW + B_WS3, 64, 0, 0, 0, 0, 0, 80, mbar, phase, bar_id, t, REC(T_HS2), aH0, 128 * 64 * 2);
         float sigma;
         {
-            epilogue_save<2>(tmem_row, 0, false, sCIN, REC(T_CIN), t, 80, 16);
+            epilogue_save<2>(tmem_row, 0, false, sCIN, nullptr, t, 80, 16);
             uint32_t v[16];
             umma::tmem_ld16(tmem_row + 64, v);
             umma::tmem_ld_wait();
@@ -300,16 +328,14 @@ head_train_fwd_kernel(FwdParams p) {
             sh_eval<4, false>(dx, dy, dz, Y, nullptr, nullptr, nullptr);
             const uint4 w0 = make_uint4(pack2(Y[0], Y[1]), pack2(Y[2], Y[3]), pack2(Y[4], Y[5]), pack2(Y[6], Y[7]));
             const uint4 w1 = make_uint4(pack2(Y[8], Y[9]), pack2(Y[10], Y[11]), pack2(Y[12], Y[13]), pack2(Y[14], Y[15]));
-            const uint32_t o0 = umma::il_offset(t, 0, 80), o1 = umma::il_offset(t, 8, 80);
-            *reinterpret_cast<uint4*>(sCIN + o0) = w0;
-            *reinterpret_cast<uint4*>(sCIN + o1) = w1;
-            if (rec) { *reinterpret_cast<uint4*>(rec + T_CIN + o0) = w0; *reinterpret_cast<uint4*>(rec + T_CIN + o1) = w1; }
+            *reinterpret_cast<uint4*>(sCIN + umma::il_offset(t, 0, 80)) = w0;
+            *reinterpret_cast<uint4*>(sCIN + umma::il_offset(t, 8, 80)) = w1;
         }
-        // ---- colour L1 -> H0 (saved as HC1)
-        mma_stage(tmem_acc, aCIN, 80, 0, aW + B_WC1, 80, 0, 0, 0, aOnes, aB2, 64, mbar, phase, bar_id, t);
-        epilogue_save<2>(tmem_row, 0, true, sH0, REC(T_HC1), t, 64, 0);
-        // ---- colour L2 -> sigmoid
-        mma_stage(tmem_acc, aH0, 64, 0, aW + B_WC2, 64, 0, 0, 0, 0, 0, 16, mbar, phase, bar_id, t);
+        // ---- colour L1 -> H0 (CIN saved)
+        mma_stage_save(tmem_acc, aCIN, 80, 0, aW + B_WC1, 80, 0, 0, 0, aOnes, aB2, 64, mbar, phase, bar_id, t, REC(T_CIN), aCIN, 128 * 80 * 2);
+        epilogue_save<2>(tmem_row, 0, true, sH0, nullptr, t, 64, 0);
+        // ---- colour L2 -> sigmoid (H0 saved as HC1)
+        mma_stage_save(tmem_acc, aH0, 64, 0, aW + B_WC2, 64, 0, 0, 0, 0, 0, 16, mbar, phase, bar_id, t, REC(T_HC1), aH0, 128 * 64 * 2);
         {
             uint32_t v[16];
             umma::tmem_ld16(tmem_row, v);
@@ -329,6 +355,7 @@ head_train_fwd_kernel(FwdParams p) {
         umma::group_sync(bar_id, 128);
     }
 #undef REC
+    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // this group's tile saves are complete before its smem goes away
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 1) umma::tmem_dealloc(tmem_slot, 512);
