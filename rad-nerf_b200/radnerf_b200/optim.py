@@ -55,7 +55,16 @@ def _descriptor_table(rows, device):
         for k in ("param", "grad", "exp_avg", "exp_avg_sq", "step", "ema"):
             setattr(d, k, r.get(k) or 0)
         d.n, d.first_chunk, d.group = r["n"], f, r.get("group", 0)
-    blob = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(device)
+    host = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy())
+    if torch.cuda.is_current_stream_capturing():
+        # a step that is being captured re-points its table (fresh gradient tensors): the upload must be a capturable copy, i.e. from
+        # pinned memory that outlives the graph (kept alive on the returned tensor)
+        host = host.pin_memory()
+        blob = torch.empty_like(host, device=device)
+        blob.copy_(host, non_blocking=True)
+        blob._rn_host_source = host
+    else:
+        blob = host.to(device)
     return blob, total
 
 
