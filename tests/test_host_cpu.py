@@ -301,3 +301,87 @@ def test_config1_case(oracle):
     # per-ray outputs are addressed by ray id (raymarching.cu:622, 690-697): a different slot order leaves them where they are
     e = c1.compare(shuffled, res)
     assert all(v is True or v == 0.0 for v in e.values()), e
+
+
+def _dp_flat_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.join(ROOT, "rad-nerf_b200"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from radnerf_b200.train import GradSync
+    m = _toy_model()
+    sync = GradSync(m.parameters(), table_numel=1024, overlap=False)      # what GraphedTrainStep uses: no hook-driven reductions
+    got = []
+    for step in range(3):
+        for p in m.parameters():
+            if p.grad is not None:
+                p.grad.zero_()
+        sync.begin_step()
+        _toy_loss(m, 100 * step + rank).backward()
+        if step == 0:
+            sync.flatten()       # after the first backward: the small gradients become views of one buffer, exchanged in place
+            ptrs = {id(p): p.grad.data_ptr() for p in m.parameters() if p.grad is not None}
+        sync.finish()
+        got.append([None if p.grad is None else p.grad.clone() for p in m.parameters()])
+        assert all(p.grad.data_ptr() == ptrs[id(p)] for p in m.parameters() if p.grad is not None)   # backward accumulated INTO the views
+    flat_ok = sync.flat is not None and all(p.grad.untyped_storage().data_ptr() == sync.flat.untyped_storage().data_ptr() for p in sync.flat_params)
+    out[rank] = (got, sync.bytes_last, flat_ok, [p.numel() for p in sync.flat_params])
+    dist.destroy_process_group()
+
+
+def test_gradsync_flat_bucket_two_ranks_gloo():
+    """the in-place gradient exchange of the graphed data-parallel step: after flatten() the small parameters' .grad are views of ONE
+    flat buffer that is all-reduced where it lies, the table is reduced after backward (no hooks); every step yields the mean over ranks
+    of the per-rank gradients and parameters without a gradient stay without one"""
+    world = 2
+    out = mp.Manager().dict()
+    port = 29500 + (os.getpid() + 57) % 1000
+    mp.spawn(_dp_flat_worker, args=(world, port, out), nprocs=world, join=True)
+    for step in range(3):
+        want = None
+        for r in range(world):
+            m = _toy_model()
+            _toy_loss(m, 100 * step + r).backward()
+            g = [None if p.grad is None else p.grad / world for p in m.parameters()]
+            want = g if want is None else [a if b is None else a + b for a, b in zip(want, g)]
+        for r in range(world):
+            for a, b in zip(out[r][0][step], want):
+                assert (a is None) == (b is None)
+                if a is not None:
+                    assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
+    assert out[0][2] and out[1][2] and out[0][3] == [6, 3]
+    assert out[0][1] == (1024 + 6 + 3) * 4
+
+
+def test_graphed_step_capacity_has_headroom_and_hysteresis():
+    """GraphedTrainStep._capacity (host logic, no GPU): 20 % headroom rounded to the bucket, kept while the estimate stays within
+    [60 %, 100 %] of it, re-sized on overflow or a large shrink"""
+    from radnerf_b200.train import GraphedTrainStep
+    s = GraphedTrainStep.__new__(GraphedTrainStep)
+    s.bucket, s.capacity, s.mc_host = 1 << 16, None, 0
+    padded, cap = s._capacity(700000)
+    assert padded == 700000 + (128 - 700000 % 128) and cap == 13 * 65536 and cap >= 1.2 * 700000
+    s.capacity = cap
+    assert s._capacity(int(0.95 * cap))[1] == cap and s._capacity(int(0.61 * cap))[1] == cap      # drift inside the band: same graph
+    assert s._capacity(cap + 1)[1] > cap                                                          # overflow: grow
+    assert s._capacity(int(0.3 * cap))[1] < cap                                                   # large shrink: shrink
+
+
+def test_ops_frame_is_registered_by_the_oracle_only():
+    """the reference's op-by-op inference loop is test infrastructure: radnerf_b200.model has no such loop of its own and raises without
+    the registration that importing oracle.ops_frame (tests/conftest.py) performs"""
+    from radnerf_b200 import model as M
+    from oracle import ops_frame
+    assert M._OPS_FRAME is ops_frame.ops_frame
+    src = open(os.path.join(ROOT, "rad-nerf_b200", "radnerf_b200", "model.py")).read()
+    assert "march_rays(" not in src and "composite_rays(" not in src
+    saved = M._OPS_FRAME
+    try:
+        M.register_ops_frame(None)
+        from oracle.cpu_backend import CPUOps
+        import bench
+        m = bench.make_model("cpu", ops=CPUOps(), fp16=False)
+        z = torch.zeros(1, 4, 3)
+        with pytest.raises(RuntimeError, match="test infrastructure"):
+            m.render(z, z + 1, None, torch.zeros(1, 4, 2), torch.zeros(1, 6), path="ops")
+    finally:
+        M.register_ops_frame(saved)
