@@ -224,72 +224,63 @@ class NeRFNetwork(nn.Module):
         self.poses = None         # [n, 4, 4]
 
     # ------------------------------------------------------------------------------------- network pieces
+    # (the op-by-op network: autograd fallback of the training step, the torso branch, the parity yardstick of the fused kernels.
+    #  Every per-frame vector -- audio code, eye value, individual codes, encoded pose -- is broadcast over the batch with _rows.)
+    @staticmethod
+    def _rows(v, n):
+        """a per-frame vector [1, k] (or [k]) as n identical rows"""
+        return v.reshape(1, -1).expand(n, -1)
+
     def encode_audio(self, a):
-        """[8, dim, 16] window -> [1, 64] (network.py:170-185)"""
+        """[8, dim, 16] window -> [1, 64] (network.py:170-185); None passes through (no audio conditioning)"""
         if a is None:
             return None
-        if self.emb:
-            a = self.embedding(a).transpose(-1, -2).contiguous()
-        enc_a = self.audio_net(a)
-        if self.att > 0:
-            enc_a = self.audio_att_net(enc_a.unsqueeze(0))
-        return enc_a
+        feats = self.embedding(a).transpose(-1, -2).contiguous() if self.emb else a
+        code = self.audio_net(feats)
+        return self.audio_att_net(code.unsqueeze(0)) if self.att > 0 else code
 
     def _ambient_and_features(self, x, enc_a):
+        """(ambient coordinate [N,2] in [-1,1], spatial features, ambient-grid features) -- network.py:233-247"""
+        n = x.shape[0]
+        spatial = self.encoder(x, bound=self.bound)
         if enc_a is None:
-            ambient = torch.zeros_like(x[:, :self.ambient_dim])
-            enc_x = self.encoder(x, bound=self.bound)
-            enc_w = self.encoder_ambient(ambient, bound=1)
+            ambient = x.new_zeros(n, self.ambient_dim)
         else:
-            enc_a = enc_a.repeat(x.shape[0], 1)
-            enc_x = self.encoder(x, bound=self.bound)
-            ambient = torch.cat([enc_x, enc_a], dim=1)
-            ambient = self.ambient_net(ambient).float()
-            ambient = torch.tanh(ambient)  # audio-driven 2-D coordinate in [-1, 1]
-            enc_w = self.encoder_ambient(ambient, bound=1)
-        return ambient, enc_x, enc_w
+            ambient = torch.tanh(self.ambient_net(torch.cat([spatial, self._rows(enc_a, n)], 1)).float())
+        return ambient, spatial, self.encoder_ambient(ambient, bound=1)
 
-    def _sigma_head(self, enc_x, enc_w, e, n):
-        if e is not None:
-            h = torch.cat([enc_x, enc_w, e.repeat(n, 1)], dim=-1)
-        else:
-            h = torch.cat([enc_x, enc_w], dim=-1)
-        h = self.sigma_net(h)
-        return self.ops.trunc_exp(h[..., 0]), h[..., 1:]
+    def _sigma_head(self, spatial, ambient_feat, e, n):
+        """density MLP on [spatial | ambient | eye] -> (sigma [N], geo_feat [N,64]) -- network.py:249-262"""
+        cols = [spatial, ambient_feat] + ([self._rows(e, n)] if e is not None else [])
+        out = self.sigma_net(torch.cat(cols, -1))
+        return self.ops.trunc_exp(out[..., 0]), out[..., 1:]
 
     def forward(self, x, d, enc_a, c, e=None):
         """x [N,3] in [-bound,bound]; d [N,3]; enc_a [1,64]; c [ind_dim]; e [1,1] -> sigma [N], color [N,3], ambient [N,2]
         (network.py:222-283)"""
-        ambient, enc_x, enc_w = self._ambient_and_features(x, enc_a)
-        sigma, geo_feat = self._sigma_head(enc_x, enc_w, e, x.shape[0])
-        enc_d = self.encoder_dir(d)
-        if c is not None:
-            h = torch.cat([enc_d, geo_feat, c.repeat(x.shape[0], 1)], dim=-1)
-        else:
-            h = torch.cat([enc_d, geo_feat], dim=-1)
-        color = torch.sigmoid(self.color_net(h))
-        return sigma, color, ambient
+        n = x.shape[0]
+        ambient, spatial, ambient_feat = self._ambient_and_features(x, enc_a)
+        sigma, geo_feat = self._sigma_head(spatial, ambient_feat, e, n)
+        cols = [self.encoder_dir(d), geo_feat] + ([self._rows(c, n)] if c is not None else [])
+        return sigma, torch.sigmoid(self.color_net(torch.cat(cols, -1))), ambient
 
     def density(self, x, enc_a, e=None):
         """(network.py:286-325)"""
-        _, enc_x, enc_w = self._ambient_and_features(x, enc_a)
-        sigma, geo_feat = self._sigma_head(enc_x, enc_w, e, x.shape[0])
+        _, spatial, ambient_feat = self._ambient_and_features(x, enc_a)
+        sigma, geo_feat = self._sigma_head(spatial, ambient_feat, e, x.shape[0])
         return {'sigma': sigma, 'geo_feat': geo_feat}
 
     def forward_torso(self, x, poses, enc_a, c=None):
-        """x [N,2] in [-1,1]; poses [1,6] -> alpha [N,1], color [N,3], dx [N,2] (network.py:188-219)"""
-        x = x * self.opt.torso_shrink
-        enc_pose = self.pose_encoder(poses)
-        enc_x = self.torso_deform_encoder(x)
-        if c is not None:
-            h = torch.cat([enc_x, enc_pose.repeat(x.shape[0], 1), c.repeat(x.shape[0], 1)], dim=-1)
-        else:
-            h = torch.cat([enc_x, enc_pose.repeat(x.shape[0], 1)], dim=-1)
-        dx = self.torso_deform_net(h)
-        x = (x + dx).clamp(-1, 1)
-        x = self.torso_encoder(x, bound=1)
-        h = self.torso_net(torch.cat([x, h], dim=-1))
-        return torch.sigmoid(h[..., :1]), torch.sigmoid(h[..., 1:]), dx
+        """x [N,2] in [-1,1]; poses [1,6] -> alpha [N,1], color [N,3], dx [N,2] (network.py:188-219): a pose-conditioned deformation of
+        the pixel coordinate, then the 2-D torso grid + MLP at the deformed position"""
+        n = x.shape[0]
+        pix = x * self.opt.torso_shrink
+        cond = [self.torso_deform_encoder(pix), self._rows(self.pose_encoder(poses), n)] + ([self._rows(c, n)] if c is not None else [])
+        cond = torch.cat(cond, -1)
+        offset = self.torso_deform_net(cond)
+        feat = self.torso_encoder((pix + offset).clamp(-1, 1), bound=1)
+        out = torch.sigmoid(self.torso_net(torch.cat([feat, cond], -1)))
+        return out[..., :1], out[..., 1:], offset
 
     def get_params(self, lr, lr_net, wd=0):
         """optimizer groups (network.py:329-361)"""
@@ -327,17 +318,18 @@ class NeRFNetwork(nn.Module):
         self.local_step = 0
 
     def _frame_conditioning(self, auds, index):
-        """per-frame constants: smoothed audio code and the individual code (renderer.py:187-204)"""
-        enc_a = self.encode_audio(auds)
-        if enc_a is not None and self.smooth_lips:
-            if self.enc_a is not None:
-                _lambda = 0.35
-                enc_a = _lambda * self.enc_a + (1 - _lambda) * enc_a
-            self.enc_a = enc_a
-        ind_code = None
+        """per-frame constants: the audio code -- exponentially smoothed over frames when lip smoothing is on (0.35 of the previous
+        frame's code) -- and the individual code of the frame (renderer.py:187-204)"""
+        code = self.encode_audio(auds)
+        if code is not None and self.smooth_lips:
+            previous = self.enc_a
+            if previous is not None:
+                code = 0.35 * previous + (1 - 0.35) * code
+            self.enc_a = code
+        individual = None
         if self.individual_dim > 0:
-            ind_code = self.individual_codes[index] if self.training else self.individual_codes[0]
-        return enc_a, ind_code
+            individual = self.individual_codes[index if self.training else 0]
+        return code, individual
 
     def run_cuda(self, rays_o, rays_d, auds, bg_coords, poses, eye=None, index=0, dt_gamma=0, bg_color=None, perturb=False,
                  force_all_rays=False, max_steps=1024, T_thresh=1e-4, **kwargs):
