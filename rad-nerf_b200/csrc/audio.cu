@@ -373,11 +373,13 @@ struct ProgramBuilder {
 void set_audio_prof(void* p) { cudaMemcpyToSymbol(g_audio_prof_dev, &p, sizeof(p)); }
 
 int launch_audio_frame(const AudioParams& p, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};           // the opt-in is a per-device function attribute: remembered per device, not per process
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
         RN_REQUIRE(cudaFuncSetAttribute(audio_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AUDIO_SMEM_BYTES) == cudaSuccess,
                    "shared memory opt-in failed");
-        attr_set = true;
+        if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
     }
     ProgramBuilder b;
     const uint32_t F = p.F, Cin = p.Cin;

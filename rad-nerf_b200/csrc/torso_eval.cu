@@ -172,11 +172,13 @@ torso_eval_kernel(TorsoEvalParams p) {
 }  // namespace
 
 int launch_torso_eval(const TorsoEvalParams& p, uint32_t max_tiles, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};         // per device: the shared-memory opt-in is an attribute of the function ON a device
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    if (dev_id < 0 || dev_id >= 64 || !configured[dev_id]) {
         cudaError_t e = cudaFuncSetAttribute(torso_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TORSO_SMEM);
         if (e != cudaSuccess) { set_error("torso_eval: cannot reserve %u bytes of shared memory: %s", TORSO_SMEM, cudaGetErrorString(e)); return (int)e; }
-        configured = true;
+        if (dev_id >= 0 && dev_id < 64) configured[dev_id] = true;
     }
     uint32_t grid = (max_tiles + EVAL_GROUPS - 1) / EVAL_GROUPS;
     if (grid > RN_NUM_SMS) grid = RN_NUM_SMS;
