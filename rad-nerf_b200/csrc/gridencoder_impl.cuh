@@ -19,7 +19,9 @@
 // (product rounded to half, then a half add; gridencoder.cu:163,186) so forward results are bit-identical.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace rn {
 namespace grid {
@@ -190,15 +192,63 @@ __device__ __forceinline__ float corner_weight(const Cell<D>& c, uint32_t corner
 // ======================================================================================================
 // forward
 // ======================================================================================================
-template <typename T, int D, int C, bool VEC_OUT>
-__global__ void __launch_bounds__(256)
+// STAGE: the north_star's "coarse levels in shared memory by TMA".  A persistent CTA copies the leading DENSE levels of the table
+// (index < size without hashing or wrapping, so the level is one contiguous run of rows) into dynamic shared memory with one bulk copy
+// per level, as many levels as `stage_bytes` holds, and gathers those levels with shared-memory loads; the other levels keep the
+// read-only global path.  Same cells, same weights, same rounding: bit-identical outputs (tests/test_gpu_round2.py).
+template <typename T, int C>
+__device__ __forceinline__ Row<T, C> load_row_staged(const T* p) {
+    Row<T, C> r;
+    constexpr int BYTES = C * sizeof(T);
+    if constexpr (BYTES == 2) *reinterpret_cast<unsigned short*>(r.v) = *reinterpret_cast<const unsigned short*>(p);
+    else if constexpr (BYTES == 4) *reinterpret_cast<unsigned int*>(r.v) = *reinterpret_cast<const unsigned int*>(p);
+    else if constexpr (BYTES == 8) *reinterpret_cast<uint2*>(r.v) = *reinterpret_cast<const uint2*>(p);
+    else if constexpr (BYTES == 16) *reinterpret_cast<uint4*>(r.v) = *reinterpret_cast<const uint4*>(p);
+    else {
+        reinterpret_cast<uint4*>(r.v)[0] = reinterpret_cast<const uint4*>(p)[0];
+        reinterpret_cast<uint4*>(r.v)[1] = reinterpret_cast<const uint4*>(p)[1];
+    }
+    return r;
+}
+
+constexpr uint32_t NOT_STAGED = 0xffffffffu;
+
+template <typename T, int D, int C, bool VEC_OUT, bool STAGE = false>
+__global__ void __launch_bounds__(STAGE ? 512 : 256)
 grid_forward_kernel(const float* __restrict__ inputs, const T* __restrict__ table, const int32_t* __restrict__ offsets,
                     T* __restrict__ outputs, T* __restrict__ dy_dx, uint32_t B, uint32_t L, float S, uint32_t H,
-                    uint32_t gridtype, uint32_t align_corners, uint32_t interp, uint32_t layout) {
+                    uint32_t gridtype, uint32_t align_corners, uint32_t interp, uint32_t layout, uint32_t stage_bytes = 0) {
     __shared__ LevelMeta meta[MAX_LEVELS];
+    __shared__ uint32_t staged_at[STAGE ? MAX_LEVELS : 1];   // byte offset of a staged level in the shared copy, or NOT_STAGED
+    __shared__ alignas(8) uint64_t stage_bar;
+    extern __shared__ __align__(128) unsigned char staged_rows[];
     for (uint32_t l = threadIdx.x; l < L; l += blockDim.x)
         make_level_meta(meta[l], l, offsets, S, H, D, gridtype, align_corners != 0);
     __syncthreads();
+    if constexpr (STAGE) {
+        if (threadIdx.x == 0) {
+            umma::mbar_init(&stage_bar, 1);
+            umma::fence_mbar_init();
+            uint32_t used = 0;
+            for (uint32_t l = 0; l < L; ++l) {
+                const uint32_t bytes = meta[l].size * (uint32_t)(C * sizeof(T));   // sizes are multiples of 8 rows: 16-byte granular
+                const bool fits = meta[l].mode == 0 && (bytes & 15u) == 0 && used + bytes <= stage_bytes;
+                staged_at[l] = fits ? used : NOT_STAGED;
+                if (fits) used += bytes;
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(&stage_bar)), "r"(used) : "memory");
+            for (uint32_t l = 0; l < L; ++l) {
+                if (staged_at[l] == NOT_STAGED) continue;
+                const uint32_t bytes = meta[l].size * (uint32_t)(C * sizeof(T));
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 umma::smem_u32(staged_rows + staged_at[l])),
+                             "l"(table + (size_t)meta[l].offset * C), "r"(bytes), "r"(umma::smem_u32(&stage_bar))
+                             : "memory");
+            }
+        }
+        __syncthreads();
+        umma::mbar_wait(&stage_bar, 0);
+    }
 
     for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         float x[D];
@@ -238,9 +288,18 @@ grid_forward_kernel(const float* __restrict__ inputs, const T* __restrict__ tabl
                 const Cell<D> cell = locate<D>(x, m, align_corners != 0, interp);
 
                 Row<T, C> rows[1 << D];
+                bool from_shared = false;
+                if constexpr (STAGE) from_shared = staged_at[l] != NOT_STAGED;     // uniform over the CTA (every thread is on level l)
+                if (from_shared) {
+                    const T* rows_l = reinterpret_cast<const T*>(staged_rows + staged_at[l]);
 #pragma unroll
-                for (uint32_t k = 0; k < (1u << D); ++k)
-                    rows[k] = load_row<T, C>(tbl + (size_t)corner_row<D>(m, cell.pg, k) * C);
+                    for (uint32_t k = 0; k < (1u << D); ++k)
+                        rows[k] = load_row_staged<T, C>(rows_l + (size_t)corner_row<D>(m, cell.pg, k) * C);
+                } else {
+#pragma unroll
+                    for (uint32_t k = 0; k < (1u << D); ++k)
+                        rows[k] = load_row<T, C>(tbl + (size_t)corner_row<D>(m, cell.pg, k) * C);
+                }
 #pragma unroll
                 for (uint32_t k = 0; k < (1u << D); ++k) {
                     const float w = corner_weight<D>(cell, k);
@@ -712,11 +771,37 @@ template <int D> int forward_d(const FwdArgs& a);
 template <int D> int backward_d(const BwdArgs& a);
 template <int D> int tv_d(const TvArgs& a);
 
+// shared memory per CTA for the staged forward, from the environment on every call (a getenv is nanoseconds next to a launch; tests
+// and tools switch it between calls); capped at what one CTA can opt into
+inline uint32_t forward_stage_bytes() {
+    const char* v = std::getenv("RADNERF_GRID_STAGE_KB");
+    if (!v || !*v) return 0;
+    long kb = std::strtol(v, nullptr, 10);
+    if (kb <= 0) return 0;
+    if (kb > 220) kb = 220;
+    return (uint32_t)kb * 1024u;
+}
+
 template <typename T, int D, int C>
 int launch_forward(const FwdArgs& a) {
     const uint32_t threads = 256;
     const uint32_t grid = wave_grid(a.B, threads, 32);
     const bool vec = a.layout == RN_LAYOUT_BLC && ((uintptr_t)a.out % 16 == 0) && ((a.L * C * sizeof(T)) % 16 == 0);
+    if constexpr (D <= 3 && C == 2) {
+        // coarse levels staged in shared memory (see STAGE above).  Opt-in: RADNERF_GRID_STAGE_KB=<KiB of shared memory per CTA>;
+        // measured against the plain kernel in profiles/r02_grid_forward_staged.json (DESIGN.md section 4 says which way it went)
+        const uint32_t stage_bytes = forward_stage_bytes();
+        if (stage_bytes && vec && ((uintptr_t)a.emb % 16 == 0) && a.B >= 4u * RN_NUM_SMS * 512u) {
+            auto kernel = grid_forward_kernel<T, D, C, true, true>;
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+            if (e != cudaSuccess) { set_error("grid_forward (staged): cannot reserve %u bytes of shared memory: %s", stage_bytes, cudaGetErrorString(e)); return (int)e; }
+            uint32_t per_sm = (227u * 1024u) / (stage_bytes + 5u * 1024u);      // + static shared memory and the per-CTA reservation
+            per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);                 // 64 registers x 512 threads: two CTAs per SM at most
+            kernel<<<wave_grid(a.B, 512, per_sm), 512, stage_bytes, a.st>>>(a.inputs, (const T*)a.emb, a.offsets, (T*)a.out, (T*)a.dy_dx, a.B,
+                                                                          a.L, a.S, a.H, a.gridtype, a.ac, a.interp, a.layout, stage_bytes);
+            return finish_launch("rn_grid_encode_forward (staged)");
+        }
+    }
     if (vec)
         grid_forward_kernel<T, D, C, true><<<grid, threads, 0, a.st>>>(a.inputs, (const T*)a.emb, a.offsets, (T*)a.out,
             (T*)a.dy_dx, a.B, a.L, a.S, a.H, a.gridtype, a.ac, a.interp, a.layout);

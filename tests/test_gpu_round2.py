@@ -235,3 +235,34 @@ def test_gather_to_root_protocol_with_two_ranks_emulated_on_one_gpu():
         else:
             assert torch.equal(staged32[i], want), i
     assert int(ctrl[0][0]) == (n_frames // n_slots) * ctas and int(ctrl[1][1]) == n_frames // n_slots       # arrivals at the root, frames consumed
+
+
+@pytest.mark.parametrize("D,dtype,kb", [(3, torch.float16, 24), (3, torch.float16, 100), (3, torch.float32, 160), (2, torch.float16, 64),
+                                        (2, torch.float32, 200)])
+def test_grid_forward_with_coarse_levels_staged_in_shared_memory_is_bit_identical(D, dtype, kb, monkeypatch):
+    """RADNERF_GRID_STAGE_KB: the persistent forward that bulk-copies the leading dense levels into shared memory
+    (gridencoder_impl.cuh, STAGE) must return exactly the words of the plain kernel -- outputs and dy_dx, in-range, out-of-range
+    and ragged-tail rows included"""
+    from gridencoder import GridEncoder
+    torch.manual_seed(D * 7 + kb)
+    enc = GridEncoder(input_dim=D, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=16, desired_resolution=2048).cuda()
+    with torch.no_grad():
+        enc.embeddings.uniform_(-1, 1)
+    B = 4 * 148 * 512 + 1237
+    x = (torch.rand(B, D, device="cuda") * 2.2 - 1.1)          # ~9 % of the rows per axis fall outside [-1, 1]
+
+    def run():
+        xi = x.clone().requires_grad_(True)                     # dy_dx is produced when the input needs a gradient
+        with torch.autocast("cuda", dtype=torch.float16, enabled=dtype == torch.float16):
+            out = enc(xi, bound=1)
+        g, = torch.autograd.grad(out.float().square().sum(), xi)
+        return out.detach().clone(), g.detach().clone()
+
+    monkeypatch.delenv("RADNERF_GRID_STAGE_KB", raising=False)
+    plain, plain_g = run()
+    monkeypatch.setenv("RADNERF_GRID_STAGE_KB", str(kb))
+    staged, staged_g = run()
+    assert plain.dtype == dtype
+    assert torch.equal(plain.view(torch.int16 if dtype == torch.float16 else torch.int32),
+                       staged.view(torch.int16 if dtype == torch.float16 else torch.int32))
+    assert torch.equal(plain_g, staged_g)
