@@ -114,6 +114,8 @@ __device__ __forceinline__ void accum2(float2& acc, float w, uint32_t g) {
 // LB = levels per batch: all gathers of a batch are issued before the first interpolation, so a point costs 16 / LB dependent memory
 // round trips.  Measured (round 2): LB = 8 for the 2-D grids changes nothing (tile 31 605 -> 31 106 cycles, registers 107 -> 126): the
 // encode phases are not waiting on gather round trips but on their own dependent instruction chains with 4 warps per scheduler.
+// Also measured and not kept: a bilinear fast path for the 3-D levels whose z stride is 0 (levels 9-15: both z-corners are one row, so
+// 2 loads + 8 FMAs instead of 4 + 16; taken per 4-level batch, registers unchanged): head_eval 52.3 -> 53.2 us per launch, i.e. nothing.
 template <int D, int LB = 4>
 static __device__ __noinline__ void fast_encode(const float (&x)[D], const uint2* __restrict__ table64, const FastLevel* __restrict__ lv,
                                                 uint8_t* dst, uint32_t row, uint32_t Kdst, uint32_t dcol0) {
