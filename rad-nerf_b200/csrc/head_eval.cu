@@ -38,21 +38,23 @@ constexpr uint32_t B_WC1 = B_WS3 + 80 * 64 * 2;
 constexpr uint32_t B_WC2 = B_WC1 + 64 * 80 * 2;
 static_assert(B_WC2 + 16 * 64 * 2 == HEAD_BLOB_BYTES, "blob layout");
 
-// per-group activation buffers (40 KB).  Aliasing is safe because every stage waits for its MMA before the next write:
+// per-group activation buffers (32 KB).  Aliasing is safe because every stage waits for its MMA (the operand has been read) before
+// the next write, which also lets a hidden layer's output overwrite its own input:
 //   A0  [128x32]  enc_x           written by the 3-D encode, read by ambient-L1 and sigma-L1
-//   H1  [128x64]  hidden          ambient-L2 out, sigma-L1 out, colour-L1 ... (see the stage list in the kernel)
-//   CIN [128x80]  = A0 + H1 region, colour-L1 input [sh | geo_feat], written after sigma-L2/L1 retired A0 and H1
-//   H0  [128x64]  hidden; its first 8 KB double as EW [128x32] (enc_w) between ambient-L3 and sigma-L1
+//   H   [128x64]  hidden          every 64-wide layer output, written IN PLACE over the layer's input
+//   CIN [128x80]  = A0 + most of H, colour-L1 input [sh | geo_feat], written after sigma-L1 / L3 retired A0 and H
+//   EW  [128x32]  enc_w           written by the 2-D encode, read by sigma-L1
+// (round 2, late: H0/H1 ping-pong dropped, 40 -> 32 KB per group, so that FIVE groups = 20 warps fit beside the 52 KB of weights)
 constexpr uint32_t G_A0 = 0;
-constexpr uint32_t G_H1 = G_A0 + 128 * 32 * 2;
+constexpr uint32_t G_H = G_A0 + 128 * 32 * 2;
 constexpr uint32_t G_CIN = 0;
-constexpr uint32_t G_H0 = G_H1 + 128 * 64 * 2;
-constexpr uint32_t G_EW = G_H0;
-constexpr uint32_t GROUP_BYTES = G_H0 + 128 * 64 * 2;
-static_assert(G_H0 >= 128 * 80 * 2, "CIN must fit in A0 + H1");
-constexpr int HEAD_GROUPS = 4;
+constexpr uint32_t G_EW = G_H + 128 * 64 * 2;
+constexpr uint32_t GROUP_BYTES = G_EW + 128 * 32 * 2;
+static_assert(G_EW >= 128 * 80 * 2, "CIN must fit in A0 + H");
+constexpr int HEAD_GROUPS = 5;
 constexpr uint32_t HEAD_SMEM = HEAD_BLOB_BYTES + HEAD_GROUPS * GROUP_BYTES;
-constexpr uint32_t TMEM_COLS_PER_GROUP = 128;
+constexpr uint32_t TMEM_COLS_PER_GROUP = 96;         // widest accumulator is 80 columns (sigma-L3); 5 x 96 = 480 of the 512 columns
+static_assert(HEAD_GROUPS * TMEM_COLS_PER_GROUP <= 512, "TMEM columns");
 // (a register cap through a larger launch bound -- 80 registers, so that the small kernels of other frame lanes fit next to a resident
 // CTA -- was measured in round 2: the spills cost more than the co-residency gives, 56.7 vs 52.6 us per launch, 3 200 vs 3 300 frames/s)
 #define HEAD_LAUNCH_BOUND (HEAD_GROUPS * 128)
@@ -76,7 +78,11 @@ head_eval_kernel(HeadEvalParams p, const FrameCur* cur) {
     if (ctl->done) return;
     const uint32_t n_samples = ctl->n_samples;
     const uint32_t n_tiles = (n_samples + EVAL_TILE - 1) / EVAL_TILE;
-    if (blockIdx.x * HEAD_GROUPS >= n_tiles) return;
+    // groups in use: all five when the launch is more than one round of four (sustained throughput: 20 warps hide the gather / MMA
+    // round trips better, +5-8 % frames/s on one GPU); a launch that fits in one round of four keeps four, because a tile runs faster
+    // with fewer co-resident groups and such launches (a rank's share of a ray-sharded frame, the last march iterations) are pure latency
+    const uint32_t groups = n_tiles > gridDim.x * 4u ? (uint32_t)HEAD_GROUPS : 4u;
+    if (blockIdx.x * groups >= n_tiles) return;
 
     const uint32_t tid = threadIdx.x, g = tid >> 7, t = tid & 127, warp = tid >> 5;
     uint8_t* s_blob = smem;
@@ -129,8 +135,8 @@ head_eval_kernel(HeadEvalParams p, const FrameCur* cur) {
     const uint32_t bar_id = 1 + g;
     uint8_t* sA0 = s_grp + G_A0;
     uint8_t* sEW = s_grp + G_EW;
-    uint8_t* sH0 = s_grp + G_H0;
-    uint8_t* sH1 = s_grp + G_H1;
+    uint8_t* sH0 = s_grp + G_H;      // one hidden buffer: the two names only keep the stage list below readable
+    uint8_t* sH1 = s_grp + G_H;
     uint8_t* sCIN = s_grp + G_CIN;
     const uint32_t aA0 = umma::smem_u32(sA0), aEW = umma::smem_u32(sEW), aH0 = umma::smem_u32(sH0), aH1 = umma::smem_u32(sH1),
                    aCIN = umma::smem_u32(sCIN);
@@ -142,7 +148,7 @@ head_eval_kernel(HeadEvalParams p, const FrameCur* cur) {
     long long c_enc3 = 0, c_enc2 = 0, c_mma = 0, c_epi = 0, c_tile = 0, c_last = 0;
     const bool prof = PROF && p.prof != nullptr && t == 0;
 #define RN_TICK(acc) if constexpr (PROF) { if (prof) { const long long now = clock64(); acc += now - c_last; c_last = now; } }
-    for (uint32_t tile = blockIdx.x * HEAD_GROUPS + g; tile < n_tiles; tile += gridDim.x * HEAD_GROUPS) {
+    for (uint32_t tile = g < groups ? blockIdx.x * groups + g : n_tiles; tile < n_tiles; tile += gridDim.x * groups) {
         if constexpr (PROF) { if (prof) c_last = clock64(); }
         const long long c_start = c_last;
         const uint32_t s = tile * EVAL_TILE + t;
@@ -260,7 +266,7 @@ int launch_head_eval(const HeadEvalParams& p, const FrameCur* cur, uint32_t max_
     cudaError_t e = p.prof ? cudaFuncSetAttribute(head_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM)
                            : cudaFuncSetAttribute(head_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM);
     if (e != cudaSuccess) { set_error("head_eval: cannot reserve %u bytes of shared memory: %s", HEAD_SMEM, cudaGetErrorString(e)); return (int)e; }
-    uint32_t grid = (max_tiles + HEAD_GROUPS - 1) / HEAD_GROUPS;
+    uint32_t grid = (max_tiles + 3) / 4;      // sized for four groups per CTA; the kernel switches to five when that is more than one round
     if (grid > RN_NUM_SMS) grid = RN_NUM_SMS;
     if (grid == 0) grid = 1;
     if (p.prof) head_eval_kernel<true><<<grid, HEAD_GROUPS * 128, HEAD_SMEM, st>>>(p, cur);

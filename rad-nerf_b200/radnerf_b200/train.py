@@ -250,6 +250,7 @@ class GraphedTrainStep:
         self.mc_host = 0           # last mean_count known to the HOST (decides the capacity bucket)
         self.mc_pending = None     # (pinned int32, event): an asynchronous read-back of a device-side mean_count
         self.capacity = None       # sample slots of the captured step's buffers
+        self.max_samples = None    # rays x max_steps of the current batch shape: the marcher's hard bound (top rung of _capacity)
         self._params = [p for g in optimizer.param_groups for p in g["params"]]
 
     def _eager(self, batch):
@@ -274,6 +275,15 @@ class GraphedTrainStep:
         cap = self.capacity
         if cap is None or padded > cap or padded < 0.6 * cap:
             cap = (int(padded * 1.2) + self.bucket - 1) // self.bucket * self.bucket
+            # TOP RUNG: the marcher cannot emit more than rays x max_steps samples.  A capacity that comes within 25 % of that bound is
+            # raised to the bound itself: the estimate keeps growing for the first occupancy updates of a run, and one more re-capture
+            # (up to ~170 ms on a slow host, seen inside a timed window of the bench) costs more than the padding, which the kernels
+            # skip (m_valid) -- from here on the step is never captured again for growth
+            top = getattr(self, "max_samples", None)
+            if top:
+                top = (int(top) + 128 + self.bucket - 1) // self.bucket * self.bucket
+                if cap >= 0.75 * top:
+                    cap = top
         return padded, cap
 
     def _set_budget(self, padded):
@@ -370,6 +380,7 @@ class GraphedTrainStep:
             self.warm = m.mean_count > 0                   # one eager step in the steady regime: lazy initialisations, grads exist
             return self._eager(batch)
         self._follow_mean_count()
+        self.max_samples = int(torch.as_tensor(batch["rays_o"]).numel() // 3) * int(m.opt.max_steps)
         padded, capacity = self._capacity()
         key = (capacity, shapes, self.phase)
         if key != self.key:

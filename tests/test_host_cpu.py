@@ -364,6 +364,15 @@ def test_graphed_step_capacity_has_headroom_and_hysteresis():
     assert s._capacity(int(0.95 * cap))[1] == cap and s._capacity(int(0.61 * cap))[1] == cap      # drift inside the band: same graph
     assert s._capacity(cap + 1)[1] > cap                                                          # overflow: grow
     assert s._capacity(int(0.3 * cap))[1] < cap                                                   # large shrink: shrink
+    # top rung: with the marcher's bound known, an estimate whose capacity comes within 25 % of rays x max_steps gets the bound itself,
+    # and nothing the estimate does afterwards (it cannot exceed the bound) asks for another capture
+    s.capacity, s.max_samples = None, 65536 * 16
+    top = ((65536 * 16 + 128 + s.bucket - 1) // s.bucket) * s.bucket
+    assert s._capacity(200000)[1] < 0.75 * top                                                    # early run: a small rung
+    assert s._capacity(690000)[1] == top
+    s.capacity = top
+    for mc in (700000, 910000, 65536 * 16, int(0.61 * top)):
+        assert s._capacity(mc)[1] == top
 
 
 def test_ops_frame_is_registered_by_the_oracle_only():
