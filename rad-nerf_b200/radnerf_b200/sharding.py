@@ -98,6 +98,9 @@ class FrameSharder:
                 k, self.parity = self.parity, (self.parity + 1) % len(bufs)
             else:
                 k = slot % len(bufs)
+            # buffer k may still be read on another rank (its staging copy of the previous frame that went through this buffer is
+            # ordered on ITS stream, not on ours): nobody stores into it before every rank has reached this point of its stream
+            hdls[k].barrier(channel=1)
             abi.check(abi.lib().rn_scatter_rows_to_peers(abi.ptr(local), abi.ptr(ids32), local.shape[0], self.W, hdls[k].buffer_ptrs_dev,
                                                          self.world, abi.cur_stream()))
             hdls[k].barrier(channel=0)   # every rank's rows have landed in every rank's buffer k
